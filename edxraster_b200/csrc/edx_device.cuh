@@ -1,0 +1,247 @@
+// edx_device.cuh — device-side types and arithmetic of the raster hot path (sm_100a).
+//
+// Every expression that feeds coverage, the depth test or the depth value is written with explicit
+// round-to-nearest intrinsics (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn never contract into FMA) and
+// wrapping unsigned integer arithmetic, in the operation order of the reference
+// (/root/reference/EDXRaster/Core/*.h, cited per function) so results are bit-identical to its SSE path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace edx {
+
+// ---------------------------------------------------------------------------------------------
+// Layout constants
+// ---------------------------------------------------------------------------------------------
+constexpr int BIN_LOG2 = 6;              // a CTA owns a 64x64-pixel bin ...
+constexpr int BIN = 1 << BIN_LOG2;
+constexpr int TILE_LOG2 = 4;             // ... one warp per 16x16 tile ...
+constexpr int TILE_PX = 1 << TILE_LOG2;
+constexpr int BLOCK_PX = 8;              // ... tested as four 8x8 blocks, then pixels
+constexpr int TILES_PER_BIN = (BIN / TILE_PX) * (BIN / TILE_PX);   // 16
+constexpr int KEYS_PER_BIN = BIN * BIN;                            // 4096
+constexpr int TILE_THREADS = TILES_PER_BIN * 32;                   // 512
+constexpr int SURV_CAP = 1024;           // per-bin survivor list held in shared memory
+
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+enum Shader { SH_DEPTH_ONLY = 0, SH_BLINN_PHONG = 1, SH_LAMBERT = 2, SH_LAMBERT_ALBEDO = 3 };
+
+// Post-setup triangle routed to the tile path (48 bytes, three 16-byte loads).
+struct __align__(16) BigRec {
+    int v0x, v0y, v1x, v1y;
+    int v2x, v2y; float z0, z1;
+    float z2, invDet; uint32_t prim; uint32_t pad;
+};
+
+// What the resolve pass needs to shade a pixel owned by a fan triangle of a clipped polygon (96 bytes).
+struct __align__(16) ClipRec {
+    int v0x, v0y, v1x, v1y;
+    int v2x, v2y; float invDet; uint32_t src;      // src: 2 bits per vertex, 0..2 = original vertex, 3 = blended
+    float invW0, invW1, invW2; uint32_t valid;
+    float wt[3][3];                                 // clip weights of the three fan vertices (Clipper.h:16-17)
+    float pad[3];
+};
+
+// Debug dump of stages a3-a6 (edx_debug_raster_triangles).
+struct DumpRec { int i[7]; float f[7]; };
+
+struct Counters {
+    uint32_t nBig;           // triangles appended to the tile path
+    uint32_t nClipQueue;     // straddling triangles queued for the clipper
+    uint32_t nClipRecs;      // fan-triangle records written by the clipper
+    uint32_t nDump;
+    uint32_t pad[4];
+};
+
+struct FrameParams {
+    float mvp[16];           // Core/Renderer.cpp:90
+    float raster[16];        // Core/Renderer.cpp:91
+    float eye[3];            // Core/Renderer.cpp:289
+    float light[3];          // normalised (1,1,-1), Core/Renderer.cpp:290 + Shader.h:258
+    float albedo[3];
+    int width, height, binsX, binsY;
+    int shader, smallMax, hiz, hierarchical, captureIds, dump;
+    // mesh (SoA streams built at upload)
+    const float4* pos4;      // x, y, z, texcoord.v
+    const float4* nrm4;      // nx, ny, nz, texcoord.u
+    const uint32_t* i0; const uint32_t* i1; const uint32_t* i2;
+    uint32_t nTris, nVerts;
+    // frame state
+    unsigned long long* keys;            // 64-bit visibility keys, bin/tile/block-tiled, L2 resident
+    BigRec* big; uint32_t bigCap;
+    uint32_t* clipQueue; uint32_t clipQueueCap;
+    ClipRec* clipRecs; uint32_t clipRecCap;
+    uint32_t* clipSlot;                  // per submitted triangle: first ClipRec of its polygon
+    Counters* counters;
+    uchar4* color; float* depth; uint32_t* ids;
+    DumpRec* dumpBuf; uint32_t dumpCap;
+};
+
+struct V4 { float x, y, z, w; };
+
+// ---------------------------------------------------------------------------------------------
+// fp32 helpers that can never be contracted
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// ((a*x + b*y) + c*z) + d : the row . vector order of Matrix::TransformPoint (SURVEY.md §8c shim 1/2)
+__device__ __forceinline__ float row_dot(float a, float b, float c, float d, float x, float y, float z)
+{
+    return fadd(fadd(fadd(fmul(a, x), fmul(b, y)), fmul(c, z)), d);
+}
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+    return fadd(fadd(fmul(ax, bx), fmul(ay, by)), fmul(az, bz));
+}
+// b0*a0 + b1*a1 + b2*a2, left to right (Shader.h:161-169)
+__device__ __forceinline__ float blend3(float b0, float b1, float b2, float a0, float a1, float a2)
+{
+    return fadd(fadd(fmul(b0, a0), fmul(b1, a1)), fmul(b2, a2));
+}
+
+// Stage a1: DefaultVertexShader::Execute, Core/Shader.h:40-49 (w_in = 1)
+__device__ __forceinline__ V4 to_clip(const float* M, float x, float y, float z)
+{
+    V4 r;
+    r.x = row_dot(M[0], M[1], M[2], M[3], x, y, z);
+    r.y = row_dot(M[4], M[5], M[6], M[7], x, y, z);
+    r.z = row_dot(M[8], M[9], M[10], M[11], x, y, z);
+    r.w = row_dot(M[12], M[13], M[14], M[15], x, y, z);
+    return r;
+}
+
+// Stage a2: Clipper::ComputeClipCode, Core/Clipper.h:48-68
+enum { LEFT_BIT = 1, RIGHT_BIT = 2, BOTTOM_BIT = 4, TOP_BIT = 8, NEAR_BIT = 16, FAR_BIT = 32 };
+__device__ __forceinline__ uint32_t clip_code(const V4& v)
+{
+    uint32_t c = 0;
+    if (v.x < -v.w) c |= LEFT_BIT;
+    if (v.x > v.w) c |= RIGHT_BIT;
+    if (v.y < -v.w) c |= BOTTOM_BIT;
+    if (v.y > v.w) c |= TOP_BIT;
+    if (v.z > v.w) c |= FAR_BIT;
+    if (v.z < 0.0f) c |= NEAR_BIT;
+    return c;
+}
+
+// `int = float * 16.0` (RasterTriangle.h:35-40): exact scale, truncate toward zero; anything outside
+// int32 (or NaN) becomes the x86 integer-indefinite value the reference's cvttsd2si produces.
+__device__ __forceinline__ int snap_28_4(float f)
+{
+    float s = fmul(f, 16.0f);
+    if (!(s >= -2147483648.0f && s < 2147483648.0f)) return (int)0x80000000;
+    return __float2int_rz(s);
+}
+
+struct SetupTri {
+    int v0x, v0y, v1x, v1y, v2x, v2y;
+    float invDet;
+};
+
+// Vector4::HomogeneousProject + Matrix::TransformPoint(Vector3, raster) + snap of x and y
+// (Clipper.h:161-163, RasterTriangle.h:29-40)
+__device__ __forceinline__ void project_snap(const float* R, const V4& c, int& sx, int& sy)
+{
+    float ax = fdiv(c.x, c.w), ay = fdiv(c.y, c.w), az = fdiv(c.z, c.w);
+    float x = row_dot(R[0], R[1], R[2], R[3], ax, ay, az);
+    float y = row_dot(R[4], R[5], R[6], R[7], ax, ay, az);
+    float w = row_dot(R[12], R[13], R[14], R[15], ax, ay, az);
+    if (w != 1.0f) { x = fdiv(x, w); y = fdiv(y, w); }
+    sx = snap_28_4(x);
+    sy = snap_28_4(y);
+}
+
+// Stage a5: RasterTriangle::Setup, RasterTriangle.h:27-60. false = culled (det <= 0).
+__device__ __forceinline__ bool setup_tri(const float* R, const V4& c0, const V4& c1, const V4& c2, SetupTri& s)
+{
+    project_snap(R, c0, s.v0x, s.v0y);
+    project_snap(R, c1, s.v1x, s.v1y);
+    project_snap(R, c2, s.v2x, s.v2y);
+    uint32_t B1 = (uint32_t)s.v1y - (uint32_t)s.v2y, C1 = (uint32_t)s.v2x - (uint32_t)s.v1x;
+    uint32_t B2 = (uint32_t)s.v2y - (uint32_t)s.v0y, C2 = (uint32_t)s.v0x - (uint32_t)s.v2x;
+    int det = (int)(C2 * B1 - C1 * B2);
+    if (det <= 0) return false;
+    s.invDet = fdiv(1.0f, __int2float_rn(det));
+    return true;
+}
+
+// Edge equations of one triangle, ready for per-pixel evaluation.
+// Fill rule: the SSE TopLeftEdge of RasterTriangle.h:296-299 (mask bit-cast to -1).
+struct Edges {
+    uint32_t B0, C0, B1, C1, B2, C2;
+    int v0x, v0y, v1x, v1y, v2x, v2y;
+    int bias0, bias1, bias2;
+
+    __device__ __forceinline__ static int top_left(int ax, int ay, int bx, int by)
+    {
+        return ((by > ay) || (ay == by && ax > bx)) ? -1 : 0;
+    }
+    __device__ __forceinline__ void init(int a0x, int a0y, int a1x, int a1y, int a2x, int a2y)
+    {
+        v0x = a0x; v0y = a0y; v1x = a1x; v1y = a1y; v2x = a2x; v2y = a2y;
+        B0 = (uint32_t)v0y - (uint32_t)v1y; C0 = (uint32_t)v1x - (uint32_t)v0x;     // RasterTriangle.h:42-47
+        B1 = (uint32_t)v1y - (uint32_t)v2y; C1 = (uint32_t)v2x - (uint32_t)v1x;
+        B2 = (uint32_t)v2y - (uint32_t)v0y; C2 = (uint32_t)v0x - (uint32_t)v2x;
+        bias0 = top_left(v0x, v0y, v1x, v1y);
+        bias1 = top_left(v1x, v1y, v2x, v2y);
+        bias2 = top_left(v2x, v2y, v0x, v0y);
+    }
+    // biased edge functions at a sub-pixel position (RasterTriangle.h:301-312)
+    __device__ __forceinline__ int e0(int px, int py) const { return (int)(B0 * (uint32_t)(px - v0x) + C0 * (uint32_t)(py - v0y) + (uint32_t)bias0); }
+    __device__ __forceinline__ int e1(int px, int py) const { return (int)(B1 * (uint32_t)(px - v1x) + C1 * (uint32_t)(py - v1y) + (uint32_t)bias1); }
+    __device__ __forceinline__ int e2(int px, int py) const { return (int)(B2 * (uint32_t)(px - v2x) + C2 * (uint32_t)(py - v2y) + (uint32_t)bias2); }
+};
+
+// Barycentrics and depth from the UNBIASED edge values of edges 1 and 2
+// (TriangleSSE::CalcBarycentricCoord / GetDepth, RasterTriangle.h:324-337)
+__device__ __forceinline__ void barycentric(int raw1, int raw2, float invDet, float& l0, float& l1)
+{
+    l0 = fmul(__int2float_rn(raw1), invDet);
+    l1 = fmul(__int2float_rn(raw2), invDet);
+}
+__device__ __forceinline__ float depth_at(float l0, float l1, float z0, float z1, float z2)
+{
+    float l2 = fsub(fsub(1.0f, l0), l1);
+    return fadd(fadd(fmul(l0, z0), fmul(l1, z1)), fmul(l2, z2));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 64-bit visibility key. Sequential LESS_EQUAL testing with immediate write
+// (FrameBuffer.cpp:54-68) leaves, per pixel, the minimum depth and — among fragments at that
+// depth — the LAST one in submission order. min() over
+// (orderedDepth << 32) | ~prim reproduces that in any processing order.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long make_key(float d, uint32_t prim)
+{
+    uint32_t b = __float_as_uint(fadd(d, 0.0f));               // -0 -> +0, so equal depths tie exactly
+    b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+    return ((unsigned long long)b << 32) | (unsigned long long)(0xFFFFFFFFu - prim);
+}
+__device__ __forceinline__ float key_depth(unsigned long long k)
+{
+    uint32_t b = (uint32_t)(k >> 32);
+    b = (b & 0x80000000u) ? (b & 0x7FFFFFFFu) : ~b;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ uint32_t key_prim(unsigned long long k) { return 0xFFFFFFFFu - (uint32_t)k; }
+
+// key address of pixel (x, y): [bin][tile 4x4][block 2x2][8x8]
+__device__ __forceinline__ uint32_t key_index(int x, int y, int binsX)
+{
+    uint32_t bin = (uint32_t)(y >> BIN_LOG2) * (uint32_t)binsX + (uint32_t)(x >> BIN_LOG2);
+    uint32_t tile = (uint32_t)(((y >> TILE_LOG2) & 3) * 4 + ((x >> TILE_LOG2) & 3));
+    uint32_t block = (uint32_t)(((y >> 3) & 1) * 2 + ((x >> 3) & 1));
+    return ((bin * 16u + tile) * 4u + block) * 64u + (uint32_t)((y & 7) * 8 + (x & 7));
+}
+
+// pixel-centre range covered by a snapped bounding box: centres sit at 16*i + 8 (Rasterizer.h:23)
+__device__ __forceinline__ int first_centre(int lo) { return (lo + 7) >> 4; }     // ceil((lo - 8) / 16)
+__device__ __forceinline__ int last_centre(int hi) { return (hi - 8) >> 4; }      // floor((hi - 8) / 16)
+
+__device__ __forceinline__ int min3i(int a, int b, int c) { return min(a, min(b, c)); }
+__device__ __forceinline__ int max3i(int a, int b, int c) { return max(a, max(b, c)); }
+
+} // namespace edx

@@ -1,0 +1,643 @@
+// edx_kernels.cuh — CUDA kernels of the raster hot path, sm_100a.
+//
+// Frame = geom_kernel -> clip_kernel -> tile_kernel:
+//   geom_kernel  one thread per submitted triangle: vertex transform (a1), clip codes (a2), setup (a5),
+//                exact culls; triangles whose pixel-centre box is <= smallMax rasterise immediately with
+//                64-bit atomicMin into the L2-resident visibility-key buffer, larger ones are appended
+//                to the tile-path list, straddlers go to the clip queue.
+//   clip_kernel  Sutherland-Hodgman in clip space (a3/a4) for the queued straddlers, fan, setup, same routing.
+//   tile_kernel  one CTA per 64x64 bin, one warp per 16x16 tile: stages the bin's keys in shared memory,
+//                culls the large-triangle list against the bin (edge tests + hierarchical Z), rasterises
+//                survivors 16x16 -> 8x8 -> pixel with ballot masks, then resolves every pixel (depth,
+//                perspective-correct interpolation, Blinn-Phong) and writes the tile to HBM once.
+#pragma once
+#include "edx_device.cuh"
+
+namespace edx {
+
+// ---------------------------------------------------------------------------------------------
+// Mesh upload: 32-byte AoS vertices -> two float4 streams; uint32 x 3 indices -> three streams
+// (Utils/InputBuffer.h:16-28,148-194). Runs once per mesh, not per frame.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_vertices_kernel(const float4* __restrict__ aos, float4* __restrict__ pos4,
+                                                             float4* __restrict__ nrm4, uint32_t nVerts)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nVerts) return;
+    float4 a = __ldg(aos + 2 * (size_t)i);          // px py pz nx
+    float4 b = __ldg(aos + 2 * (size_t)i + 1);      // ny nz u  v
+    pos4[i] = make_float4(a.x, a.y, a.z, b.w);
+    nrm4[i] = make_float4(a.w, b.x, b.y, b.z);
+}
+
+__global__ void __launch_bounds__(256) split_indices_kernel(const uint32_t* __restrict__ idx, uint32_t* __restrict__ i0,
+                                                            uint32_t* __restrict__ i1, uint32_t* __restrict__ i2, uint32_t nTris)
+{
+    // 256 triangles = 768 consecutive words per CTA, staged through shared memory so both the
+    // global read and the three global writes are fully coalesced.
+    __shared__ uint32_t s[768];
+    size_t base = (size_t)blockIdx.x * 256;
+    size_t words = 3 * (size_t)nTris;
+    for (int k = threadIdx.x; k < 768; k += 256) {
+        size_t w = base * 3 + k;
+        s[k] = w < words ? __ldg(idx + w) : 0u;
+    }
+    __syncthreads();
+    size_t t = base + threadIdx.x;
+    if (t < nTris) {
+        i0[t] = s[3 * threadIdx.x];
+        i1[t] = s[3 * threadIdx.x + 1];
+        i2[t] = s[3 * threadIdx.x + 2];
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_keys_kernel(ulonglong2* __restrict__ keys, size_t nPairs)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nPairs) keys[i] = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+}
+
+// Stage a1 on its own (Renderer::VertexProcessing, Core/Renderer.cpp:120-127): SoA position stream in,
+// clip-space float4 out. The frame path fuses this arithmetic into geom_kernel; this kernel serves
+// edx_debug_clip_vertices (stage parity) and callers that want the projected stream.
+__global__ void __launch_bounds__(256) vertex_transform_kernel(const __grid_constant__ FrameParams P, float4* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nVerts) return;
+    float4 p = __ldg(P.pos4 + i);
+    V4 c = to_clip(P.mvp, p.x, p.y, p.z);
+    out[i] = make_float4(c.x, c.y, c.z, c.w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Routing of one post-setup triangle (shared by geom_kernel and clip_kernel)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_append(uint32_t* counter)
+{
+    // warp-aggregated atomic: one atomicAdd per group of lanes that reached this point together
+    uint32_t mask = __activemask();
+    uint32_t lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ void route_triangle(const FrameParams& P, const SetupTri& s, float z0, float z1, float z2,
+                                               float iw0, float iw1, float iw2, uint32_t prim)
+{
+    if (P.dump) {
+        uint32_t at = atomicAdd(&P.counters->nDump, 1u);
+        if (at < P.dumpCap) {
+            DumpRec& d = P.dumpBuf[at];
+            d.i[0] = (int)prim; d.i[1] = s.v0x; d.i[2] = s.v0y; d.i[3] = s.v1x; d.i[4] = s.v1y; d.i[5] = s.v2x; d.i[6] = s.v2y;
+            d.f[0] = z0; d.f[1] = z1; d.f[2] = z2; d.f[3] = iw0; d.f[4] = iw1; d.f[5] = iw2; d.f[6] = s.invDet;
+        }
+    }
+    // Pixel centres inside the snapped bounding box, clamped to the screen. A covered centre always
+    // lies inside the box, so this is the same pixel set the reference visits (Rasterizer.h:132-137)
+    // minus pixels that cannot be covered; an empty range is an exact cull.
+    int x0 = max(0, first_centre(min3i(s.v0x, s.v1x, s.v2x)));
+    int x1 = min(P.width - 1, last_centre(max3i(s.v0x, s.v1x, s.v2x)));
+    int y0 = max(0, first_centre(min3i(s.v0y, s.v1y, s.v2y)));
+    int y1 = min(P.height - 1, last_centre(max3i(s.v0y, s.v1y, s.v2y)));
+    if (x0 > x1 || y0 > y1) return;
+
+    if (x1 - x0 < P.smallMax && y1 - y0 < P.smallMax) {
+        // Small triangle: rasterise here. Stages a10/a12/a13 per pixel:
+        // coverage (Rasterizer.h:162), barycentrics + depth (RasterTriangle.h:324-337), depth test as key-min.
+        Edges e;
+        e.init(s.v0x, s.v0y, s.v1x, s.v1y, s.v2x, s.v2y);
+        const int cx = (x0 << 4) + 8, cy = (y0 << 4) + 8;
+        uint32_t r0 = (uint32_t)e.e0(cx, cy), r1 = (uint32_t)e.e1(cx, cy), r2 = (uint32_t)e.e2(cx, cy);
+        const uint32_t sB0 = e.B0 << 4, sB1 = e.B1 << 4, sB2 = e.B2 << 4;   // one pixel = 16 sub-pixels (RasterTriangle.h:53-58)
+        const uint32_t sC0 = e.C0 << 4, sC1 = e.C1 << 4, sC2 = e.C2 << 4;
+        for (int y = y0; y <= y1; y++) {
+            uint32_t a0 = r0, a1 = r1, a2 = r2;
+            for (int x = x0; x <= x1; x++) {
+                if ((int)(a0 | a1 | a2) >= 0) {
+                    float l0, l1;
+                    barycentric((int)(a1 - (uint32_t)e.bias1), (int)(a2 - (uint32_t)e.bias2), s.invDet, l0, l1);
+                    float d = depth_at(l0, l1, z0, z1, z2);
+                    if (d <= 1.0f)     // depth buffer is cleared to 1.0 and tested LESS_EQUAL (FrameBuffer.cpp:64,103)
+                        atomicMin(P.keys + key_index(x, y, P.binsX), make_key(d, prim));
+                }
+                a0 += sB0; a1 += sB1; a2 += sB2;
+            }
+            r0 += sC0; r1 += sC1; r2 += sC2;
+        }
+    } else {
+        uint32_t at = warp_append(&P.counters->nBig);
+        if (at < P.bigCap) {
+            BigRec r;
+            r.v0x = s.v0x; r.v0y = s.v0y; r.v1x = s.v1x; r.v1y = s.v1y; r.v2x = s.v2x; r.v2y = s.v2y;
+            r.z0 = z0; r.z1 = z1; r.z2 = z2; r.invDet = s.invDet; r.prim = prim; r.pad = 0;
+            int4* dst = reinterpret_cast<int4*>(P.big + at);
+            const int4* src = reinterpret_cast<const int4*>(&r);
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// geom_kernel: stages a1, a2, a5, a6 and the small-triangle part of a10-a13
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) geom_kernel(const __grid_constant__ FrameParams P)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.nTris) return;
+    uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
+    float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
+    V4 c0 = to_clip(P.mvp, p0.x, p0.y, p0.z);
+    V4 c1 = to_clip(P.mvp, p1.x, p1.y, p1.z);
+    V4 c2 = to_clip(P.mvp, p2.x, p2.y, p2.z);
+    uint32_t k0 = clip_code(c0), k1 = clip_code(c1), k2 = clip_code(c2);
+    if (k0 | k1 | k2) {
+        if (!(k0 & k1 & k2)) {                       // Clipper.h:107-109: straddles the frustum
+            uint32_t at = warp_append(&P.counters->nClipQueue);
+            if (at < P.clipQueueCap) P.clipQueue[at] = t;
+        }
+        return;
+    }
+    SetupTri s;
+    if (!setup_tri(P.raster, c0, c1, c2, s)) return;
+    // Renderer.cpp:139-147: invW = 1/w, z = z * invW
+    float iw0 = fdiv(1.0f, c0.w), iw1 = fdiv(1.0f, c1.w), iw2 = fdiv(1.0f, c2.w);
+    route_triangle(P, s, fmul(c0.z, iw0), fmul(c1.z, iw1), fmul(c2.z, iw2), iw0, iw1, iw2, t * 8u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// clip_kernel: stages a3/a4 (Clipper.h:71-288) for queued straddlers
+// ---------------------------------------------------------------------------------------------
+struct Poly {
+    V4 p[10];
+    float w[10][3];
+    int n;
+};
+
+__device__ __forceinline__ bool plane_inside(int plane, const V4& v)
+{
+    switch (plane) {
+    case LEFT_BIT:   return v.x >= -v.w;
+    case RIGHT_BIT:  return v.x <= v.w;
+    case BOTTOM_BIT: return v.y >= -v.w;
+    case TOP_BIT:    return v.y <= v.w;
+    case FAR_BIT:    return v.z <= v.w;
+    default:         return v.z >= 0.0f;
+    }
+}
+
+__device__ __forceinline__ float plane_param(int plane, const V4& a, const V4& b)
+{
+    switch (plane) {                                  // Clipper.h:241,248,255,262,269,276
+    case LEFT_BIT:   return fdiv(fadd(a.w, a.x), fsub(fadd(a.x, a.w), fadd(b.x, b.w)));
+    case RIGHT_BIT:  return fdiv(fsub(a.x, a.w), fsub(fsub(a.x, a.w), fsub(b.x, b.w)));
+    case BOTTOM_BIT: return fdiv(fadd(a.w, a.y), fsub(fadd(a.y, a.w), fadd(b.y, b.w)));
+    case TOP_BIT:    return fdiv(fsub(a.y, a.w), fsub(fsub(a.y, a.w), fsub(b.y, b.w)));
+    case FAR_BIT:    return fdiv(fsub(a.z, a.w), fsub(fsub(a.z, a.w), fsub(b.z, b.w)));
+    default:         return fdiv(a.z, fsub(a.z, b.z));
+    }
+}
+
+__device__ __forceinline__ void cut_edge(int plane, const Poly& in, int i, int j, Poly& out)
+{
+    const V4 a = in.p[i], b = in.p[j];
+    float t = plane_param(plane, a, b);
+    float s = fsub(1.0f, t);
+    V4 r;                                             // Clipper.h:210-213
+    r.x = fadd(fmul(a.x, s), fmul(b.x, t));
+    r.y = fadd(fmul(a.y, s), fmul(b.y, t));
+    r.z = fadd(fmul(a.z, s), fmul(b.z, t));
+    r.w = fadd(fmul(a.w, s), fmul(b.w, t));
+    switch (plane) {                                  // snap onto the plane (:242,249,256,263,270,277)
+    case LEFT_BIT:   r.x = -r.w; break;
+    case RIGHT_BIT:  r.x = r.w; break;
+    case BOTTOM_BIT: r.y = -r.w; break;
+    case TOP_BIT:    r.y = r.w; break;
+    case FAR_BIT:    r.z = r.w; break;
+    default:         r.z = 0.0f; break;
+    }
+    int n = out.n++;
+    out.p[n] = r;
+    for (int k = 0; k < 3; k++) out.w[n][k] = fadd(fmul(in.w[i][k], s), fmul(in.w[j][k], t));
+}
+
+__device__ __forceinline__ void copy_vertex(const Poly& in, int j, Poly& out)
+{
+    int n = out.n++;
+    out.p[n] = in.p[j];
+    out.w[n][0] = in.w[j][0]; out.w[n][1] = in.w[j][1]; out.w[n][2] = in.w[j][2];
+}
+
+__device__ void clip_by_plane(int plane, const Poly& in, Poly& out)     // Clipper.h:192-232
+{
+    out.n = 0;
+    for (int i = 0; i < in.n; i++) {
+        int j = (i + 1 == in.n) ? 0 : i + 1;
+        bool in0 = plane_inside(plane, in.p[i]), in1 = plane_inside(plane, in.p[j]);
+        if (in0) {
+            if (in1) copy_vertex(in, j, out);
+            else cut_edge(plane, in, i, j, out);
+        } else if (in1) {
+            cut_edge(plane, in, i, j, out);
+            copy_vertex(in, j, out);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ FrameParams P)
+{
+    const uint32_t n = min(P.counters->nClipQueue, P.clipQueueCap);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const uint32_t t = P.clipQueue[q];
+        uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
+        float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
+        V4 c[3];
+        c[0] = to_clip(P.mvp, p0.x, p0.y, p0.z);
+        c[1] = to_clip(P.mvp, p1.x, p1.y, p1.z);
+        c[2] = to_clip(P.mvp, p2.x, p2.y, p2.z);
+        uint32_t k0 = clip_code(c[0]), k1 = clip_code(c[1]), k2 = clip_code(c[2]);
+        uint32_t planes = (k0 ^ k1) | (k1 ^ k2) | (k2 ^ k0);           // Clipper.h:119
+
+        Poly a, b;
+        a.n = 3;
+        for (int k = 0; k < 3; k++) {
+            a.p[k] = c[k];
+            a.w[k][0] = k == 0 ? 1.0f : 0.0f; a.w[k][1] = k == 1 ? 1.0f : 0.0f; a.w[k][2] = k == 2 ? 1.0f : 0.0f;
+        }
+        Poly* cur = &a; Poly* buf = &b;
+        const int order[6] = { LEFT_BIT, RIGHT_BIT, BOTTOM_BIT, TOP_BIT, FAR_BIT, NEAR_BIT };   // Clipper.h:237-278
+        for (int k = 0; k < 6; k++) {
+            if (planes & order[k]) { clip_by_plane(order[k], *cur, *buf); Poly* tmp = cur; cur = buf; buf = tmp; }
+        }
+        int nv = cur->n;
+        for (int k = 0; k < cur->n; k++)
+            if (cur->p[k].w <= 0.0f) nv = 0;                           // Clipper.h:280-287
+        if (nv < 3) continue;
+
+        // Clipper.h:121-153: vertices whose weight is exactly 1 ARE the original vertex (original
+        // clip position included); the others are new vertices at the clipped position.
+        uint32_t srcs = 0;
+        for (int k = 0; k < nv; k++) {
+            uint32_t src = 3;
+            if (cur->w[k][0] == 1.0f) src = 0;
+            else if (cur->w[k][1] == 1.0f) src = 1;
+            else if (cur->w[k][2] == 1.0f) src = 2;
+            if (src < 3) cur->p[k] = c[src];
+            srcs |= src << (2 * k);
+        }
+        const uint32_t nFan = (uint32_t)(nv - 2);
+        const uint32_t slot = atomicAdd(&P.counters->nClipRecs, nFan);
+        const bool haveRecs = slot + nFan <= P.clipRecCap;
+        if (haveRecs) P.clipSlot[t] = slot;
+
+        const V4 f0 = cur->p[0];
+        const float iwA = fdiv(1.0f, f0.w), zA = fmul(f0.z, iwA);
+        for (int k = 2; k < nv; k++) {                                  // Clipper.h:156-170 fan (0, k-1, k)
+            const V4 f1 = cur->p[k - 1], f2 = cur->p[k];
+            SetupTri s;
+            bool ok = setup_tri(P.raster, f0, f1, f2, s);
+            float iwB = fdiv(1.0f, f1.w), iwC = fdiv(1.0f, f2.w);
+            if (haveRecs) {
+                ClipRec r;
+                r.v0x = s.v0x; r.v0y = s.v0y; r.v1x = s.v1x; r.v1y = s.v1y; r.v2x = s.v2x; r.v2y = s.v2y;
+                r.invDet = ok ? s.invDet : 0.0f;
+                r.src = (srcs & 3u) | (((srcs >> (2 * (k - 1))) & 3u) << 2) | (((srcs >> (2 * k)) & 3u) << 4);
+                r.invW0 = iwA; r.invW1 = iwB; r.invW2 = iwC; r.valid = ok ? 1u : 0u;
+                for (int m = 0; m < 3; m++) { r.wt[0][m] = cur->w[0][m]; r.wt[1][m] = cur->w[k - 1][m]; r.wt[2][m] = cur->w[k][m]; }
+                r.pad[0] = r.pad[1] = r.pad[2] = 0.0f;
+                int4* dst = reinterpret_cast<int4*>(P.clipRecs + slot + (k - 2));
+                const int4* src = reinterpret_cast<const int4*>(&r);
+                #pragma unroll
+                for (int m = 0; m < 6; m++) dst[m] = src[m];
+            }
+            if (ok) route_triangle(P, s, zA, fmul(f1.z, iwB), fmul(f2.z, iwC), iwA, iwB, iwC, t * 8u + (uint32_t)(k - 2));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile_kernel helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t order_f32(float f)
+{
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// Exact classification of a triangle against the pixel centres of rect [px0, px0+size) x [py0, py0+size)
+// (clamped to the screen), using the same biased edge functions as per-pixel coverage. `reject`: no
+// centre can be covered; `full`: every centre is covered. This is the role of the reject / accept
+// corners of RasterTriangle.h:65-150, Renderer.cpp:189-224 and Rasterizer.h:42-85, evaluated at the
+// extreme pixel centres instead of the tile corners (so it is exact rather than conservative).
+// With wantZ it also returns conservative bounds of the depth the triangle can produce in the rect.
+__device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0, int size, int W, int H, bool wantZ,
+                                              bool& reject, bool& full, float& zmin, float& zmax)
+{
+    reject = true; full = false; zmin = 0.0f; zmax = 0.0f;
+    const int rx1 = min(px0 + size - 1, W - 1), ry1 = min(py0 + size - 1, H - 1);
+    if (px0 > rx1 || py0 > ry1) return;
+    const int tx0 = first_centre(min3i(r.v0x, r.v1x, r.v2x)), tx1 = last_centre(max3i(r.v0x, r.v1x, r.v2x));
+    const int ty0 = first_centre(min3i(r.v0y, r.v1y, r.v2y)), ty1 = last_centre(max3i(r.v0y, r.v1y, r.v2y));
+    if (tx0 > rx1 || tx1 < px0 || ty0 > ry1 || ty1 < py0) return;
+    Edges e;
+    e.init(r.v0x, r.v0y, r.v1x, r.v1y, r.v2x, r.v2y);
+    const int cx0 = (px0 << 4) + 8, cx1 = (rx1 << 4) + 8, cy0 = (py0 << 4) + 8, cy1 = (ry1 << 4) + 8;
+    const bool b0 = (int)e.B0 > 0, c0 = (int)e.C0 > 0, b1 = (int)e.B1 > 0, c1 = (int)e.C1 > 0, b2 = (int)e.B2 > 0, c2 = (int)e.C2 > 0;
+    if (e.e0(b0 ? cx1 : cx0, c0 ? cy1 : cy0) < 0) return;
+    if (e.e1(b1 ? cx1 : cx0, c1 ? cy1 : cy0) < 0) return;
+    if (e.e2(b2 ? cx1 : cx0, c2 ? cy1 : cy0) < 0) return;
+    reject = false;
+    full = e.e0(b0 ? cx0 : cx1, c0 ? cy0 : cy1) >= 0 && e.e1(b1 ? cx0 : cx1, c1 ? cy0 : cy1) >= 0 &&
+           e.e2(b2 ? cx0 : cx1, c2 ? cy0 : cy1) >= 0;
+    if (!wantZ) return;
+    // Depth is affine in the pixel position up to fp32 rounding: bound the exact plane over the rect in
+    // fp64, intersect with the vertex range, widen by a margin that dominates the fp32 error of
+    // barycentric()/depth_at() (<= ~1.3e-6 * max|z|).
+    const double det = (double)(int)(e.C2 * e.B1 - e.C1 * e.B2);
+    const double dz0 = (double)r.z0 - (double)r.z2, dz1 = (double)r.z1 - (double)r.z2;
+    const double B1 = (double)(int)e.B1, C1 = (double)(int)e.C1, B2 = (double)(int)e.B2, C2 = (double)(int)e.C2;
+    const double mx = 0.5 * ((double)cx0 + (double)cx1) - (double)r.v2x, my = 0.5 * ((double)cy0 + (double)cy1) - (double)r.v2y;
+    const double zc = (double)r.z2 + ((B1 * mx + C1 * my) * dz0 + (B2 * mx + C2 * my) * dz1) / det;
+    const double ext = (fabs(B1 * dz0 + B2 * dz1) * (0.5 * (double)(cx1 - cx0)) + fabs(C1 * dz0 + C2 * dz1) * (0.5 * (double)(cy1 - cy0))) / det;
+    const float vlo = fminf(r.z0, fminf(r.z1, r.z2)), vhi = fmaxf(r.z0, fmaxf(r.z1, r.z2));
+    const float margin = 1e-5f * fmaxf(fabsf(vlo), fabsf(vhi)) + 1e-30f;
+    zmin = __double2float_rd(fmax(zc - ext, (double)vlo)) - margin;
+    zmax = __double2float_ru(fmin(zc + ext, (double)vhi)) + margin;
+}
+
+// One warp rasterises one triangle into its 16x16 tile: 8x8 block masks by ballot, then pixels.
+// tkeys = the tile's 256 keys in shared memory, laid out [block 2x2][8x8].
+__device__ __forceinline__ void raster_tile_tri(unsigned long long* tkeys, const BigRec& r, int tx0, int ty0,
+                                                int W, int H, bool full, bool hierarchical)
+{
+    const int lane = threadIdx.x & 31;
+    Edges e;
+    e.init(r.v0x, r.v0y, r.v1x, r.v1y, r.v2x, r.v2y);
+    uint32_t rejMask = 0, accMask = full ? 0xFu : 0u;
+    if (!full && hierarchical) {
+        bool rej, acc; float zl, zh;
+        const int q = lane & 3;
+        classify_rect(r, tx0 + (q & 1) * BLOCK_PX, ty0 + (q >> 1) * BLOCK_PX, BLOCK_PX, W, H, false, rej, acc, zl, zh);
+        rejMask = __ballot_sync(0xFFFFFFFFu, rej) & 0xFu;
+        accMask = __ballot_sync(0xFFFFFFFFu, acc) & 0xFu;
+    }
+    #pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        if ((rejMask >> q) & 1u) continue;
+        const bool acc = (accMask >> q) & 1u;
+        const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7);
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
+            if (px < W && py < H) {
+                const int cx = (px << 4) + 8, cy = (py << 4) + 8;
+                const int a1 = e.e1(cx, cy), a2 = e.e2(cx, cy);
+                if (acc || ((e.e0(cx, cy) | a1 | a2) >= 0)) {
+                    float l0, l1;
+                    barycentric(a1 - e.bias1, a2 - e.bias2, r.invDet, l0, l1);
+                    float d = depth_at(l0, l1, r.z0, r.z1, r.z2);
+                    if (d <= 1.0f) {
+                        unsigned long long key = make_key(d, r.prim);
+                        const int at = q * 64 + lane + 32 * h;
+                        if (key < tkeys[at]) tkeys[at] = key;      // the warp owns the tile: no atomics needed
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint8_t to_u8(float c)       // Color4b::FromFloats (Renderer.cpp:296-299; DESIGN.md shim 13)
+{
+    float t = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
+    float s = fadd(fmul(t, 255.0f), 0.5f);
+    if (!(s >= 0.0f)) return 0;
+    return (uint8_t)__float2int_rz(s);
+}
+
+__device__ __forceinline__ float rsqrt_exact(float x) { return fdiv(1.0f, __fsqrt_rn(x)); }   // DESIGN.md shim 9
+
+// Stages a15-a17 for one pixel: re-derive the owning triangle from its prim id (visibility-buffer
+// style: nothing per-triangle was stored for small triangles), interpolate perspective-correctly
+// (Shader.h:142-170), shade (Shader.h:185-282) and pack (Renderer.cpp:295-301).
+__device__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int py)
+{
+    const uint32_t t = prim >> 3, fan = prim & 7u;
+    const uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
+    const float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
+    const float4 n0 = __ldg(P.nrm4 + i0), n1 = __ldg(P.nrm4 + i1), n2 = __ldg(P.nrm4 + i2);
+    const V4 c0 = to_clip(P.mvp, p0.x, p0.y, p0.z), c1 = to_clip(P.mvp, p1.x, p1.y, p1.z), c2 = to_clip(P.mvp, p2.x, p2.y, p2.z);
+
+    int v1x, v1y, v2x, v2y, v0y, v0x;
+    float invDet, iw0, iw1, iw2;
+    float A[3][6];                     // position.xyz, normal.xyz of the three (fan) vertices
+    if ((clip_code(c0) | clip_code(c1) | clip_code(c2)) == 0) {
+        SetupTri s;
+        setup_tri(P.raster, c0, c1, c2, s);
+        v0x = s.v0x; v0y = s.v0y; v1x = s.v1x; v1y = s.v1y; v2x = s.v2x; v2y = s.v2y; invDet = s.invDet;
+        iw0 = fdiv(1.0f, c0.w); iw1 = fdiv(1.0f, c1.w); iw2 = fdiv(1.0f, c2.w);
+        A[0][0] = p0.x; A[0][1] = p0.y; A[0][2] = p0.z; A[0][3] = n0.x; A[0][4] = n0.y; A[0][5] = n0.z;
+        A[1][0] = p1.x; A[1][1] = p1.y; A[1][2] = p1.z; A[1][3] = n1.x; A[1][4] = n1.y; A[1][5] = n1.z;
+        A[2][0] = p2.x; A[2][1] = p2.y; A[2][2] = p2.z; A[2][3] = n2.x; A[2][4] = n2.y; A[2][5] = n2.z;
+    } else {
+        const ClipRec* rp = P.clipRecs + (__ldg(P.clipSlot + t) + fan);
+        const int4 w0 = __ldg(reinterpret_cast<const int4*>(rp));
+        const int4 w1 = __ldg(reinterpret_cast<const int4*>(rp) + 1);
+        const float4 w2 = __ldg(reinterpret_cast<const float4*>(rp) + 2);
+        const float4 w3 = __ldg(reinterpret_cast<const float4*>(rp) + 3);
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(rp) + 4);
+        const float4 w5 = __ldg(reinterpret_cast<const float4*>(rp) + 5);
+        v0x = w0.x; v0y = w0.y; v1x = w0.z; v1y = w0.w; v2x = w1.x; v2y = w1.y;
+        invDet = __int_as_float(w1.z);
+        const uint32_t src = (uint32_t)w1.w;
+        iw0 = w2.x; iw1 = w2.y; iw2 = w2.z;
+        const float wt[3][3] = { { w3.x, w3.y, w3.z }, { w3.w, w4.x, w4.y }, { w4.z, w4.w, w5.x } };
+        const float O[3][6] = { { p0.x, p0.y, p0.z, n0.x, n0.y, n0.z }, { p1.x, p1.y, p1.z, n1.x, n1.y, n1.z }, { p2.x, p2.y, p2.z, n2.x, n2.y, n2.z } };
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uint32_t sk = (src >> (2 * k)) & 3u;
+            #pragma unroll
+            for (int m = 0; m < 6; m++) {
+                // Clipper.h:141-146: weight.x*a + weight.y*b + weight.z*c for new vertices
+                float blended = blend3(wt[k][0], wt[k][1], wt[k][2], O[0][m], O[1][m], O[2][m]);
+                A[k][m] = sk == 0 ? O[0][m] : (sk == 1 ? O[1][m] : (sk == 2 ? O[2][m] : blended));
+            }
+        }
+    }
+    const uint32_t B1 = (uint32_t)v1y - (uint32_t)v2y, C1 = (uint32_t)v2x - (uint32_t)v1x;
+    const uint32_t B2 = (uint32_t)v2y - (uint32_t)v0y, C2 = (uint32_t)v0x - (uint32_t)v2x;
+    const uint32_t dx = (uint32_t)((px << 4) + 8 - v2x), dy = (uint32_t)((py << 4) + 8 - v2y);
+    float b0, b1;
+    barycentric((int)(B1 * dx + C1 * dy), (int)(B2 * dx + C2 * dy), invDet, b0, b1);
+    // Fragment::Interpolate, Shader.h:151-159
+    float b2 = fsub(fsub(1.0f, b0), b1);
+    b0 = fmul(b0, iw0); b1 = fmul(b1, iw1); b2 = fmul(b2, iw2);
+    const float invB = fdiv(1.0f, fadd(fadd(b0, b1), b2));
+    b0 = fmul(b0, invB); b1 = fmul(b1, invB);
+    b2 = fsub(fsub(1.0f, b0), b1);
+    const float posx = blend3(b0, b1, b2, A[0][0], A[1][0], A[2][0]);
+    const float posy = blend3(b0, b1, b2, A[0][1], A[1][1], A[2][1]);
+    const float posz = blend3(b0, b1, b2, A[0][2], A[1][2], A[2][2]);
+    float nx = blend3(b0, b1, b2, A[0][3], A[1][3], A[2][3]);
+    float ny = blend3(b0, b1, b2, A[0][4], A[1][4], A[2][4]);
+    float nz = blend3(b0, b1, b2, A[0][5], A[1][5], A[2][5]);
+    // Shader.h:256-264
+    float w = rsqrt_exact(dot3(nx, ny, nz, nx, ny, nz));
+    nx = fmul(nx, w); ny = fmul(ny, w); nz = fmul(nz, w);
+    float dA = dot3(P.light[0], P.light[1], P.light[2], nx, ny, nz);
+    if (dA < 0.0f) dA = 0.0f;
+    const float diffuse = fmul(fmul(fadd(dA, 0.2f), 3.0f), 0.31830988618f);
+    float cr = diffuse, cg = diffuse, cb = diffuse;
+    if (P.shader == SH_BLINN_PHONG) {
+        // Shader.h:266-280
+        float ex = fsub(P.eye[0], posx), ey = fsub(P.eye[1], posy), ez = fsub(P.eye[2], posz);
+        w = rsqrt_exact(dot3(ex, ey, ez, ex, ey, ez));
+        ex = fmul(ex, w); ey = fmul(ey, w); ez = fmul(ez, w);
+        float hx = fadd(P.light[0], ex), hy = fadd(P.light[1], ey), hz = fadd(P.light[2], ez);
+        w = rsqrt_exact(dot3(hx, hy, hz, hx, hy, hz));
+        hx = fmul(hx, w); hy = fmul(hy, w); hz = fmul(hz, w);
+        const float spec = fmul(powf(dot3(nx, ny, nz, hx, hy, hz), 200.0f), 3.0f);
+        cr = cg = cb = fadd(diffuse, spec);
+    } else if (P.shader == SH_LAMBERT_ALBEDO) {
+        cr = fmul(diffuse, P.albedo[0]); cg = fmul(diffuse, P.albedo[1]); cb = fmul(diffuse, P.albedo[2]);
+    }
+    return make_uchar4(to_u8(cr), to_u8(cg), to_u8(cb), 255);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile_kernel: stages a7-a11 for large triangles + a13 resolve + a15-a17 for every pixel
+// ---------------------------------------------------------------------------------------------
+struct TileShared {
+    unsigned long long keys[KEYS_PER_BIN];     // 32 KB: [tile 4x4][block 2x2][8x8]
+    BigRec surv[SURV_CAP];                     // 48 KB
+    uint32_t survCount;
+    uint32_t binU;                             // order_f32 of the bin's depth upper bound
+};
+
+__device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShared& S, int ox, int oy)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
+    const int n = (int)S.survCount;
+    if (tx0 >= P.width || ty0 >= P.height || n == 0) return;
+    unsigned long long* tkeys = S.keys + warp * 256;
+    const bool hiz = P.hiz && P.hierarchical;
+    // pass A: depth upper bound of the tile = nearest far-side of any triangle that covers it fully
+    float U = 1.0f;
+    if (hiz) {
+        for (int b = 0; b < n; b += 32) {
+            const int j = b + lane;
+            if (j < n) {
+                bool rej, full; float zl, zh;
+                classify_rect(S.surv[j], tx0, ty0, TILE_PX, P.width, P.height, true, rej, full, zl, zh);
+                if (!rej && full && zh <= 1.0f) U = fminf(U, zh);
+            }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) U = fminf(U, __shfl_xor_sync(0xFFFFFFFFu, U, o));
+    }
+    // pass B: lane-per-triangle tile test, then warp-per-triangle rasterisation of the survivors
+    for (int b = 0; b < n; b += 32) {
+        const int j = b + lane;
+        bool keep = false, full = false;
+        if (j < n) {
+            bool rej; float zl, zh;
+            classify_rect(S.surv[j], tx0, ty0, TILE_PX, P.width, P.height, hiz, rej, full, zl, zh);
+            keep = !rej && (!hiz || zl <= U);
+            if (!P.hierarchical) full = false;
+        }
+        uint32_t keepMask = __ballot_sync(0xFFFFFFFFu, keep);
+        const uint32_t fullMask = __ballot_sync(0xFFFFFFFFu, keep && full);
+        while (keepMask) {
+            const int l = __ffs(keepMask) - 1;
+            keepMask &= keepMask - 1;
+            raster_tile_tri(tkeys, S.surv[b + l], tx0, ty0, P.width, P.height, (fullMask >> l) & 1u, P.hierarchical != 0);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TILE_THREADS, 1) tile_kernel(const __grid_constant__ FrameParams P)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    TileShared& S = *reinterpret_cast<TileShared*>(smemRaw);
+    const int tid = threadIdx.x;
+    const int bin = blockIdx.x;
+    const int ox = (bin % P.binsX) << BIN_LOG2, oy = (bin / P.binsX) << BIN_LOG2;
+
+    // stage the bin's keys (what the small-triangle path left in L2) and reset them for the next frame
+    {
+        ulonglong2* g = reinterpret_cast<ulonglong2*>(P.keys + (size_t)bin * KEYS_PER_BIN);
+        ulonglong2* s = reinterpret_cast<ulonglong2*>(S.keys);
+        const ulonglong2 empty = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+        #pragma unroll
+        for (int k = 0; k < KEYS_PER_BIN / 2 / TILE_THREADS; k++) {
+            const int at = tid + k * TILE_THREADS;
+            s[at] = g[at];
+            g[at] = empty;
+        }
+    }
+    if (tid == 0) { S.survCount = 0; S.binU = order_f32(1.0f); }
+    __syncthreads();
+
+    // sweep the large-triangle list: exact reject + hierarchical-Z against the bin, survivors to smem
+    const uint32_t nBig = min(P.counters->nBig, P.bigCap);
+    const bool hiz = P.hiz && P.hierarchical;
+    for (uint32_t base = 0; base < nBig; base += TILE_THREADS) {
+        if (S.survCount > SURV_CAP - TILE_THREADS) {          // uniform: read after a barrier
+            raster_survivors(P, S, ox, oy);
+            __syncthreads();
+            if (tid == 0) S.survCount = 0;
+            __syncthreads();
+        }
+        const uint32_t i = base + tid;
+        if (i < nBig) {
+            BigRec r;
+            const int4* src = reinterpret_cast<const int4*>(P.big + i);
+            int4* dst = reinterpret_cast<int4*>(&r);
+            dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
+            bool rej, full; float zl, zh;
+            classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, rej, full, zl, zh);
+            if (!rej) {
+                bool keep = true;
+                if (hiz) {
+                    keep = order_f32(zl) <= S.binU;            // racy read of a monotonically shrinking bound: conservative
+                    if (full && zh <= 1.0f) atomicMin(&S.binU, order_f32(zh));
+                }
+                if (keep) {
+                    const uint32_t at = atomicAdd(&S.survCount, 1u);
+                    int4* d2 = reinterpret_cast<int4*>(&S.surv[at]);
+                    d2[0] = dst[0]; d2[1] = dst[1]; d2[2] = dst[2];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    raster_survivors(P, S, ox, oy);
+    __syncwarp();
+
+    // resolve: every warp finishes its own tile; each pixel is written to HBM exactly once
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
+    if (tx0 >= P.width || ty0 >= P.height) return;
+    const unsigned long long* tkeys = S.keys + warp * 256;
+    #pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7);
+        #pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const int py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
+            if (px >= P.width || py >= P.height) continue;
+            const unsigned long long key = tkeys[q * 64 + lane + 32 * h];
+            const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);   // bottom-up, FrameBuffer.cpp:41
+            const bool hit = key != KEY_EMPTY;
+            P.depth[at] = hit ? key_depth(key) : 1.0f;
+            if (P.captureIds) P.ids[at] = hit ? key_prim(key) : 0xFFFFFFFFu;
+            if (P.shader != SH_DEPTH_ONLY)
+                P.color[at] = hit ? shade_pixel(P, key_prim(key), px, py) : make_uchar4(0, 0, 0, 0);
+        }
+    }
+}
+
+} // namespace edx

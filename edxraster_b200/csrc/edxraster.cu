@@ -1,0 +1,609 @@
+// edxraster.cu — C ABI (include/edxraster_c.h) over the sm_100a kernels in edx_kernels.cuh.
+//
+// Host-side frame orchestration: the counterpart of Renderer::RenderMesh (Core/Renderer.cpp:100-118)
+// and of the Renderer's buffer ownership (Renderer.h:18-31). No CPU fallback exists: without a
+// CUDA device every entry point reports an error.
+#include "../../include/edxraster_c.h"
+#include "edx_host_math.h"
+#include "edx_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace edx;
+
+struct edx_mesh {
+    float4* pos4 = nullptr;
+    float4* nrm4 = nullptr;
+    uint32_t* i0 = nullptr; uint32_t* i1 = nullptr; uint32_t* i2 = nullptr;
+    uint32_t* clipSlot = nullptr;
+    void* staging = nullptr; size_t stagingBytes = 0;     // device-side landing area for the AoS upload
+    uint32_t nVerts = 0, nTris = 0, capVerts = 0, capTris = 0;
+};
+
+struct edx_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool ownStream = true;
+    uint32_t width = 0, height = 0, binsX = 0, binsY = 0;
+    bool initialized = false;
+
+    // Renderer::SetTransform state (RenderStates.h:15-19)
+    edx_host::Mat4 mv, mvInv, proj, mvp, raster;
+    float eye[3], light[3], albedo[3];
+    int shader = EDX_SHADER_BLINN_PHONG;
+    int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
+    int smallMax = 8, hiz = 1;
+    bool colorDirty = false;
+
+    unsigned long long* keys = nullptr;
+    uchar4* color = nullptr; float* depth = nullptr; uint32_t* ids = nullptr;
+    BigRec* big = nullptr; uint32_t bigCap = 0;
+    uint32_t* clipQueue = nullptr; uint32_t clipQueueCap = 0;
+    ClipRec* clipRecs = nullptr; uint32_t clipRecCap = 0;
+    Counters* counters = nullptr;
+    Counters* hostCounters = nullptr;        // pinned
+    uint8_t* hostColor = nullptr;            // pinned mirror behind GetBackBuffer
+    size_t hostColorBytes = 0;
+
+    const edx_mesh* lastMesh = nullptr;
+    bool framePending = false;
+    int launches = 0;
+    edx_stats stats;
+    cudaEvent_t evTimer[2] = { nullptr, nullptr };
+    cudaEvent_t evStage[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::string error;
+};
+
+namespace {
+
+int fail(edx_context* c, int code, const std::string& msg)
+{
+    if (c) c->error = msg;
+    return code;
+}
+
+#define EDX_CUDA(ctx, call)                                                                          \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? EDX_ERR_OOM : EDX_ERR_CUDA,           \
+                        std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+    } while (0)
+
+template <typename T> void dev_free(T*& p) { if (p) { cudaFree(p); p = nullptr; } }
+
+int bind(edx_context* c) { EDX_CUDA(c, cudaSetDevice(c->device)); return EDX_OK; }
+
+void release_frame_buffers(edx_context* c)
+{
+    dev_free(c->keys); dev_free(c->color); dev_free(c->depth); dev_free(c->ids);
+    if (c->hostColor) { cudaFreeHost(c->hostColor); c->hostColor = nullptr; }
+}
+
+int allocate_frame_buffers(edx_context* c, uint32_t w, uint32_t h)
+{
+    release_frame_buffers(c);
+    c->width = w; c->height = h;
+    c->binsX = (w + BIN - 1) / BIN;                    // cf. Renderer.cpp:26-27 (32-px tiles there)
+    c->binsY = (h + BIN - 1) / BIN;
+    const size_t nKeys = (size_t)c->binsX * c->binsY * KEYS_PER_BIN;
+    const size_t nPix = (size_t)w * h;
+    EDX_CUDA(c, cudaMalloc(&c->keys, nKeys * sizeof(unsigned long long)));
+    EDX_CUDA(c, cudaMalloc(&c->color, nPix * sizeof(uchar4)));
+    EDX_CUDA(c, cudaMalloc(&c->depth, nPix * sizeof(float)));
+    EDX_CUDA(c, cudaMalloc(&c->ids, nPix * sizeof(uint32_t)));
+    c->hostColorBytes = nPix * 4;
+    EDX_CUDA(c, cudaMallocHost(&c->hostColor, c->hostColorBytes));
+    const size_t pairs = nKeys / 2;
+    fill_keys_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<ulonglong2*>(c->keys), pairs);
+    EDX_CUDA(c, cudaGetLastError());
+    EDX_CUDA(c, cudaMemsetAsync(c->color, 0, nPix * sizeof(uchar4), c->stream));     // FrameBuffer.cpp:91-95
+    EDX_CUDA(c, cudaMemsetAsync(c->ids, 0xFF, nPix * sizeof(uint32_t), c->stream));
+    c->colorDirty = false;
+    return EDX_OK;
+}
+
+template <typename T> int grow(edx_context* c, T*& p, uint32_t& cap, uint64_t need)
+{
+    if (need <= cap && p) return EDX_OK;
+    uint64_t want = std::max<uint64_t>(need + need / 4 + 1024, 4096);
+    if (want > 0xFFFFFFF0ull) return fail(c, EDX_ERR_OVERFLOW, "queue would exceed 2^32 entries");
+    dev_free(p);
+    EDX_CUDA(c, cudaMalloc(&p, (size_t)want * sizeof(T)));
+    cap = (uint32_t)want;
+    return EDX_OK;
+}
+
+void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
+{
+    memset(&P, 0, sizeof(P));
+    memcpy(P.mvp, c->mvp.m, 64);
+    memcpy(P.raster, c->raster.m, 64);
+    memcpy(P.eye, c->eye, 12); memcpy(P.light, c->light, 12); memcpy(P.albedo, c->albedo, 12);
+    P.width = (int)c->width; P.height = (int)c->height; P.binsX = (int)c->binsX; P.binsY = (int)c->binsY;
+    P.shader = c->shader; P.smallMax = c->smallMax; P.hiz = c->hiz; P.hierarchical = c->hierarchical;
+    P.captureIds = c->captureIds; P.dump = 0;
+    P.pos4 = m->pos4; P.nrm4 = m->nrm4; P.i0 = m->i0; P.i1 = m->i1; P.i2 = m->i2;
+    P.nTris = m->nTris; P.nVerts = m->nVerts;
+    P.keys = c->keys;
+    P.big = c->big; P.bigCap = c->bigCap;
+    P.clipQueue = c->clipQueue; P.clipQueueCap = c->clipQueueCap;
+    P.clipRecs = c->clipRecs; P.clipRecCap = c->clipRecCap;
+    P.clipSlot = m->clipSlot;
+    P.counters = c->counters;
+    P.color = c->color; P.depth = c->depth; P.ids = c->ids;
+}
+
+// One frame on the stream. dumpBuf != nullptr routes post-setup triangles to the debug dump as well.
+int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t dumpCap)
+{
+    // initial queue sizes; grown on demand after a frame reports it needed more
+    if (int r = grow(c, c->big, c->bigCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
+    if (int r = grow(c, c->clipQueue, c->clipQueueCap, std::max<uint64_t>(1u << 14, m->nTris / 32))) return r;
+    if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
+
+    FrameParams P;
+    fill_params(c, m, P);
+    if (dumpBuf) { P.dump = 1; P.dumpBuf = dumpBuf; P.dumpCap = dumpCap; }
+
+    if (c->shader == EDX_SHADER_DEPTH_ONLY && c->colorDirty) {
+        // depth-only frames never touch colour: restore the cleared state once (FrameBuffer.cpp:91-95)
+        EDX_CUDA(c, cudaMemsetAsync(c->color, 0, (size_t)c->width * c->height * 4, c->stream));
+        c->colorDirty = false;
+    }
+    if (c->shader != EDX_SHADER_DEPTH_ONLY) c->colorDirty = true;
+
+    c->launches = 0;
+    EDX_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(Counters), c->stream));
+    if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[0], c->stream));
+    if (m->nTris) {
+        geom_kernel<<<(m->nTris + 255) / 256, 256, 0, c->stream>>>(P);
+        c->launches++;
+    }
+    if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[1], c->stream));
+    if (m->nTris) {
+        clip_kernel<<<148 * 4, 128, 0, c->stream>>>(P);
+        c->launches++;
+    }
+    if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[2], c->stream));
+    tile_kernel<<<c->binsX * c->binsY, TILE_THREADS, sizeof(TileShared), c->stream>>>(P);
+    c->launches++;
+    if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[3], c->stream));
+    EDX_CUDA(c, cudaGetLastError());
+    EDX_CUDA(c, cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
+    return EDX_OK;
+}
+
+// Wait for the pending frame; if a queue overflowed, grow it and run the frame again.
+int finish_frame(edx_context* c)
+{
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (!c->framePending) return EDX_OK;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        const Counters& k = *c->hostCounters;
+        const bool over = k.nBig > c->bigCap || k.nClipQueue > c->clipQueueCap || k.nClipRecs > c->clipRecCap;
+        c->stats.binned_tris = k.nBig; c->stats.clipped_tris = k.nClipQueue; c->stats.clip_records = k.nClipRecs;
+        if (!over) {
+            if (c->profiling) {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, c->evStage[0], c->evStage[1]); c->stats.stage_ms[0] = ms;
+                cudaEventElapsedTime(&ms, c->evStage[1], c->evStage[2]); c->stats.stage_ms[1] = ms;
+                cudaEventElapsedTime(&ms, c->evStage[2], c->evStage[3]); c->stats.stage_ms[2] = ms;
+                cudaEventElapsedTime(&ms, c->evStage[0], c->evStage[3]); c->stats.stage_ms[3] = ms;
+            }
+            c->framePending = false;
+            return EDX_OK;
+        }
+        // a clip-queue overflow hides fan triangles, so size the dependent queues generously too
+        if (int r = grow(c, c->big, c->bigCap, (uint64_t)k.nBig + (k.nClipQueue > c->clipQueueCap ? 7ull * k.nClipQueue : 0))) return r;
+        if (int r = grow(c, c->clipQueue, c->clipQueueCap, k.nClipQueue)) return r;
+        if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(k.nClipRecs, 7ull * std::min<uint64_t>(k.nClipQueue, c->clipQueueCap)))) return r;
+        c->stats.regrow_count++;
+        if (int r = enqueue_frame(c, c->lastMesh, nullptr, 0)) return r;
+        EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return fail(c, EDX_ERR_OVERFLOW, "internal queues still overflow after 8 regrow attempts");
+}
+
+int upload_mesh(edx_context* c, edx_mesh* m, const void* vertices, uint32_t nv, const uint32_t* indices, uint32_t nt)
+{
+    const size_t vb = (size_t)nv * 32, ib = (size_t)nt * 12;
+    const size_t need = std::max(vb, ib);
+    if (need > m->stagingBytes) {
+        dev_free(m->staging);
+        EDX_CUDA(c, cudaMalloc(&m->staging, std::max<size_t>(need, 256)));
+        m->stagingBytes = std::max<size_t>(need, 256);
+    }
+    m->nVerts = nv; m->nTris = nt;
+    if (nv) {
+        EDX_CUDA(c, cudaMemcpyAsync(m->staging, vertices, vb, cudaMemcpyHostToDevice, c->stream));
+        split_vertices_kernel<<<(nv + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(m->staging), m->pos4, m->nrm4, nv);
+    }
+    if (nt) {
+        EDX_CUDA(c, cudaMemcpyAsync(m->staging, indices, ib, cudaMemcpyHostToDevice, c->stream));
+        split_indices_kernel<<<(nt + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(m->staging), m->i0, m->i1, m->i2, nt);
+    }
+    EDX_CUDA(c, cudaGetLastError());
+    return EDX_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* edx_version(void) { return "edxraster_b200 0.1.0 (sm_100a)"; }
+
+int edx_create(int device, edx_context** out)
+{
+    if (!out) return EDX_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return EDX_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return EDX_ERR_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return EDX_ERR_CUDA;
+    if (prop.major != 10) return EDX_ERR_NO_DEVICE;           // kernels are built for sm_100a only
+    edx_context* c = new edx_context;
+    c->device = device;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->mv = c->mvInv = c->proj = c->mvp = c->raster = edx_host::identity();
+    c->eye[0] = c->eye[1] = c->eye[2] = 0.0f;
+    const float l[3] = { 1.0f, 1.0f, -1.0f };                   // Renderer.cpp:290
+    edx_host::normalize3(l, c->light);
+    c->albedo[0] = c->albedo[1] = c->albedo[2] = 0.9f;          // Mesh.cpp:48,67
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc(&c->counters, sizeof(Counters)) == cudaSuccess &&
+              cudaMallocHost(&c->hostCounters, sizeof(Counters)) == cudaSuccess &&
+              cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess;
+    for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&c->evTimer[i]) == cudaSuccess;
+    for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&c->evStage[i]) == cudaSuccess;
+    if (!ok) { edx_destroy(c); return EDX_ERR_CUDA; }
+    memset(c->hostCounters, 0, sizeof(Counters));
+    *out = c;
+    return EDX_OK;
+}
+
+void edx_destroy(edx_context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    release_frame_buffers(c);
+    dev_free(c->big); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->counters);
+    if (c->hostCounters) cudaFreeHost(c->hostCounters);
+    for (auto& e : c->evTimer) if (e) cudaEventDestroy(e);
+    for (auto& e : c->evStage) if (e) cudaEventDestroy(e);
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* edx_last_error(const edx_context* c) { return c ? c->error.c_str() : "null context"; }
+
+int edx_initialize(edx_context* c, uint32_t width, uint32_t height)
+{
+    if (!c || width == 0 || height == 0 || width > 16384 || height > 16384) return fail(c, EDX_ERR_INVALID, "bad size");
+    // 28.4 edge functions are int32: (16 W)(16 H) must stay below 2^31
+    if ((uint64_t)(width * 16ull + 512) * (uint64_t)(height * 16ull + 512) >= (1ull << 31))
+        return fail(c, EDX_ERR_UNSUPPORTED, "resolution exceeds the int32 range of the 28.4 edge functions (max ~3840x2160)");
+    if (int r = bind(c)) return r;
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    // RenderStates::DefaultSettings (RenderStates.h:55-61)
+    c->msaaLog2 = 0; c->hierarchical = 1; c->texFilter = 2;
+    c->framePending = false;
+    if (int r = allocate_frame_buffers(c, width, height)) return r;
+    c->initialized = true;
+    return EDX_OK;
+}
+
+int edx_resize(edx_context* c, uint32_t width, uint32_t height)
+{
+    if (!c || !c->initialized) return fail(c, EDX_ERR_INVALID, "not initialised");
+    if (width == 0 || height == 0 || width > 16384 || height > 16384) return fail(c, EDX_ERR_INVALID, "bad size");
+    if ((uint64_t)(width * 16ull + 512) * (uint64_t)(height * 16ull + 512) >= (1ull << 31))
+        return fail(c, EDX_ERR_UNSUPPORTED, "resolution exceeds the int32 range of the 28.4 edge functions");
+    if (int r = bind(c)) return r;
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->framePending = false;
+    return allocate_frame_buffers(c, width, height);
+}
+
+int edx_set_transform(edx_context* c, const float mv[16], const float proj[16], const float raster[16])
+{
+    if (!c || !mv || !proj || !raster) return fail(c, EDX_ERR_INVALID, "null matrix");
+    memcpy(c->mv.m, mv, 64); memcpy(c->proj.m, proj, 64); memcpy(c->raster.m, raster, 64);
+    c->mvInv = edx_host::inverse(c->mv);                    // Renderer.cpp:88
+    c->mvp = edx_host::multiply(c->proj, c->mv);            // Renderer.cpp:90
+    const float zero[3] = { 0.0f, 0.0f, 0.0f };
+    edx_host::transform_point3(c->mvInv, zero, c->eye);     // Renderer.cpp:289
+    return EDX_OK;
+}
+
+int edx_set_msaa_mode(edx_context* c, int log2)
+{
+    if (!c) return EDX_ERR_INVALID;
+    if (log2 != 0) return fail(c, EDX_ERR_UNSUPPORTED, "MSAA above 1x is not implemented in this round (SURVEY.md §8f rank 1)");
+    c->msaaLog2 = 0;
+    return EDX_OK;
+}
+
+int edx_set_texture_filter(edx_context* c, int filter)
+{
+    if (!c || filter < 0 || filter > 5) return fail(c, EDX_ERR_INVALID, "filter out of range");
+    c->texFilter = filter;
+    return EDX_OK;
+}
+
+int edx_set_hierarchical_rasterize(edx_context* c, int enabled)
+{
+    if (!c) return EDX_ERR_INVALID;
+    c->hierarchical = enabled ? 1 : 0;
+    return EDX_OK;
+}
+
+int edx_set_pixel_shader(edx_context* c, int shader)
+{
+    if (!c || shader < 0 || shader > 3) return fail(c, EDX_ERR_INVALID, "unknown shader");
+    c->shader = shader;
+    return EDX_OK;
+}
+
+int edx_set_albedo(edx_context* c, float r, float g, float b)
+{
+    if (!c) return EDX_ERR_INVALID;
+    c->albedo[0] = r; c->albedo[1] = g; c->albedo[2] = b;
+    return EDX_OK;
+}
+
+int edx_set_option(edx_context* c, const char* name, int value)
+{
+    if (!c || !name) return EDX_ERR_INVALID;
+    if (!strcmp(name, "small_max")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max in [0,64]"); c->smallMax = value; return EDX_OK; }
+    if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }
+    return fail(c, EDX_ERR_INVALID, std::string("unknown option ") + name);
+}
+
+int edx_mesh_create(edx_context* c, const void* vertices, uint32_t nv, const uint32_t* indices, uint32_t nt,
+                    const uint32_t* tex_ids, edx_mesh** out)
+{
+    (void)tex_ids;      // texture slots feed only the textured shader
+    if (!c || !out || (nv && !vertices) || (nt && !indices)) return fail(c, EDX_ERR_INVALID, "null buffer");
+    if (nt > (1u << 29) - 1) return fail(c, EDX_ERR_UNSUPPORTED, "more than 2^29-1 triangles per mesh (prim id = tri*8 + fan)");
+    if (int r = bind(c)) return r;
+    edx_mesh* m = new edx_mesh;
+    m->capVerts = std::max(nv, 1u); m->capTris = std::max(nt, 1u);
+    cudaError_t e = cudaMalloc(&m->pos4, (size_t)m->capVerts * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->nrm4, (size_t)m->capVerts * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&m->i0, (size_t)m->capTris * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&m->i1, (size_t)m->capTris * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&m->i2, (size_t)m->capTris * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&m->clipSlot, (size_t)m->capTris * 4);
+    if (e != cudaSuccess) { edx_mesh_destroy(c, m); return fail(c, EDX_ERR_OOM, cudaGetErrorString(e)); }
+    if (int r = upload_mesh(c, m, vertices, nv, indices, nt)) { edx_mesh_destroy(c, m); return r; }
+    // copy semantics of CreateVertexBuffer / CreateIndexBuffer: the caller's arrays are free on return
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { edx_mesh_destroy(c, m); return fail(c, EDX_ERR_CUDA, "mesh upload failed"); }
+    *out = m;
+    return EDX_OK;
+}
+
+int edx_mesh_update(edx_context* c, edx_mesh* m, const void* vertices, uint32_t nv, const uint32_t* indices, uint32_t nt)
+{
+    if (!c || !m || (nv && !vertices) || (nt && !indices)) return fail(c, EDX_ERR_INVALID, "null buffer");
+    if (nv > m->capVerts || nt > m->capTris) return fail(c, EDX_ERR_INVALID, "mesh_update larger than the mesh's capacity");
+    if (int r = bind(c)) return r;
+    return upload_mesh(c, m, vertices, nv, indices, nt);
+}
+
+int edx_mesh_destroy(edx_context* c, edx_mesh* m)
+{
+    if (!m) return EDX_OK;
+    if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->lastMesh == m) { c->lastMesh = nullptr; c->framePending = false; } }
+    dev_free(m->pos4); dev_free(m->nrm4); dev_free(m->i0); dev_free(m->i1); dev_free(m->i2); dev_free(m->clipSlot);
+    if (m->staging) cudaFree(m->staging);
+    delete m;
+    return EDX_OK;
+}
+
+int edx_render_mesh(edx_context* c, const edx_mesh* m)
+{
+    if (!c || !m) return fail(c, EDX_ERR_INVALID, "null mesh");
+    if (!c->initialized) return fail(c, EDX_ERR_INVALID, "Initialize has not been called");
+    if (int r = bind(c)) return r;
+    c->lastMesh = m;
+    c->stats.submitted_tris = m->nTris;
+    if (int r = enqueue_frame(c, m, nullptr, 0)) return r;
+    c->framePending = true;
+    return EDX_OK;
+}
+
+int edx_synchronize(edx_context* c)
+{
+    if (!c) return EDX_ERR_INVALID;
+    if (int r = bind(c)) return r;
+    return finish_frame(c);
+}
+
+const uint8_t* edx_get_back_buffer(edx_context* c)
+{
+    if (!c || !c->initialized) return nullptr;
+    if (bind(c) || finish_frame(c)) return nullptr;
+    if (cudaMemcpyAsync(c->hostColor, c->color, c->hostColorBytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        c->error = "frame read-back failed";
+        return nullptr;
+    }
+    return c->hostColor;
+}
+
+int edx_read_depth(edx_context* c, float* out)
+{
+    if (!c || !out || !c->initialized) return fail(c, EDX_ERR_INVALID, "bad argument");
+    if (int r = bind(c)) return r;
+    if (int r = finish_frame(c)) return r;
+    EDX_CUDA(c, cudaMemcpyAsync(out, c->depth, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToHost, c->stream));
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EDX_OK;
+}
+
+int edx_set_capture_ids(edx_context* c, int enabled)
+{
+    if (!c) return EDX_ERR_INVALID;
+    c->captureIds = enabled ? 1 : 0;
+    return EDX_OK;
+}
+
+int edx_read_winner_ids(edx_context* c, uint32_t* out)
+{
+    if (!c || !out || !c->initialized) return fail(c, EDX_ERR_INVALID, "bad argument");
+    if (!c->captureIds) return fail(c, EDX_ERR_INVALID, "edx_set_capture_ids(ctx, 1) must be set before the frame");
+    if (int r = bind(c)) return r;
+    if (int r = finish_frame(c)) return r;
+    EDX_CUDA(c, cudaMemcpyAsync(out, c->ids, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToHost, c->stream));
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EDX_OK;
+}
+
+int edx_debug_clip_vertices(edx_context* c, const edx_mesh* m, float* out)
+{
+    if (!c || !m || !out) return fail(c, EDX_ERR_INVALID, "bad argument");
+    if (int r = bind(c)) return r;
+    if (!m->nVerts) return EDX_OK;
+    float4* d = nullptr;
+    EDX_CUDA(c, cudaMalloc(&d, (size_t)m->nVerts * 16));
+    FrameParams P;
+    fill_params(c, m, P);
+    vertex_transform_kernel<<<(m->nVerts + 255) / 256, 256, 0, c->stream>>>(P, d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d, (size_t)m->nVerts * 16, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(c, EDX_ERR_CUDA, cudaGetErrorString(e));
+    return EDX_OK;
+}
+
+int edx_debug_raster_triangles(edx_context* c, const edx_mesh* m, uint64_t capacity, int32_t* ints7, float* floats7, uint64_t* count)
+{
+    if (!c || !m || !ints7 || !floats7 || !count || !c->initialized) return fail(c, EDX_ERR_INVALID, "bad argument");
+    if (capacity == 0 || capacity > 0x7FFFFFFFull) return fail(c, EDX_ERR_INVALID, "bad capacity");
+    if (int r = bind(c)) return r;
+    if (int r = finish_frame(c)) return r;
+    DumpRec* d = nullptr;
+    EDX_CUDA(c, cudaMalloc(&d, (size_t)capacity * sizeof(DumpRec)));
+    int rc = EDX_OK;
+    uint32_t n = 0;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        c->lastMesh = m;
+        rc = enqueue_frame(c, m, d, (uint32_t)capacity);
+        if (rc) break;
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = fail(c, EDX_ERR_CUDA, "dump frame failed"); break; }
+        const Counters& k = *c->hostCounters;
+        n = k.nDump;
+        if (k.nClipQueue > c->clipQueueCap) {        // the dump must see every clipped triangle
+            if ((rc = grow(c, c->clipQueue, c->clipQueueCap, k.nClipQueue))) break;
+            continue;
+        }
+        break;
+    }
+    if (!rc && n > capacity) rc = fail(c, EDX_ERR_OVERFLOW, "dump capacity too small");
+    if (!rc) {
+        std::vector<DumpRec> h(n);
+        if (n && cudaMemcpy(h.data(), d, (size_t)n * sizeof(DumpRec), cudaMemcpyDeviceToHost) != cudaSuccess)
+            rc = fail(c, EDX_ERR_CUDA, "dump copy failed");
+        else {
+            std::sort(h.begin(), h.end(), [](const DumpRec& a, const DumpRec& b) { return (uint32_t)a.i[0] < (uint32_t)b.i[0]; });
+            for (uint32_t i = 0; i < n; i++) { memcpy(ints7 + 7 * (size_t)i, h[i].i, 28); memcpy(floats7 + 7 * (size_t)i, h[i].f, 28); }
+            *count = n;
+        }
+    }
+    cudaFree(d);
+    c->framePending = true;              // a regular frame was rendered alongside; let finish_frame vet its queues
+    if (!rc) rc = finish_frame(c);
+    return rc;
+}
+
+int edx_get_derived_state(const edx_context* c, float mvp[16], float eye[3], float light[3])
+{
+    if (!c) return EDX_ERR_INVALID;
+    if (mvp) memcpy(mvp, c->mvp.m, 64);
+    if (eye) memcpy(eye, c->eye, 12);
+    if (light) memcpy(light, c->light, 12);
+    return EDX_OK;
+}
+
+void* edx_device_color(edx_context* c) { return c ? c->color : nullptr; }
+void* edx_device_depth(edx_context* c) { return c ? c->depth : nullptr; }
+
+int edx_set_stream(edx_context* c, void* s)
+{
+    if (!c) return EDX_ERR_INVALID;
+    if (int r = bind(c)) return r;
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s;
+    c->ownStream = false;
+    return EDX_OK;
+}
+
+int edx_timer_begin(edx_context* c)
+{
+    if (!c) return EDX_ERR_INVALID;
+    if (int r = bind(c)) return r;
+    EDX_CUDA(c, cudaEventRecord(c->evTimer[0], c->stream));
+    return EDX_OK;
+}
+
+int edx_timer_end(edx_context* c, float* ms)
+{
+    if (!c || !ms) return EDX_ERR_INVALID;
+    if (int r = bind(c)) return r;
+    EDX_CUDA(c, cudaEventRecord(c->evTimer[1], c->stream));
+    EDX_CUDA(c, cudaEventSynchronize(c->evTimer[1]));
+    EDX_CUDA(c, cudaEventElapsedTime(ms, c->evTimer[0], c->evTimer[1]));
+    return finish_frame(c);
+}
+
+int edx_set_profiling(edx_context* c, int enabled)
+{
+    if (!c) return EDX_ERR_INVALID;
+    c->profiling = enabled ? 1 : 0;
+    return EDX_OK;
+}
+
+int edx_get_stats(edx_context* c, edx_stats* out)
+{
+    if (!c || !out) return EDX_ERR_INVALID;
+    *out = c->stats;
+    return EDX_OK;
+}
+
+int edx_last_launch_count(const edx_context* c) { return c ? c->launches : 0; }
+
+int edx_write_frame_to_file(edx_context* c, const char* path)
+{
+    if (!c || !path) return fail(c, EDX_ERR_INVALID, "null path");
+    const uint8_t* px = edx_get_back_buffer(c);
+    if (!px) return EDX_ERR_CUDA;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(c, EDX_ERR_INVALID, std::string("cannot open ") + path);
+    const uint32_t w = c->width, h = c->height, rowBytes = (w * 3 + 3) & ~3u, size = 54 + rowBytes * h;
+    uint8_t hdr[54] = { 'B', 'M' };
+    auto put32 = [&](int at, uint32_t v) { hdr[at] = v & 255; hdr[at + 1] = (v >> 8) & 255; hdr[at + 2] = (v >> 16) & 255; hdr[at + 3] = (v >> 24) & 255; };
+    put32(2, size); put32(10, 54); put32(14, 40); put32(18, w); put32(22, h);
+    hdr[26] = 1; hdr[28] = 24; put32(34, rowBytes * h);
+    fwrite(hdr, 1, 54, f);
+    std::vector<uint8_t> row(rowBytes, 0);
+    for (uint32_t y = 0; y < h; y++) {          // both BMP and the back buffer are bottom-up
+        const uint8_t* src = px + (size_t)y * w * 4;
+        for (uint32_t x = 0; x < w; x++) { row[3 * x] = src[4 * x + 2]; row[3 * x + 1] = src[4 * x + 1]; row[3 * x + 2] = src[4 * x]; }
+        fwrite(row.data(), 1, rowBytes, f);
+    }
+    fclose(f);
+    return EDX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,184 @@
+"""Python mirror of the reference's renderer-facing API over the C ABI.
+
+Same member names and argument meaning as EDX::RasterRenderer::Renderer (Core/Renderer.h:36-50) and
+Mesh (Utils/Mesh.h:29-68) so parity tests read like calls into the reference. Everything executes in
+the CUDA library; this file only marshals numpy arrays through ctypes.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import EdxError
+
+SHADER_DEPTH_ONLY, SHADER_BLINN_PHONG, SHADER_LAMBERT, SHADER_LAMBERT_ALBEDO = 0, 1, 2, 3
+
+
+def _f32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Mesh:
+    """Utils/Mesh.h: owns the vertex / index buffers (here: device copies)."""
+
+    def __init__(self, renderer, vertices, indices):
+        self._r = renderer
+        v = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 8)
+        i = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+        self.num_verts, self.num_tris = v.shape[0], i.shape[0]
+        h = C.c_void_p()
+        renderer._check(renderer._lib.edx_mesh_create(renderer._h, v.ctypes.data, v.shape[0], i.ctypes.data, i.shape[0], None, C.byref(h)))
+        self._h = h
+
+    def update(self, vertices_ptr, num_verts, indices_ptr, num_tris):
+        """Re-upload from raw host pointers (e.g. pinned torch tensors); asynchronous."""
+        self._r._check(self._r._lib.edx_mesh_update(self._r._h, self._h, vertices_ptr, num_verts, indices_ptr, num_tris))
+        self.num_verts, self.num_tris = num_verts, num_tris
+
+    def Release(self):
+        if self._h:
+            self._r._lib.edx_mesh_destroy(self._r._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Release()
+        except Exception:
+            pass
+
+
+class Renderer:
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.edx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise EdxError(rc, "edx_create failed (no B200 / CUDA device?)")
+        self._h = h
+        self.width = self.height = 0
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EdxError(rc, self._lib.edx_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._lib.edx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- Core/Renderer.h:40-50 -------------------------------------------------------------
+    def Initialize(self, width, height):
+        self._check(self._lib.edx_initialize(self._h, width, height))
+        self.width, self.height = int(width), int(height)
+
+    def Resize(self, width, height):
+        self._check(self._lib.edx_resize(self._h, width, height))
+        self.width, self.height = int(width), int(height)
+
+    def SetTransform(self, model_view, proj, to_raster):
+        mv, p, r = (np.ascontiguousarray(m, dtype=np.float32).reshape(16) for m in (model_view, proj, to_raster))
+        self._check(self._lib.edx_set_transform(self._h, _f32(mv), _f32(p), _f32(r)))
+
+    def RenderMesh(self, mesh):
+        self._check(self._lib.edx_render_mesh(self._h, mesh._h))
+
+    def GetBackBuffer(self):
+        p = self._lib.edx_get_back_buffer(self._h)
+        if not p:
+            raise EdxError(-2, self._lib.edx_last_error(self._h).decode())
+        return np.ctypeslib.as_array(p, shape=(self.height, self.width, 4))
+
+    def SetMSAAMode(self, log2):
+        self._check(self._lib.edx_set_msaa_mode(self._h, log2))
+
+    def SetTextureFilter(self, f):
+        self._check(self._lib.edx_set_texture_filter(self._h, f))
+
+    def SetHierarchicalRasterize(self, on):
+        self._check(self._lib.edx_set_hierarchical_rasterize(self._h, 1 if on else 0))
+
+    def WriteFrameToFile(self, path):
+        self._check(self._lib.edx_write_frame_to_file(self._h, path.encode()))
+
+    # --- extensions -------------------------------------------------------------------------
+    def SetPixelShader(self, shader):
+        self._check(self._lib.edx_set_pixel_shader(self._h, shader))
+
+    def SetAlbedo(self, r, g, b):
+        self._check(self._lib.edx_set_albedo(self._h, r, g, b))
+
+    def CreateMesh(self, vertices, indices):
+        return Mesh(self, vertices, indices)
+
+    def Synchronize(self):
+        self._check(self._lib.edx_synchronize(self._h))
+
+    def GetDepthBuffer(self):
+        out = np.empty((self.height, self.width), np.float32)
+        self._check(self._lib.edx_read_depth(self._h, _f32(out)))
+        return out
+
+    def SetCaptureIds(self, on):
+        self._check(self._lib.edx_set_capture_ids(self._h, 1 if on else 0))
+
+    def GetWinnerIds(self):
+        out = np.empty((self.height, self.width), np.uint32)
+        self._check(self._lib.edx_read_winner_ids(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return out
+
+    def DebugClipVertices(self, mesh):
+        out = np.empty((mesh.num_verts, 4), np.float32)
+        self._check(self._lib.edx_debug_clip_vertices(self._h, mesh._h, _f32(out)))
+        return out
+
+    def DebugRasterTriangles(self, mesh, capacity=None):
+        cap = int(capacity or (mesh.num_tris * 7 + 16))
+        ints = np.zeros((cap, 7), np.int32)
+        flts = np.zeros((cap, 7), np.float32)
+        n = C.c_uint64(0)
+        self._check(self._lib.edx_debug_raster_triangles(self._h, mesh._h, cap, ints.ctypes.data_as(C.POINTER(C.c_int32)), _f32(flts), C.byref(n)))
+        return ints[:n.value], flts[:n.value]
+
+    def DerivedState(self):
+        mvp, eye, light = np.zeros(16, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self._check(self._lib.edx_get_derived_state(self._h, _f32(mvp), _f32(eye), _f32(light)))
+        return mvp.reshape(4, 4), eye, light
+
+    def DeviceColorPtr(self):
+        return self._lib.edx_device_color(self._h)
+
+    def DeviceDepthPtr(self):
+        return self._lib.edx_device_depth(self._h)
+
+    def SetStream(self, cuda_stream_ptr):
+        self._check(self._lib.edx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def TimerBegin(self):
+        self._check(self._lib.edx_timer_begin(self._h))
+
+    def TimerEnd(self):
+        ms = C.c_float(0)
+        self._check(self._lib.edx_timer_end(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def SetProfiling(self, on):
+        self._check(self._lib.edx_set_profiling(self._h, 1 if on else 0))
+
+    def GetStats(self):
+        s = _lib.Stats()
+        self._check(self._lib.edx_get_stats(self._h, C.byref(s)))
+        return {"submitted_tris": s.submitted_tris, "clipped_tris": s.clipped_tris, "binned_tris": s.binned_tris,
+                "clip_records": s.clip_records, "regrow_count": s.regrow_count,
+                "stage_ms": {"geom": s.stage_ms[0], "clip": s.stage_ms[1], "tile": s.stage_ms[2], "total": s.stage_ms[3]}}
+
+    def SetOption(self, name, value):
+        self._check(self._lib.edx_set_option(self._h, name.encode(), int(value)))
+
+    def LastLaunchCount(self):
+        return int(self._lib.edx_last_launch_count(self._h))

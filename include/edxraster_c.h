@@ -1,0 +1,147 @@
+/* edxraster_c.h — C ABI of the B200-native EDXRaster raster hot path.
+ *
+ * The reference has no FFI: its boundary is the C++ class EDX::RasterRenderer::Renderer in a static
+ * library (EDXRaster/Core/Renderer.h:36-50) fed by Mesh / IVertexBuffer / IndexBuffer
+ * (EDXRaster/Utils/Mesh.h:29-68, Utils/InputBuffer.h:43-66,148-194). Each entry point below names the
+ * reference member it replaces. The C++ classes with the reference's own names live in
+ * include/edxraster/Renderer.h and forward here; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns an edx_status (0 = ok, <0 = error) unless
+ *    it returns a pointer; edx_last_error() gives the message. Nothing aborts or throws.
+ *  - matrices: 16 floats, row-major, column-vector convention (clip = Proj * ModelView * p), exactly
+ *    what Renderer::SetTransform receives (Core/Renderer.cpp:85-92).
+ *  - vertices: the reference's 32-byte submission format, position(3) normal(3) texcoord(2) floats
+ *    (Utils/InputBuffer.h:16-28); indices: uint32 x 3 per triangle (InputBuffer.h:151,175-179).
+ *  - frame buffer: RGBA8, x fastest, row 0 = BOTTOM scanline (Core/FrameBuffer.cpp:41, Main.cpp:75).
+ *    Depth and winner-id read-backs use the same bottom-up order.
+ *  - one context per GPU; a context is not thread-safe, distinct contexts are independent.
+ *  - there is NO CPU fallback: every call fails with EDX_ERR_NO_DEVICE / EDX_ERR_CUDA without a GPU.
+ */
+#ifndef EDXRASTER_C_H
+#define EDXRASTER_C_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct edx_context edx_context;
+typedef struct edx_mesh edx_mesh;
+
+typedef enum edx_status {
+    EDX_OK = 0,
+    EDX_ERR_INVALID = -1,      /* bad argument */
+    EDX_ERR_CUDA = -2,         /* CUDA runtime error, see edx_last_error */
+    EDX_ERR_OOM = -3,          /* device or pinned-host allocation failed */
+    EDX_ERR_OVERFLOW = -4,     /* an internal queue could not be grown */
+    EDX_ERR_UNSUPPORTED = -5,  /* feature outside the round's scope (e.g. MSAA > 1x) */
+    EDX_ERR_NO_DEVICE = -6     /* no CUDA device / wrong architecture */
+} edx_status;
+
+/* Pixel shaders. The reference hard-codes LambertianAlbedoPixelShader (Core/Renderer.cpp:41) and has
+ * no setter; the selector is our one API extension on the render path. */
+typedef enum edx_shader {
+    EDX_SHADER_DEPTH_ONLY = 0,      /* depth test only, colour buffer left cleared */
+    EDX_SHADER_BLINN_PHONG = 1,     /* Core/Shader.h:246-282 */
+    EDX_SHADER_LAMBERT = 2,         /* Core/Shader.h:185-207 */
+    EDX_SHADER_LAMBERT_ALBEDO = 3   /* Core/Shader.h:209-244 with the constant texture of Utils/Mesh.cpp:48,67 */
+} edx_shader;
+
+typedef struct edx_stats {
+    uint64_t submitted_tris;   /* triangles in the last RenderMesh call */
+    uint64_t clipped_tris;     /* triangles that went through the polygon clipper */
+    uint64_t binned_tris;      /* post-setup triangles routed to the tile (large-triangle) path */
+    uint64_t clip_records;     /* fan triangles emitted by the clipper */
+    uint32_t regrow_count;     /* times an internal queue was grown and the frame re-run */
+    uint32_t reserved;
+    float    stage_ms[8];      /* valid with profiling on: geom, clip, tile, total; rest 0 */
+} edx_stats;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* new Renderer (RealtimeViewer/Main.cpp:37); `device` = CUDA ordinal. */
+int edx_create(int device, edx_context** out);
+/* Renderer::~Renderer (Core/Renderer.cpp:365-371) */
+void edx_destroy(edx_context* ctx);
+const char* edx_last_error(const edx_context* ctx);
+/* version string and the architecture the kernels were built for ("sm_100a") */
+const char* edx_version(void);
+
+/* Renderer::Initialize (Core/Renderer.cpp:22-62) / Renderer::Resize (:64-83) */
+int edx_initialize(edx_context* ctx, uint32_t width, uint32_t height);
+int edx_resize(edx_context* ctx, uint32_t width, uint32_t height);
+/* Renderer::SetTransform (Core/Renderer.cpp:85-92). Derives MVP = proj * model_view and the
+ * model-view inverse exactly as the reference does. */
+int edx_set_transform(edx_context* ctx, const float model_view[16], const float proj[16], const float to_raster[16]);
+/* Renderer::SetMSAAMode (Core/Renderer.cpp:94-98). Only 0 (1x) is implemented this round. */
+int edx_set_msaa_mode(edx_context* ctx, int sample_count_log2);
+/* Renderer::SetTextureFilter (Core/Renderer.h:48). Stored; no textured shader this round. */
+int edx_set_texture_filter(edx_context* ctx, int filter);
+/* Renderer::SetHierarchicalRasterize (Core/Renderer.h:49). Off = per-pixel tests only; same image. */
+int edx_set_hierarchical_rasterize(edx_context* ctx, int enabled);
+/* Renderer::SetWriteFrames / WriteFrameToFile (Core/Renderer.h:50, Renderer.cpp:352-358): 24-bit BMP. */
+int edx_write_frame_to_file(edx_context* ctx, const char* path);
+/* extension */
+int edx_set_pixel_shader(edx_context* ctx, int shader);
+int edx_set_albedo(edx_context* ctx, float r, float g, float b);
+
+/* ---- meshes -------------------------------------------------------------------------------- */
+/* CreateVertexBuffer + CreateIndexBuffer (Utils/InputBuffer.h:136-146,196-205): copies the caller's
+ * host arrays to the device (SoA streams). tex_ids may be NULL (Mesh::GetTextureIds, Mesh.h:56-59). */
+int edx_mesh_create(edx_context* ctx, const void* vertices_pnt32, uint32_t vertex_count,
+                    const uint32_t* indices, uint32_t triangle_count, const uint32_t* tex_ids, edx_mesh** out);
+/* Re-upload into an existing mesh of the same or smaller size (streaming geometry). */
+int edx_mesh_update(edx_context* ctx, edx_mesh* mesh, const void* vertices_pnt32, uint32_t vertex_count,
+                    const uint32_t* indices, uint32_t triangle_count);
+/* Mesh::Release (Utils/Mesh.cpp:72-78) */
+int edx_mesh_destroy(edx_context* ctx, edx_mesh* mesh);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+/* Renderer::RenderMesh (Core/Renderer.cpp:100-118): clear, vertex transform, clip + setup, raster,
+ * depth test, shade, frame-buffer update. Asynchronous on the context's stream. */
+int edx_render_mesh(edx_context* ctx, const edx_mesh* mesh);
+/* Renderer::GetBackBuffer (Core/Renderer.cpp:360-363): waits for the frame, copies it to a pinned
+ * host mirror and returns a borrowed pointer valid until the next RenderMesh / Resize. NULL on error. */
+const uint8_t* edx_get_back_buffer(edx_context* ctx);
+/* wait for all queued work on the context's stream */
+int edx_synchronize(edx_context* ctx);
+
+/* ---- read-backs for parity (ours; the reference keeps depth private, FrameBuffer.h:20) ------ */
+int edx_read_depth(edx_context* ctx, float* out_w_times_h);
+/* per pixel: submitted-triangle index * 8 + fan index of the fragment that owns it, 0xFFFFFFFF = none.
+ * Needs edx_set_capture_ids(ctx, 1) before the frame. */
+int edx_set_capture_ids(edx_context* ctx, int enabled);
+int edx_read_winner_ids(edx_context* ctx, uint32_t* out_w_times_h);
+/* stage dumps: clip-space vertices (vertex_count x 4 floats) of stage a1, Core/Renderer.cpp:120-127 */
+int edx_debug_clip_vertices(edx_context* ctx, const edx_mesh* mesh, float* out_xyzw);
+/* post-setup triangles (stages a3-a6) sorted by prim id; ints: prim,v0x,v0y,v1x,v1y,v2x,v2y;
+ * floats: z0,z1,z2,invW0,invW1,invW2,invDet. Returns the count through *count (<= capacity). */
+int edx_debug_raster_triangles(edx_context* ctx, const edx_mesh* mesh, uint64_t capacity,
+                               int32_t* ints7, float* floats7, uint64_t* count);
+/* MVP, eye position and normalised light direction the shaders will use */
+int edx_get_derived_state(const edx_context* ctx, float mvp[16], float eye[3], float light[3]);
+
+/* ---- device-side access and measurement ----------------------------------------------------- */
+/* device pointers of the current colour (RGBA8) / depth (f32) buffers, for NCCL gathers without a
+ * host round trip */
+void* edx_device_color(edx_context* ctx);
+void* edx_device_depth(edx_context* ctx);
+/* use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own */
+int edx_set_stream(edx_context* ctx, void* cuda_stream);
+/* CUDA-event timing on the context's stream: begin, N x render, end -> elapsed ms (synchronises) */
+int edx_timer_begin(edx_context* ctx);
+int edx_timer_end(edx_context* ctx, float* elapsed_ms);
+/* per-stage CUDA events inside RenderMesh (adds event records; off by default) */
+int edx_set_profiling(edx_context* ctx, int enabled);
+int edx_get_stats(edx_context* ctx, edx_stats* out);
+/* tuning knobs: "small_max" (largest pixel-centre bbox side rasterised directly, default 8),
+ * "hiz" (hierarchical-Z culling of the tile path, default 1) */
+int edx_set_option(edx_context* ctx, const char* name, int value);
+/* number of kernel launches issued by the last RenderMesh (for bench.py's gpu_launches) */
+int edx_last_launch_count(const edx_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDXRASTER_C_H */
