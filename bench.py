@@ -1,0 +1,489 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native EDXRaster raster hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU reference arm (oracle on host cores)
+
+Workload (BASELINE.json configs[1], "C2"): 1,000,000 random <=4-px triangles at 1920x1080, depth test
+only, fixed submission order. One step = one frame of the hot path (Renderer::RenderMesh,
+/root/reference/EDXRaster/Core/Renderer.cpp:100-118) per GPU. Metric: Mtris/s (submitted triangles per
+second, whole job); Gpix/s and frames/s ride along as extra keys.
+
+Timing: CUDA events on the launching stream around exactly K steps, barrier + synchronize on both
+sides, max over ranks. Inputs are made larger than L2 by rotating over 4 device copies of the mesh
+(4 x 108 MB of SoA streams > 126 MB L2), so every frame reads its geometry from HBM. At N > 1 the
+frames are independent (weak scaling: one frame per rank per step) and the finished depth buffers
+are gathered to rank 0 over NCCL, overlapped with the next frame's render.
+
+Rank 0 prints ONE JSON line on stdout; everything else goes to stderr.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOADS = {
+    # name: (description, algorithmic bytes per frame as a function of (nv, nt, w, h), shaded)
+    "C1": "C1: UV sphere 100x100 (20,000 tris), 1280x720, Blinn-Phong + depth",
+    "C2": "C2: 1,000,000 random <=4px triangles, 1920x1080, depth test only, fixed order",
+    "C3": "C3: 2,000 screen-covering triangles, 3840x2160, Blinn-Phong, perspective-correct interpolation",
+    "C4": "C4: 10,000,000-triangle displaced grid, 1920x1080, near/side-plane clipping, Blinn-Phong",
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def algorithmic_bytes(nv, nt, w, h, shaded):
+    """vertex attributes once, indices once, frame buffer written once."""
+    return (32 * nv + 12 * nt + 8 * w * h) if shaded else (12 * nv + 12 * nt + 4 * w * h)
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_scene(name, scale):
+    from edxraster_b200 import scenes
+    return scenes.by_name(name, scale)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: NVML sampler thread (the recipe's nvidia-smi line is too coarse for millisecond regions)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples = []          # (t, sm_mhz, reasons_bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # honour CUDA_VISIBLE_DEVICES remapping
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[index])
+                except Exception:
+                    phys = index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:       # pragma: no cover
+            log("clock sampler unavailable:", e)
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+
+    def summary(self, t0, t1):
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "window": "unavailable"}
+        nv = self.nv
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed"
+        if len(inside) < 3:
+            inside, window = self.samples, "warmup+timed"
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+            getattr(nv, "nvmlClocksEventReasonApplicationsClocksSetting", 0x2): "applications_clocks_setting",
+        }
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        reasons = sorted(v for k, v in names.items() if k and (bits & k))
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(inside), "window": window}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference's SSE path on all host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_frames(scene, threads, frames, warm, timing=True, tri_limit=None):
+    from oracle import orc
+    orc.build()
+    o = orc.Oracle(scene.width, scene.height, threads, timing=timing)
+    o.set_transform(scene.mv, scene.proj, scene.raster)
+    o.set_shader(scene.shader)
+    idx = scene.indices if tri_limit is None else scene.indices[:tri_limit]
+    for _ in range(warm):
+        o.render(scene.vertices, idx)
+    times = []
+    for _ in range(frames):
+        t = time.perf_counter()
+        o.render(scene.vertices, idx)
+        times.append(time.perf_counter() - t)
+    th = o.threads
+    st = o.stats()
+    o.close()
+    return times, th, int(idx.shape[0]), st
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    scene = make_scene(args.workload, args.scale)
+    nt = scene.num_tris
+    # calibrate: one full frame, then bound the per-step sample so K+W steps end within ~2 minutes
+    t_probe, threads, _, _ = cpu_frames(scene, 0, 1, 1)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    limit = None
+    if t_probe[0] > budget:
+        limit = max(1000, int(nt * budget / t_probe[0]))
+    times, threads, used, st = cpu_frames(scene, 0, args.steps, min(args.warmup, 3), tri_limit=limit)
+    total = sum(times)
+    value = used * len(times) / total / 1e6
+    sample = ("full frames (%d triangles each)" % used) if limit is None else \
+        ("first %d of %d triangles per step (bounded sample, same resolution and state)" % (used, nt))
+    line = {
+        "impl": "reference", "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 depth / i32 28.4 fixed-point coverage",
+        "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "triangles": nt, "resolution": [scene.width, scene.height]},
+        "frames_per_s": len(times) / total, "gpix_per_s": scene.width * scene.height * len(times) / total / 1e9,
+        "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "CPU restatement of the reference SSE path (oracle/, timing build: rsqrtps+NR, OpenMP); "
+                                 "the reference itself cannot be built offline (SURVEY.md F1/F2)"},
+        "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def time_frames(r, meshes, frames, warm):
+    """Device time of `frames` back-to-back frames (CUDA events on the context's stream)."""
+    for i in range(warm):
+        r.RenderMesh(meshes[i % len(meshes)])
+    r.Synchronize()
+    r.TimerBegin()
+    for i in range(frames):
+        r.RenderMesh(meshes[i % len(meshes)])
+    return r.TimerEnd()
+
+
+def secondary_config(name, device, peak):
+    """Quick device-resident measurement of another BASELINE config (rank 0, N=1 only)."""
+    from edxraster_b200 import renderer as R
+    t0 = time.time()
+    sc = make_scene(name, 1.0)
+    r = R.Renderer(device)
+    r.Initialize(sc.width, sc.height)
+    r.SetTransform(sc.mv, sc.proj, sc.raster)
+    r.SetPixelShader(sc.shader)
+    mesh_bytes = sc.num_verts * 32 + sc.num_tris * 16
+    copies = max(1, min(4, int(600e6 // max(mesh_bytes, 1))))
+    meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]
+    frames = 30 if sc.num_tris < 5_000_000 else 10
+    ms = time_frames(r, meshes, frames, 3) / frames
+    r.SetProfiling(True)
+    stage = {"geom": 0.0, "clip": 0.0, "tile": 0.0}
+    for i in range(5):
+        r.RenderMesh(meshes[i % copies])
+        r.Synchronize()
+        st = r.GetStats()
+        for k in stage:
+            stage[k] += st["stage_ms"][k] / 5
+    r.SetProfiling(False)
+    st = r.GetStats()
+    ab = algorithmic_bytes(sc.num_verts, sc.num_tris, sc.width, sc.height, sc.shader != 0)
+    out = {"workload": WORKLOADS[name], "ms_per_frame": ms, "mtris_per_s": sc.num_tris / ms / 1e3,
+           "gpix_per_s": sc.width * sc.height / ms / 1e6, "frames_per_s": 1000.0 / ms,
+           "algorithmic_bytes": ab, "hbm_frac_whole_frame": ab / (ms * 1e-3) / 1e9 / peak,
+           "fb_only_frac": (8 if sc.shader != 0 else 4) * sc.width * sc.height / (ms * 1e-3) / 1e9 / peak,
+           "stage_ms": stage, "binned_tris": st["binned_tris"], "clipped_tris": st["clipped_tris"],
+           "l2": "rotating %d mesh copies" % copies}
+    for m in meshes:
+        m.Release()
+    r.close()
+    log("secondary %s: %.3f ms/frame (%.1fs incl. generation)" % (name, ms, time.time() - t0))
+    return out
+
+
+def ours_arm(args):
+    import torch
+    import torch.distributed as dist
+    from edxraster_b200 import renderer as R
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    peak, peak_src = measured_hbm_peak()
+
+    sc = make_scene(args.workload, args.scale)
+    W, H, nt, nv = sc.width, sc.height, sc.num_tris, sc.num_verts
+    shaded = sc.shader != 0
+    stream = torch.cuda.Stream(device=dev)
+    r = R.Renderer(local)
+    r.SetStream(stream.cuda_stream)
+    r.Initialize(W, H)
+    r.SetTransform(sc.mv, sc.proj, sc.raster)
+    r.SetPixelShader(sc.shader)
+    copies = 4
+    meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]
+
+    # render targets as torch tensors so NCCL can send them without a copy (double-buffered)
+    tgt_color = [torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
+    tgt_depth = [torch.zeros((H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+    result = tgt_color if shaded else tgt_depth
+    recv = None
+    if world > 1 and rank == 0:
+        recv = [[torch.empty_like(result[0]) for _ in range(world)] for _ in range(2)]
+
+    def step(i, works):
+        b = i & 1
+        if world > 1 and works[b] is not None:
+            works[b].wait()                       # the gather that still reads target b (stream-level wait)
+            works[b] = None
+        r.SetRenderTarget(tgt_color[b].data_ptr(), tgt_depth[b].data_ptr())
+        r.SetTransform(sc.mv, sc.proj, sc.raster)
+        r.RenderMesh(meshes[i % copies])
+        if world > 1:
+            works[b] = dist.gather(result[b], recv[b] if rank == 0 else None, dst=0, async_op=True)
+
+    def drain(works):
+        for b in (0, 1):
+            if works[b] is not None:
+                works[b].wait()
+                works[b] = None
+
+    sampler = ClockSampler(local)
+    with torch.cuda.stream(stream):
+        works = [None, None]
+        # warm-up: at least W steps and at least ~0.3 s so clocks settle
+        t_w = time.perf_counter()
+        i = 0
+        while i < max(args.warmup, 3) or time.perf_counter() - t_w < 0.3:
+            step(i, works)
+            i += 1
+            if i % 64 == 0:
+                drain(works)
+                r.Synchronize()
+        drain(works)
+        r.Synchronize()
+        sampler.start()
+        for j in range(32):                       # keep the GPU busy while the sampler spins up
+            step(j, works)
+        drain(works)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        for i in range(args.steps):
+            step(i, works)
+        drain(works)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+        sampler.stop()
+        ms_total = ev0.elapsed_time(ev1)
+        r.Synchronize()                           # vets the internal queues of the last frame
+        launches_per_step = r.LastLaunchCount()
+        if world > 1:
+            t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+        ms_step = ms_total / args.steps
+        value = world * nt / ms_step / 1e3        # Mtris/s, whole job
+
+        # ---- end-to-end through the C ABI with HOST buffers: upload mesh, render, read result back ----
+        hv = torch.from_numpy(np.ascontiguousarray(sc.vertices)).pin_memory()
+        hi = torch.from_numpy(np.ascontiguousarray(sc.indices).view(np.int32)).pin_memory()
+        hout = torch.empty((H, W), dtype=torch.float32).pin_memory() if not shaded else None
+        r.SetRenderTarget(0, 0)
+        e2e_steps = max(3, min(args.steps, 20))
+
+        def e2e_step(i, upload):
+            if upload:
+                meshes[i % copies].update(hv.data_ptr(), nv, hi.data_ptr(), nt)
+            r.SetTransform(sc.mv, sc.proj, sc.raster)
+            r.RenderMesh(meshes[i % copies])
+            if shaded:
+                r.GetBackBuffer()                 # D2H into the pinned mirror
+            else:
+                r.ReadDepthInto(hout.data_ptr())
+
+        e2e = {}
+        for label, upload in (("stream", True), ("resident", False)):
+            for i in range(3):
+                e2e_step(i, upload)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            for i in range(e2e_steps):
+                e2e_step(i, upload)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            e2e[label] = ms / e2e_steps
+        h2d = nv * 32 + nt * 12 + 3 * 64
+        d2h = W * H * 4
+
+        # ---- per-kernel device time (CUDA events between the kernels, same stream) ----
+        r.SetProfiling(True)
+        stage = {"geom": 0.0, "clip": 0.0, "tile": 0.0, "total": 0.0}
+        prof_frames = max(5, min(args.steps, 20))
+        for i in range(prof_frames):
+            r.RenderMesh(meshes[i % copies])
+            r.Synchronize()
+            st = r.GetStats()
+            for k in stage:
+                stage[k] += st["stage_ms"][k] / prof_frames
+        r.SetProfiling(False)
+        stats = r.GetStats()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    ab = algorithmic_bytes(nv, nt, W, H, shaded)
+    dom = max(("geom", "clip", "tile"), key=lambda k: stage[k])
+    dom_ms = stage[dom]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload, {}).get(dom + "_kernel")
+        except Exception:
+            traffic = None
+    achieved = ab / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    line = {
+        "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 depth / i32 28.4 fixed-point coverage", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "triangles": nt, "vertices": nv, "resolution": [W, H],
+                   "frames_per_step_per_gpu": 1,
+                   "l2": "inputs larger than L2: round-robin over %d device copies of the mesh (%d MB of SoA streams)" % (copies, copies * (nv * 32 + nt * 12) // 1000000),
+                   "gather": "NCCL gather of finished %s buffers to rank 0, overlapped with the next frame" % ("colour" if shaded else "depth") if world > 1 else "none (1 GPU)"},
+        "frames_per_s": world * 1000.0 / ms_step, "gpix_per_s": world * W * H / ms_step / 1e6,
+        "clocks": sampler.summary(t0, t1),
+        "e2e": {"value": world * nt / e2e["stream"] / 1e3, "unit": "Mtris/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e["stream"],
+                "what": "edx_mesh_update (pinned host vertices+indices -> device) + edx_set_transform + edx_render_mesh + read-back of the frame to pinned host, every step",
+                "resident_mesh_value": world * nt / e2e["resident"] / 1e3, "resident_mesh_ms_per_step": e2e["resident"],
+                "resident_mesh_what": "mesh uploaded once (the reference viewer's usage, Main.cpp:42,71-75); per step: transform in, render, frame read back to host"},
+        "gpu_launches": launches_per_step * args.steps,
+        "kernels_per_step": {"geom_kernel": 1, "clip_kernel": 1, "tile_kernel": 1},
+        "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": ab, "kernel_ms": dom_ms,
+                     "stage_ms": stage, "whole_frame_frac": ab / (ms_step * 1e-3) / 1e9 / peak,
+                     "fb_only_frac": (8 if shaded else 4) * W * H / (ms_step * 1e-3) / 1e9 / peak},
+        "path_stats": {"binned_tris": stats["binned_tris"], "clipped_tris": stats["clipped_tris"], "regrows": stats["regrow_count"]},
+    }
+    for m in meshes:
+        m.Release()
+    r.close()
+
+    if world == 1:
+        # CPU baseline on this box's host cores: bounded sample of the same workload
+        try:
+            times, threads, used, _ = cpu_frames(sc, 0, 3, 1)
+            v = used * len(times) / sum(times) / 1e6
+            line["cpu_baseline"] = {"value": v, "unit": "Mtris/s", "cores": threads, "kind": "port",
+                                    "sample": "3 full frames of the same workload after 1 warm-up (%.2f s each)" % (sum(times) / len(times)),
+                                    "note": "oracle/ timing build (CPU restatement of the reference SSE path; the reference cannot be built offline)"}
+        except Exception as e:       # the oracle is only a reported baseline
+            line["cpu_baseline"] = {"value": None, "error": str(e)}
+        if not args.no_extra:
+            also = {}
+            for name in ("C1", "C3", "C4"):
+                if name == args.workload:
+                    continue
+                try:
+                    also[name] = secondary_config(name, local, peak)
+                except Exception as e:
+                    also[name] = {"error": str(e)}
+            line["other_configs"] = also
+    else:
+        dist.barrier()
+        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="triangle-count scale (debug only; 1.0 = BASELINE size)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary C1/C3/C4 measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    if args.gpus > 1 and "RANK" not in os.environ:
+        # convenience: self-launch one process per GPU
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return ours_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -42,6 +42,7 @@ struct edx_context {
 
     unsigned long long* keys = nullptr;
     uchar4* color = nullptr; float* depth = nullptr; uint32_t* ids = nullptr;
+    uchar4* extColor = nullptr; float* extDepth = nullptr;      // caller-owned render targets (optional)
     BigRec* big = nullptr; uint32_t bigCap = 0;
     uint32_t* clipQueue = nullptr; uint32_t clipQueueCap = 0;
     ClipRec* clipRecs = nullptr; uint32_t clipRecCap = 0;
@@ -136,7 +137,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.clipRecs = c->clipRecs; P.clipRecCap = c->clipRecCap;
     P.clipSlot = m->clipSlot;
     P.counters = c->counters;
-    P.color = c->color; P.depth = c->depth; P.ids = c->ids;
+    P.color = c->extColor ? c->extColor : c->color; P.depth = c->extDepth ? c->extDepth : c->depth; P.ids = c->ids;
 }
 
 // One frame on the stream. dumpBuf != nullptr routes post-setup triangles to the debug dump as well.
@@ -153,7 +154,7 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
 
     if (c->shader == EDX_SHADER_DEPTH_ONLY && c->colorDirty) {
         // depth-only frames never touch colour: restore the cleared state once (FrameBuffer.cpp:91-95)
-        EDX_CUDA(c, cudaMemsetAsync(c->color, 0, (size_t)c->width * c->height * 4, c->stream));
+        EDX_CUDA(c, cudaMemsetAsync(c->extColor ? c->extColor : c->color, 0, (size_t)c->width * c->height * 4, c->stream));
         c->colorDirty = false;
     }
     if (c->shader != EDX_SHADER_DEPTH_ONLY) c->colorDirty = true;
@@ -289,8 +290,8 @@ int edx_initialize(edx_context* c, uint32_t width, uint32_t height)
 {
     if (!c || width == 0 || height == 0 || width > 16384 || height > 16384) return fail(c, EDX_ERR_INVALID, "bad size");
     // 28.4 edge functions are int32: (16 W)(16 H) must stay below 2^31
-    if ((uint64_t)(width * 16ull + 512) * (uint64_t)(height * 16ull + 512) >= (1ull << 31))
-        return fail(c, EDX_ERR_UNSUPPORTED, "resolution exceeds the int32 range of the 28.4 edge functions (max ~3840x2160)");
+    if ((uint64_t)(width * 16ull) * (uint64_t)(height * 16ull) >= (1ull << 31))
+        return fail(c, EDX_ERR_UNSUPPORTED, "resolution exceeds the int32 range of the 28.4 edge functions (16W * 16H must stay below 2^31)");
     if (int r = bind(c)) return r;
     EDX_CUDA(c, cudaStreamSynchronize(c->stream));
     // RenderStates::DefaultSettings (RenderStates.h:55-61)
@@ -305,8 +306,8 @@ int edx_resize(edx_context* c, uint32_t width, uint32_t height)
 {
     if (!c || !c->initialized) return fail(c, EDX_ERR_INVALID, "not initialised");
     if (width == 0 || height == 0 || width > 16384 || height > 16384) return fail(c, EDX_ERR_INVALID, "bad size");
-    if ((uint64_t)(width * 16ull + 512) * (uint64_t)(height * 16ull + 512) >= (1ull << 31))
-        return fail(c, EDX_ERR_UNSUPPORTED, "resolution exceeds the int32 range of the 28.4 edge functions");
+    if ((uint64_t)(width * 16ull) * (uint64_t)(height * 16ull) >= (1ull << 31))
+        return fail(c, EDX_ERR_UNSUPPORTED, "resolution exceeds the int32 range of the 28.4 edge functions (16W * 16H must stay below 2^31)");
     if (int r = bind(c)) return r;
     EDX_CUDA(c, cudaStreamSynchronize(c->stream));
     c->framePending = false;
@@ -432,7 +433,7 @@ const uint8_t* edx_get_back_buffer(edx_context* c)
 {
     if (!c || !c->initialized) return nullptr;
     if (bind(c) || finish_frame(c)) return nullptr;
-    if (cudaMemcpyAsync(c->hostColor, c->color, c->hostColorBytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+    if (cudaMemcpyAsync(c->hostColor, c->extColor ? c->extColor : c->color, c->hostColorBytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
         cudaStreamSynchronize(c->stream) != cudaSuccess) {
         c->error = "frame read-back failed";
         return nullptr;
@@ -445,7 +446,7 @@ int edx_read_depth(edx_context* c, float* out)
     if (!c || !out || !c->initialized) return fail(c, EDX_ERR_INVALID, "bad argument");
     if (int r = bind(c)) return r;
     if (int r = finish_frame(c)) return r;
-    EDX_CUDA(c, cudaMemcpyAsync(out, c->depth, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToHost, c->stream));
+    EDX_CUDA(c, cudaMemcpyAsync(out, c->extDepth ? c->extDepth : c->depth, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToHost, c->stream));
     EDX_CUDA(c, cudaStreamSynchronize(c->stream));
     return EDX_OK;
 }
@@ -535,8 +536,16 @@ int edx_get_derived_state(const edx_context* c, float mvp[16], float eye[3], flo
     return EDX_OK;
 }
 
-void* edx_device_color(edx_context* c) { return c ? c->color : nullptr; }
-void* edx_device_depth(edx_context* c) { return c ? c->depth : nullptr; }
+void* edx_device_color(edx_context* c) { return c ? (c->extColor ? c->extColor : c->color) : nullptr; }
+void* edx_device_depth(edx_context* c) { return c ? (c->extDepth ? c->extDepth : c->depth) : nullptr; }
+
+int edx_set_render_target(edx_context* c, void* color, void* depth)
+{
+    if (!c) return EDX_ERR_INVALID;
+    c->extColor = (uchar4*)color;
+    c->extDepth = (float*)depth;
+    return EDX_OK;
+}
 
 int edx_set_stream(edx_context* c, void* s)
 {

@@ -1,0 +1,49 @@
+"""Frame-parallel multi-GPU farm: independent camera views are dealt round-robin to
+ranks, each rank renders its views on its own GPU, and finished frame buffers are gathered to rank 0.
+
+One process per GPU over torch.distributed. NCCL (NVLink/NVSwitch) carries only the gather of finished
+frames — the render path itself has no collective. The same code runs on gloo with CPU tensors, which
+is how the host logic is tested without GPUs.
+"""
+import torch
+import torch.distributed as dist
+
+
+def views_of_rank(num_views, world, rank):
+    """View i is rendered by rank i % world."""
+    return list(range(rank, num_views, world))
+
+
+def gather_frames(local_frames, num_views, dst=0):
+    """Collect every rank's frames on `dst` in view order.
+
+    local_frames: tensor [n_local, H, W, C] (or [n_local, H, W]) holding this rank's views in the
+    order of views_of_rank(). Returns a tensor [num_views, ...] on dst, None elsewhere.
+    """
+    world, rank = dist.get_world_size(), dist.get_rank()
+    per_rank = (num_views + world - 1) // world
+    shape = (per_rank,) + tuple(local_frames.shape[1:])
+    padded = local_frames.new_zeros(shape)
+    padded[: local_frames.shape[0]] = local_frames
+    bufs = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+    dist.gather(padded, bufs, dst=dst)
+    if rank != dst:
+        return None
+    out = local_frames.new_zeros((num_views,) + tuple(local_frames.shape[1:]))
+    for r in range(world):
+        ids = views_of_rank(num_views, world, r)
+        out[ids] = bufs[r][: len(ids)]
+    return out
+
+
+def render_views(renderer, mesh, views, out_frames, shaded=True):
+    """Render `views` (list of (model_view, proj, raster)) into out_frames[k] (device tensors)."""
+    for k, (mv, p, r) in enumerate(views):
+        if shaded:
+            renderer.SetRenderTarget(out_frames[k].data_ptr(), 0)
+        else:
+            renderer.SetRenderTarget(0, out_frames[k].data_ptr())
+        renderer.SetTransform(mv, p, r)
+        renderer.RenderMesh(mesh)
+    renderer.Synchronize()
+    renderer.SetRenderTarget(0, 0)

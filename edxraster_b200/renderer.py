@@ -156,6 +156,13 @@ class Renderer:
     def DeviceDepthPtr(self):
         return self._lib.edx_device_depth(self._h)
 
+    def SetRenderTarget(self, color_ptr, depth_ptr):
+        self._check(self._lib.edx_set_render_target(self._h, C.c_void_p(color_ptr or None), C.c_void_p(depth_ptr or None)))
+
+    def ReadDepthInto(self, host_ptr):
+        """Copy the depth buffer to caller memory (pinned for full PCIe speed); synchronises."""
+        self._check(self._lib.edx_read_depth(self._h, C.cast(C.c_void_p(host_ptr), C.POINTER(C.c_float))))
+
     def SetStream(self, cuda_stream_ptr):
         self._check(self._lib.edx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

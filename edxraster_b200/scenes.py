@@ -159,7 +159,7 @@ def displaced_grid(quads_x=2500, quads_z=2000, cell=0.02, amplitude=0.12, seed=0
     return _pack(pos, n.reshape(-1, 3), uv), idx.astype(np.uint32), (gx, gz, y)
 
 
-def grid_camera(height_field, width, height, yaw=0.0, ring=8.0, above=0.05, fov=65.0, near=1.0, far=100.0):
+def grid_camera(height_field, width, height, yaw=0.0, ring=8.0, above=0.05, fov=65.0, near=0.1, far=100.0):
     gx, gz, y = height_field
     ex, ez = ring * math.sin(yaw + math.pi), ring * math.cos(yaw + math.pi)
     ix = int(np.clip(np.searchsorted(gx, ex), 1, len(gx) - 2))

@@ -127,6 +127,9 @@ int edx_get_derived_state(const edx_context* ctx, float mvp[16], float eye[3], f
  * host round trip */
 void* edx_device_color(edx_context* ctx);
 void* edx_device_depth(edx_context* ctx);
+/* render into caller-owned device buffers (width*height RGBA8 / float32), e.g. torch tensors that
+ * an NCCL gather then sends without a copy; NULL restores the context's own buffer. */
+int edx_set_render_target(edx_context* ctx, void* device_color, void* device_depth);
 /* use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own */
 int edx_set_stream(edx_context* ctx, void* cuda_stream);
 /* CUDA-event timing on the context's stream: begin, N x render, end -> elapsed ms (synchronises) */

@@ -1,0 +1,167 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (needs a B200: -m gpu).
+
+Bar (BASELINE.json north_star): clip-space vertices, snapped setup records, per-pixel depth bits and
+owning-triangle ids bit-exact; shaded colour within +-1 of 8 bits per channel.
+"""
+import numpy as np
+import pytest
+
+from edxraster_b200 import scenes
+import parity
+from test_oracle_kats import raster_scene
+
+pytestmark = pytest.mark.gpu
+
+REDUCED = {
+    "C1": lambda: scenes.config1(),
+    "C2": lambda: scenes.config2(num_tris=150000),
+    "C3": lambda: scenes.config3(width=1280, height=720, num_tris=300),
+    "C4": lambda: scenes.config4(quads_x=600, quads_z=480),
+    "C4_yaw": lambda: scenes.config4(width=1280, height=720, quads_x=400, quads_z=320, yaw=2.1),
+    "odd_bins": lambda: scenes.config1(width=1000, height=562, slices=60, stacks=60),
+}
+
+
+def assert_parity(sc, **kw):
+    ref = parity.render_oracle(sc, shader=kw.get("shader"))
+    got = parity.render_gpu(sc, **kw)
+    rep = parity.compare(ref, got)
+    assert parity.is_parity(rep), rep
+    return ref, got, rep
+
+
+@pytest.mark.parametrize("name", sorted(REDUCED))
+def test_reduced_configs_bit_exact(name):
+    assert_parity(REDUCED[name]())
+
+
+@pytest.mark.parametrize("name", ["C1", "C3", "C4"])
+@pytest.mark.parametrize("options,hier", [({"hiz": 0}, True), ({}, False), ({"small_max": 0}, True),
+                                          ({"small_max": 2}, True), ({"small_max": 40}, True)])
+def test_tuning_knobs_never_change_the_image(name, options, hier):
+    # routing (direct vs tile path), hierarchical Z and the 8x8 block tests are pure optimisations
+    assert_parity(REDUCED[name](), options=options, hierarchical=hier, stages=False)
+
+
+@pytest.mark.parametrize("shader", [0, 1, 2, 3])
+def test_every_shader(shader):
+    sc = scenes.config1(width=640, height=360, slices=64, stacks=64)
+    assert_parity(sc, shader=shader, stages=False)
+
+
+def test_full_size_c1():
+    assert_parity(scenes.config1())
+
+
+def test_full_size_c2():
+    _, got, _ = assert_parity(scenes.config2())
+    assert got["stats"]["binned_tris"] == 0
+
+
+def test_full_size_c3():
+    _, got, _ = assert_parity(scenes.config3())
+    assert got["stats"]["clipped_tris"] == 2000
+
+
+def test_full_size_c4():
+    _, got, _ = assert_parity(scenes.config4(), stages=False)
+    assert got["stats"]["clipped_tris"] > 1000
+
+
+def test_edge_cases():
+    from edxraster_b200 import renderer as R
+    r = R.Renderer(0)
+    # empty mesh: cleared frame (FrameBuffer.cpp:89-105)
+    sc = raster_scene(np.zeros((0, 3, 2)), np.zeros((0,)), 64, 48)
+    sc["shader"] = 1
+    got = parity.render_gpu(sc, stages=False, renderer=r)
+    assert (got["depth"] == 1.0).all() and (got["color"] == 0).all() and (got["winner"] == 0xFFFFFFFF).all()
+    # everything off screen / behind the camera / degenerate / back-facing
+    far_away = [[[200, 200], [300, 200], [200, 300]], [[-50, -50], [-10, -50], [-50, -10]]]
+    sc = raster_scene(far_away, [0.5, 0.5], 64, 48)
+    ref, got, _ = assert_parity(sc, renderer=r)
+    assert (got["winner"] == 0xFFFFFFFF).all()
+    tiny = raster_scene([[[0.2, 0.2], [1.9, 0.3], [0.4, 1.8]]], [0.3], 2, 2)
+    assert_parity(tiny, renderer=r)
+    # sub-pixel slivers that touch no centre, and a triangle covering exactly one centre
+    sc = raster_scene([[[3.1, 3.1], [3.4, 3.1], [3.1, 3.4]], [[5.25, 5.25], [5.9, 5.25], [5.25, 5.9]]], [0.5, 0.5], 64, 48)
+    ref, got, _ = assert_parity(sc, renderer=r)
+    assert int((got["winner"] != 0xFFFFFFFF).sum()) == 1
+    r.close()
+
+
+def test_w_le_zero_and_huge_triangles_through_the_clipper():
+    rng = np.random.default_rng(3)
+    # random triangles in clip space with w of both signs: exercises every plane and the w <= 0 drop
+    n = 4000
+    sc = scenes.config3(width=320, height=200, num_tris=n)
+    v = sc.vertices.copy()
+    v[:, 0:3] = (rng.random((n * 3, 3)) - 0.5) * np.array([8.0, 8.0, 6.0])
+    sc["vertices"] = v
+    assert_parity(sc)
+
+
+def test_repeated_frames_are_identical_and_state_switches_are_clean():
+    from edxraster_b200 import renderer as R
+    r = R.Renderer(0)
+    a, b = scenes.config1(width=640, height=360), scenes.config4(width=640, height=360, quads_x=200, quads_z=160)
+    r.Initialize(640, 360)
+    r.SetCaptureIds(True)
+    ma, mb = r.CreateMesh(a.vertices, a.indices), r.CreateMesh(b.vertices, b.indices)
+    frames = []
+    for sc, m, shader in ((a, ma, 1), (b, mb, 1), (a, ma, 0), (a, ma, 1), (b, mb, 1)):
+        r.SetTransform(sc.mv, sc.proj, sc.raster)
+        r.SetPixelShader(shader)
+        r.RenderMesh(m)
+        frames.append((r.GetBackBuffer().copy(), r.GetDepthBuffer(), r.GetWinnerIds()))
+    # the self-cleaning key buffer leaves nothing behind: frame 3 == frame 0, frame 4 == frame 1
+    for i, j in ((0, 3), (1, 4)):
+        for x, y in zip(frames[i], frames[j]):
+            np.testing.assert_array_equal(x, y)
+    assert (frames[2][0] == 0).all()                      # depth-only frame leaves colour cleared
+    np.testing.assert_array_equal(frames[2][1], frames[0][1])
+    ref = parity.render_oracle(b)
+    np.testing.assert_array_equal(ref["winner"], frames[4][2])
+    # Resize (Renderer.cpp:64-83) rebuilds the buffers
+    r.Resize(320, 200)
+    c = scenes.config1(width=320, height=200)
+    r.SetTransform(c.mv, c.proj, c.raster)
+    r.RenderMesh(ma)
+    np.testing.assert_array_equal(parity.render_oracle(c)["winner"], r.GetWinnerIds())
+    r.close()
+
+
+def test_queue_regrow_path():
+    # > 65,536 triangles on the tile path overflow its initial queue: the frame is re-run after growing
+    rng = np.random.default_rng(5)
+    n = 90000
+    c = rng.random((n, 1, 2)) * np.array([1280, 720])
+    p = c + (rng.random((n, 3, 2)) - 0.5) * 40
+    a, b = p[:, 0] - p[:, 2], p[:, 1] - p[:, 2]
+    flip = (a[:, 0] * b[:, 1] - b[:, 0] * a[:, 1]) < 0
+    p[flip, 0], p[flip, 1] = p[flip, 1].copy(), p[flip, 0].copy()
+    sc = raster_scene(p, 0.1 + 0.8 * rng.random((n, 3)), 1280, 720)
+    _, got, _ = assert_parity(sc, stages=False)
+    assert got["stats"]["binned_tris"] > 65536 and got["stats"]["regrow_count"] >= 1
+
+
+def test_error_behaviour():
+    from edxraster_b200 import renderer as R
+    from edxraster_b200._lib import EdxError, EDX_ERR_UNSUPPORTED, EDX_ERR_INVALID
+    r = R.Renderer(0)
+    with pytest.raises(EdxError) as e:
+        r.RenderMesh(type("M", (), {"_h": None})())
+    assert e.value.code == EDX_ERR_INVALID
+    r.Initialize(64, 64)
+    with pytest.raises(EdxError) as e:
+        r.SetMSAAMode(2)
+    assert e.value.code == EDX_ERR_UNSUPPORTED
+    r.SetMSAAMode(0)
+    with pytest.raises(EdxError) as e:
+        r.Initialize(8192, 8192)                   # 28.4 edge functions would overflow int32
+    assert e.value.code == EDX_ERR_UNSUPPORTED
+    with pytest.raises(EdxError):
+        r.SetPixelShader(9)
+    with pytest.raises(EdxError):
+        r.SetOption("nonsense", 1)
+    r.close()
