@@ -21,17 +21,23 @@ constexpr int BLOCK_PX = 8;              // ... tested as four 8x8 blocks, then 
 constexpr int TILES_PER_BIN = (BIN / TILE_PX) * (BIN / TILE_PX);   // 16
 constexpr int KEYS_PER_BIN = BIN * BIN;                            // 4096
 constexpr int TILE_THREADS = TILES_PER_BIN * 32;                   // 512
-constexpr int SURV_CAP = 1024;           // per-bin survivor list held in shared memory
+constexpr int SURV_CAP = 768;            // per-bin survivor list held in shared memory
+constexpr int CAND_CAP = 4096;           // per-bin candidate indices (bin-box filter hits) held in shared memory
+constexpr int HIZ_MIN_CAND = 48;         // below this many candidates a bin skips hierarchical Z
 
 constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 
 enum Shader { SH_DEPTH_ONLY = 0, SH_BLINN_PHONG = 1, SH_LAMBERT = 2, SH_LAMBERT_ALBEDO = 3 };
 
-// Post-setup triangle routed to the tile path (48 bytes, three 16-byte loads).
+// Post-setup triangle routed to the tile path (64 bytes, four 16-byte loads).
+// (gx, gy, zref): the triangle's depth plane over pixel centres, Z(px, py) = zref + gx*px + gy*py, fitted
+// in fp32 at record creation; perr bounds the fit's error anywhere on screen. Used only for the
+// conservative hierarchical-Z bounds, never for a depth value.
 struct __align__(16) BigRec {
     int v0x, v0y, v1x, v1y;
     int v2x, v2y; float z0, z1;
-    float z2, invDet; uint32_t prim; uint32_t pad;
+    float z2, invDet; uint32_t prim; float gx;
+    float gy, zref, perr; uint32_t pad;
 };
 
 // What the resolve pass needs to shade a pixel owned by a fan triangle of a clipped polygon (96 bytes).
@@ -61,7 +67,8 @@ struct FrameParams {
     float light[3];          // normalised (1,1,-1), Core/Renderer.cpp:290 + Shader.h:258
     float albedo[3];
     int width, height, binsX, binsY;
-    int shader, smallMax, hiz, hierarchical, captureIds, dump;
+    int shader, smallMax, smallMaxClip, hiz, hierarchical, captureIds, dump;
+    int rasterAffineXY;      // raster matrix has no z column and w' == 1: skip the unused z/w and w' arithmetic
     // mesh (SoA streams built at upload)
     const float4* pos4;      // x, y, z, texcoord.v
     const float4* nrm4;      // nx, ny, nz, texcoord.u
@@ -70,6 +77,7 @@ struct FrameParams {
     // frame state
     unsigned long long* keys;            // 64-bit visibility keys, bin/tile/block-tiled, L2 resident
     BigRec* big; uint32_t bigCap;
+    uint32_t* bigBox;                    // per tile-path triangle: its bin bounding box, 4 x u8 (x0, x1, y0, y1)
     uint32_t* clipQueue; uint32_t clipQueueCap;
     ClipRec* clipRecs; uint32_t clipRecCap;
     uint32_t* clipSlot;                  // per submitted triangle: first ClipRec of its polygon
@@ -142,30 +150,46 @@ struct SetupTri {
 };
 
 // Vector4::HomogeneousProject + Matrix::TransformPoint(Vector3, raster) + snap of x and y
-// (Clipper.h:161-163, RasterTriangle.h:29-40)
-__device__ __forceinline__ void project_snap(const float* R, const V4& c, int& sx, int& sy)
+// (Clipper.h:161-163, RasterTriangle.h:29-40).
+// affineXY (decided on the host): the raster matrix has zero z-column entries in rows 0/1 and its last
+// row is (0,0,0,1). Then z/w only ever contributes +-0 to x and y and w' is exactly 1, so the three
+// operations are skipped; x and y are bit-identical for every finite input.
+__device__ __forceinline__ void project_snap(const float* R, bool affineXY, const V4& c, int& sx, int& sy)
 {
-    float ax = fdiv(c.x, c.w), ay = fdiv(c.y, c.w), az = fdiv(c.z, c.w);
-    float x = row_dot(R[0], R[1], R[2], R[3], ax, ay, az);
-    float y = row_dot(R[4], R[5], R[6], R[7], ax, ay, az);
-    float w = row_dot(R[12], R[13], R[14], R[15], ax, ay, az);
-    if (w != 1.0f) { x = fdiv(x, w); y = fdiv(y, w); }
+    const float ax = fdiv(c.x, c.w), ay = fdiv(c.y, c.w);
+    float x, y;
+    if (affineXY) {
+        x = fadd(fadd(fmul(R[0], ax), fmul(R[1], ay)), R[3]);
+        y = fadd(fadd(fmul(R[4], ax), fmul(R[5], ay)), R[7]);
+    } else {
+        const float az = fdiv(c.z, c.w);
+        x = row_dot(R[0], R[1], R[2], R[3], ax, ay, az);
+        y = row_dot(R[4], R[5], R[6], R[7], ax, ay, az);
+        const float w = row_dot(R[12], R[13], R[14], R[15], ax, ay, az);
+        if (w != 1.0f) { x = fdiv(x, w); y = fdiv(y, w); }
+    }
     sx = snap_28_4(x);
     sy = snap_28_4(y);
 }
 
-// Stage a5: RasterTriangle::Setup, RasterTriangle.h:27-60. false = culled (det <= 0).
-__device__ __forceinline__ bool setup_tri(const float* R, const V4& c0, const V4& c1, const V4& c2, SetupTri& s)
+// det, back-face / degenerate cull and 1/det from the snapped vertices (RasterTriangle.h:42-60)
+__device__ __forceinline__ bool finish_setup(SetupTri& s)
 {
-    project_snap(R, c0, s.v0x, s.v0y);
-    project_snap(R, c1, s.v1x, s.v1y);
-    project_snap(R, c2, s.v2x, s.v2y);
     uint32_t B1 = (uint32_t)s.v1y - (uint32_t)s.v2y, C1 = (uint32_t)s.v2x - (uint32_t)s.v1x;
     uint32_t B2 = (uint32_t)s.v2y - (uint32_t)s.v0y, C2 = (uint32_t)s.v0x - (uint32_t)s.v2x;
     int det = (int)(C2 * B1 - C1 * B2);
     if (det <= 0) return false;
     s.invDet = fdiv(1.0f, __int2float_rn(det));
     return true;
+}
+
+// Stage a5: RasterTriangle::Setup, RasterTriangle.h:27-60. false = culled (det <= 0).
+__device__ __forceinline__ bool setup_tri(const float* R, bool affineXY, const V4& c0, const V4& c1, const V4& c2, SetupTri& s)
+{
+    project_snap(R, affineXY, c0, s.v0x, s.v0y);
+    project_snap(R, affineXY, c1, s.v1x, s.v1y);
+    project_snap(R, affineXY, c2, s.v2x, s.v2y);
+    return finish_setup(s);
 }
 
 // Edge equations of one triangle, ready for per-pixel evaluation.

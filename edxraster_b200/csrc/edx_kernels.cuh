@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter)
 }
 
 __device__ __forceinline__ void route_triangle(const FrameParams& P, const SetupTri& s, float z0, float z1, float z2,
-                                               float iw0, float iw1, float iw2, uint32_t prim)
+                                               float iw0, float iw1, float iw2, uint32_t prim, int smallMax)
 {
     if (P.dump) {
         uint32_t at = atomicAdd(&P.counters->nDump, 1u);
@@ -104,7 +104,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
     int y1 = min(P.height - 1, last_centre(max3i(s.v0y, s.v1y, s.v2y)));
     if (x0 > x1 || y0 > y1) return;
 
-    if (x1 - x0 < P.smallMax && y1 - y0 < P.smallMax) {
+    if (x1 - x0 < smallMax && y1 - y0 < smallMax) {
         // Small triangle: rasterise here. Stages a10/a12/a13 per pixel:
         // coverage (Rasterizer.h:162), barycentrics + depth (RasterTriangle.h:324-337), depth test as key-min.
         Edges e;
@@ -113,29 +113,70 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
         uint32_t r0 = (uint32_t)e.e0(cx, cy), r1 = (uint32_t)e.e1(cx, cy), r2 = (uint32_t)e.e2(cx, cy);
         const uint32_t sB0 = e.B0 << 4, sB1 = e.B1 << 4, sB2 = e.B2 << 4;   // one pixel = 16 sub-pixels (RasterTriangle.h:53-58)
         const uint32_t sC0 = e.C0 << 4, sC1 = e.C1 << 4, sC2 = e.C2 << 4;
-        for (int y = y0; y <= y1; y++) {
-            uint32_t a0 = r0, a1 = r1, a2 = r2;
-            for (int x = x0; x <= x1; x++) {
-                if ((int)(a0 | a1 | a2) >= 0) {
-                    float l0, l1;
-                    barycentric((int)(a1 - (uint32_t)e.bias1), (int)(a2 - (uint32_t)e.bias2), s.invDet, l0, l1);
-                    float d = depth_at(l0, l1, z0, z1, z2);
-                    if (d <= 1.0f)     // depth buffer is cleared to 1.0 and tested LESS_EQUAL (FrameBuffer.cpp:64,103)
-                        atomicMin(P.keys + key_index(x, y, P.binsX), make_key(d, prim));
+        if (x1 - x0 < 8 && y1 - y0 < 8) {
+            // Phase 1: coverage only, into a 64-bit mask (bit = 8*dy + dx). Phase 2: one iteration per
+            // covered pixel. Splitting keeps the long depth/key/atomic sequence out of the divergent
+            // coverage loop, so lanes of a warp execute it together instead of one at a time.
+            const uint32_t base1 = r1 - (uint32_t)e.bias1, base2 = r2 - (uint32_t)e.bias2;   // unbiased edge 1 / 2 at (x0, y0)
+            uint32_t lo = 0, hi = 0;
+            for (int y = y0; y <= y1; y++) {
+                uint32_t a0 = r0, a1 = r1, a2 = r2, row = 0;
+                for (int x = x0; x <= x1; x++) {
+                    row |= (uint32_t)((int)(a0 | a1 | a2) >= 0) << (x - x0);
+                    a0 += sB0; a1 += sB1; a2 += sB2;
                 }
-                a0 += sB0; a1 += sB1; a2 += sB2;
+                const int dy = y - y0;
+                if (dy < 4) lo |= row << (8 * dy); else hi |= row << (8 * (dy - 4));
+                r0 += sC0; r1 += sC1; r2 += sC2;
             }
-            r0 += sC0; r1 += sC1; r2 += sC2;
+            while (lo | hi) {
+                int b;
+                if (lo) { b = __ffs(lo) - 1; lo &= lo - 1; } else { b = 32 + __ffs(hi) - 1; hi &= hi - 1; }
+                const uint32_t dx = (uint32_t)(b & 7), dy = (uint32_t)(b >> 3);
+                float l0, l1;
+                barycentric((int)(base1 + dx * sB1 + dy * sC1), (int)(base2 + dx * sB2 + dy * sC2), s.invDet, l0, l1);
+                const float d = depth_at(l0, l1, z0, z1, z2);
+                if (d <= 1.0f)     // depth buffer is cleared to 1.0 and tested LESS_EQUAL (FrameBuffer.cpp:64,103)
+                    atomicMin(P.keys + key_index(x0 + (int)dx, y0 + (int)dy, P.binsX), make_key(d, prim));
+            }
+        } else {
+            for (int y = y0; y <= y1; y++) {
+                uint32_t a0 = r0, a1 = r1, a2 = r2;
+                for (int x = x0; x <= x1; x++) {
+                    if ((int)(a0 | a1 | a2) >= 0) {
+                        float l0, l1;
+                        barycentric((int)(a1 - (uint32_t)e.bias1), (int)(a2 - (uint32_t)e.bias2), s.invDet, l0, l1);
+                        float d = depth_at(l0, l1, z0, z1, z2);
+                        if (d <= 1.0f)
+                            atomicMin(P.keys + key_index(x, y, P.binsX), make_key(d, prim));
+                    }
+                    a0 += sB0; a1 += sB1; a2 += sB2;
+                }
+                r0 += sC0; r1 += sC1; r2 += sC2;
+            }
         }
     } else {
-        uint32_t at = warp_append(&P.counters->nBig);
+        const uint32_t at = warp_append(&P.counters->nBig);
         if (at < P.bigCap) {
-            BigRec r;
-            r.v0x = s.v0x; r.v0y = s.v0y; r.v1x = s.v1x; r.v1y = s.v1y; r.v2x = s.v2x; r.v2y = s.v2y;
-            r.z0 = z0; r.z1 = z1; r.z2 = z2; r.invDet = s.invDet; r.prim = prim; r.pad = 0;
+            // Depth plane over pixel centres (sub-pixel 16*p + 8), fitted in fp32 together with a bound of
+            // its own rounding error; it only feeds the conservative hierarchical-Z test.
+            const float B1 = (float)(s.v1y - s.v2y), C1 = (float)(s.v2x - s.v1x);      // |B|,|C| < 2^24: exact
+            const float B2 = (float)(s.v2y - s.v0y), C2 = (float)(s.v0x - s.v2x);
+            const float dz0 = z0 - z2, dz1 = z1 - z2;
+            const float t0 = B1 * dz0, t1 = B2 * dz1, t2 = C1 * dz0, t3 = C2 * dz1;
+            const float ax = (t0 + t1) * s.invDet, ay = (t2 + t3) * s.invDet;            // per sub-pixel
+            const float eA = 4e-7f * (fabsf(t0) + fabsf(t1)) * s.invDet, eB = 4e-7f * (fabsf(t2) + fabsf(t3)) * s.invDet;
+            const float ox = 8.0f - (float)s.v2x, oy = 8.0f - (float)s.v2y;
+            const float zref = z2 + ax * ox + ay * oy;
+            const float perr = eA * fabsf(ox) + eB * fabsf(oy) + 2.5e-7f * (fabsf(z2) + fabsf(ax * ox) + fabsf(ay * oy)) +
+                               16.0f * (eA * (float)P.width + eB * (float)P.height);
             int4* dst = reinterpret_cast<int4*>(P.big + at);
-            const int4* src = reinterpret_cast<const int4*>(&r);
-            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+            dst[0] = make_int4(s.v0x, s.v0y, s.v1x, s.v1y);
+            dst[1] = make_int4(s.v2x, s.v2y, __float_as_int(z0), __float_as_int(z1));
+            dst[2] = make_int4(__float_as_int(z2), __float_as_int(s.invDet), (int)prim, __float_as_int(16.0f * ax));
+            dst[3] = make_int4(__float_as_int(16.0f * ay), __float_as_int(zref), __float_as_int(perr), 0);
+            P.bigBox[at] = (uint32_t)(x0 >> BIN_LOG2) | ((uint32_t)(x1 >> BIN_LOG2) << 8) |
+                           ((uint32_t)(y0 >> BIN_LOG2) << 16) | ((uint32_t)(y1 >> BIN_LOG2) << 24);
         }
     }
 }
@@ -161,10 +202,20 @@ __global__ void __launch_bounds__(256) geom_kernel(const __grid_constant__ Frame
         return;
     }
     SetupTri s;
-    if (!setup_tri(P.raster, c0, c1, c2, s)) return;
+    if (!P.dump) {
+        // Exact early cull (most sub-pixel triangles end here): snap first, and drop the triangle if its
+        // box holds no pixel centre before paying for the det / invDet / invW arithmetic.
+        project_snap(P.raster, P.rasterAffineXY != 0, c0, s.v0x, s.v0y);
+        project_snap(P.raster, P.rasterAffineXY != 0, c1, s.v1x, s.v1y);
+        project_snap(P.raster, P.rasterAffineXY != 0, c2, s.v2x, s.v2y);
+        if (max(0, first_centre(min3i(s.v0x, s.v1x, s.v2x))) > min(P.width - 1, last_centre(max3i(s.v0x, s.v1x, s.v2x))) ||
+            max(0, first_centre(min3i(s.v0y, s.v1y, s.v2y))) > min(P.height - 1, last_centre(max3i(s.v0y, s.v1y, s.v2y))))
+            return;
+        if (!finish_setup(s)) return;
+    } else if (!setup_tri(P.raster, P.rasterAffineXY != 0, c0, c1, c2, s)) return;
     // Renderer.cpp:139-147: invW = 1/w, z = z * invW
     float iw0 = fdiv(1.0f, c0.w), iw1 = fdiv(1.0f, c1.w), iw2 = fdiv(1.0f, c2.w);
-    route_triangle(P, s, fmul(c0.z, iw0), fmul(c1.z, iw1), fmul(c2.z, iw2), iw0, iw1, iw2, t * 8u);
+    route_triangle(P, s, fmul(c0.z, iw0), fmul(c1.z, iw1), fmul(c2.z, iw2), iw0, iw1, iw2, t * 8u, P.smallMax);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -200,12 +251,11 @@ __device__ __forceinline__ float plane_param(int plane, const V4& a, const V4& b
     }
 }
 
-__device__ __forceinline__ void cut_edge(int plane, const Poly& in, int i, int j, Poly& out)
+// one new vertex where edge a->b crosses `plane` (Clipper.h:210-214): position, snap, clip weights
+__device__ __forceinline__ void cut_vertex(int plane, const V4& a, const V4& b, const float* wa, const float* wb, V4& r, float* rw)
 {
-    const V4 a = in.p[i], b = in.p[j];
-    float t = plane_param(plane, a, b);
-    float s = fsub(1.0f, t);
-    V4 r;                                             // Clipper.h:210-213
+    const float t = plane_param(plane, a, b);
+    const float s = fsub(1.0f, t);
     r.x = fadd(fmul(a.x, s), fmul(b.x, t));
     r.y = fadd(fmul(a.y, s), fmul(b.y, t));
     r.z = fadd(fmul(a.z, s), fmul(b.z, t));
@@ -218,9 +268,14 @@ __device__ __forceinline__ void cut_edge(int plane, const Poly& in, int i, int j
     case FAR_BIT:    r.z = r.w; break;
     default:         r.z = 0.0f; break;
     }
-    int n = out.n++;
-    out.p[n] = r;
-    for (int k = 0; k < 3; k++) out.w[n][k] = fadd(fmul(in.w[i][k], s), fmul(in.w[j][k], t));
+    #pragma unroll
+    for (int k = 0; k < 3; k++) rw[k] = fadd(fmul(wa[k], s), fmul(wb[k], t));
+}
+
+__device__ __forceinline__ void cut_edge(int plane, const Poly& in, int i, int j, Poly& out)
+{
+    const int n = out.n++;
+    cut_vertex(plane, in.p[i], in.p[j], in.w[i], in.w[j], out.p[n], out.w[n]);
 }
 
 __device__ __forceinline__ void copy_vertex(const Poly& in, int j, Poly& out)
@@ -246,10 +301,53 @@ __device__ void clip_by_plane(int plane, const Poly& in, Poly& out)     // Clipp
     }
 }
 
+// Clipper.h:121-153: a polygon vertex whose weight is exactly 1 IS that original vertex
+__device__ __forceinline__ uint32_t vertex_source(const float* w)
+{
+    if (w[0] == 1.0f) return 0;
+    if (w[1] == 1.0f) return 1;
+    if (w[2] == 1.0f) return 2;
+    return 3;
+}
+
+// One fan triangle (0, k-1, k) of a clipped polygon: setup, shading record, routing (Clipper.h:156-170).
+// Deliberately not inlined: the clipper runs a few thousand threads, each serially; a small code
+// footprint (instruction-cache hits) matters more than call overhead there.
+__device__ __noinline__ void emit_fan(const FrameParams& P, uint32_t t, int fan, uint32_t slot, bool haveRecs,
+                                         const V4& f0, const V4& f1, const V4& f2, float iwA, float zA,
+                                         uint32_t srcBits, const float* w0, const float* w1, const float* w2)
+{
+    SetupTri s;
+    const bool ok = setup_tri(P.raster, P.rasterAffineXY != 0, f0, f1, f2, s);
+    const float iwB = fdiv(1.0f, f1.w), iwC = fdiv(1.0f, f2.w);
+    if (haveRecs) {
+        ClipRec r;
+        r.v0x = s.v0x; r.v0y = s.v0y; r.v1x = s.v1x; r.v1y = s.v1y; r.v2x = s.v2x; r.v2y = s.v2y;
+        r.invDet = ok ? s.invDet : 0.0f;
+        r.src = srcBits;
+        r.invW0 = iwA; r.invW1 = iwB; r.invW2 = iwC; r.valid = ok ? 1u : 0u;
+        #pragma unroll
+        for (int m = 0; m < 3; m++) { r.wt[0][m] = w0[m]; r.wt[1][m] = w1[m]; r.wt[2][m] = w2[m]; }
+        r.pad[0] = r.pad[1] = r.pad[2] = 0.0f;
+        int4* dst = reinterpret_cast<int4*>(P.clipRecs + slot + fan);
+        const int4* src = reinterpret_cast<const int4*>(&r);
+        #pragma unroll
+        for (int m = 0; m < 6; m++) dst[m] = src[m];
+    }
+    if (ok) route_triangle(P, s, zA, fmul(f1.z, iwB), fmul(f2.z, iwC), iwA, iwB, iwC, t * 8u + (uint32_t)fan, P.smallMaxClip);
+}
+
+__device__ __forceinline__ V4 pick3(const V4* c, uint32_t i) { return i == 0 ? c[0] : (i == 1 ? c[1] : c[2]); }
+
 __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ FrameParams P)
 {
     const uint32_t n = min(P.counters->nClipQueue, P.clipQueueCap);
-    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    // Work item q goes to lane q / W of warp q % W (W = warps in the grid): a short queue is spread one
+    // triangle per warp over the whole chip instead of packing 32 divergent clippers into each of a
+    // few warps; a long queue still fills every lane.
+    const uint32_t W = gridDim.x * (blockDim.x >> 5);
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (uint32_t q = (threadIdx.x & 31u) * W + gw; q < n; q += 32u * W) {
         const uint32_t t = P.clipQueue[q];
         uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
         float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
@@ -257,9 +355,50 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
         c[0] = to_clip(P.mvp, p0.x, p0.y, p0.z);
         c[1] = to_clip(P.mvp, p1.x, p1.y, p1.z);
         c[2] = to_clip(P.mvp, p2.x, p2.y, p2.z);
-        uint32_t k0 = clip_code(c[0]), k1 = clip_code(c[1]), k2 = clip_code(c[2]);
-        uint32_t planes = (k0 ^ k1) | (k1 ^ k2) | (k2 ^ k0);           // Clipper.h:119
+        const uint32_t k0 = clip_code(c[0]), k1 = clip_code(c[1]), k2 = clip_code(c[2]);
+        const uint32_t planes = (k0 ^ k1) | (k1 ^ k2) | (k2 ^ k0);           // Clipper.h:119
 
+        if (__popc(planes) == 1) {
+            // Fast path: exactly one plane is crossed (the common case at screen edges). The polygon has
+            // 3 or 4 vertices in an order fixed by which vertices are inside (Clipper.h:196-229), so it is
+            // built with static indices and lives in registers.
+            const int plane = (int)planes;
+            const float U[3][3] = { { 1.0f, 0.0f, 0.0f }, { 0.0f, 1.0f, 0.0f }, { 0.0f, 0.0f, 1.0f } };
+            const uint32_t in = (plane_inside(plane, c[0]) ? 1u : 0u) | (plane_inside(plane, c[1]) ? 2u : 0u) | (plane_inside(plane, c[2]) ? 4u : 0u);
+            V4 v[4]; float w[4][3]; int nv = 0;
+            #define EDX_ORIG(slot_, i_) { v[slot_] = c[i_]; w[slot_][0] = U[i_][0]; w[slot_][1] = U[i_][1]; w[slot_][2] = U[i_][2]; }
+            #define EDX_CUT(slot_, i_, j_) cut_vertex(plane, c[i_], c[j_], U[i_], U[j_], v[slot_], w[slot_]);
+            switch (in) {
+            case 1: EDX_CUT(0, 0, 1) EDX_CUT(1, 2, 0) EDX_ORIG(2, 0) nv = 3; break;                    // only v0 inside
+            case 2: EDX_CUT(0, 0, 1) EDX_ORIG(1, 1) EDX_CUT(2, 1, 2) nv = 3; break;                    // only v1
+            case 4: EDX_CUT(0, 1, 2) EDX_ORIG(1, 2) EDX_CUT(2, 2, 0) nv = 3; break;                    // only v2
+            case 6: EDX_CUT(0, 0, 1) EDX_ORIG(1, 1) EDX_ORIG(2, 2) EDX_CUT(3, 2, 0) nv = 4; break;     // v0 outside
+            case 5: EDX_CUT(0, 0, 1) EDX_CUT(1, 1, 2) EDX_ORIG(2, 2) EDX_ORIG(3, 0) nv = 4; break;     // v1 outside
+            case 3: EDX_ORIG(0, 1) EDX_CUT(1, 1, 2) EDX_CUT(2, 2, 0) EDX_ORIG(3, 0) nv = 4; break;     // v2 outside
+            default: nv = 0; break;
+            }
+            #undef EDX_ORIG
+            #undef EDX_CUT
+            if (nv == 3) { v[3] = v[2]; w[3][0] = w[2][0]; w[3][1] = w[2][1]; w[3][2] = w[2][2]; }
+            bool drop = nv == 0;
+            #pragma unroll
+            for (int k = 0; k < 4; k++) if (k < nv && v[k].w <= 0.0f) drop = true;                  // Clipper.h:280-287
+            if (drop) continue;
+            uint32_t src[4];
+            #pragma unroll
+            for (int k = 0; k < 4; k++) { src[k] = vertex_source(w[k]); if (src[k] < 3) v[k] = pick3(c, src[k]); }
+            const uint32_t nFan = (uint32_t)(nv - 2);
+            const uint32_t slot = atomicAdd(&P.counters->nClipRecs, nFan);
+            const bool haveRecs = slot + nFan <= P.clipRecCap;
+            if (haveRecs) P.clipSlot[t] = slot;
+            const float iwA = fdiv(1.0f, v[0].w), zA = fmul(v[0].z, iwA);
+            emit_fan(P, t, 0, slot, haveRecs, v[0], v[1], v[2], iwA, zA, src[0] | (src[1] << 2) | (src[2] << 4), w[0], w[1], w[2]);
+            if (nv == 4)
+                emit_fan(P, t, 1, slot, haveRecs, v[0], v[2], v[3], iwA, zA, src[0] | (src[2] << 2) | (src[3] << 4), w[0], w[2], w[3]);
+            continue;
+        }
+
+        // General path: several planes, up to 9 vertices, polygon in local memory.
         Poly a, b;
         a.n = 3;
         for (int k = 0; k < 3; k++) {
@@ -275,44 +414,21 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
         for (int k = 0; k < cur->n; k++)
             if (cur->p[k].w <= 0.0f) nv = 0;                           // Clipper.h:280-287
         if (nv < 3) continue;
-
-        // Clipper.h:121-153: vertices whose weight is exactly 1 ARE the original vertex (original
-        // clip position included); the others are new vertices at the clipped position.
         uint32_t srcs = 0;
         for (int k = 0; k < nv; k++) {
-            uint32_t src = 3;
-            if (cur->w[k][0] == 1.0f) src = 0;
-            else if (cur->w[k][1] == 1.0f) src = 1;
-            else if (cur->w[k][2] == 1.0f) src = 2;
-            if (src < 3) cur->p[k] = c[src];
+            const uint32_t src = vertex_source(cur->w[k]);
+            if (src < 3) cur->p[k] = pick3(c, src);
             srcs |= src << (2 * k);
         }
         const uint32_t nFan = (uint32_t)(nv - 2);
         const uint32_t slot = atomicAdd(&P.counters->nClipRecs, nFan);
         const bool haveRecs = slot + nFan <= P.clipRecCap;
         if (haveRecs) P.clipSlot[t] = slot;
-
         const V4 f0 = cur->p[0];
         const float iwA = fdiv(1.0f, f0.w), zA = fmul(f0.z, iwA);
         for (int k = 2; k < nv; k++) {                                  // Clipper.h:156-170 fan (0, k-1, k)
-            const V4 f1 = cur->p[k - 1], f2 = cur->p[k];
-            SetupTri s;
-            bool ok = setup_tri(P.raster, f0, f1, f2, s);
-            float iwB = fdiv(1.0f, f1.w), iwC = fdiv(1.0f, f2.w);
-            if (haveRecs) {
-                ClipRec r;
-                r.v0x = s.v0x; r.v0y = s.v0y; r.v1x = s.v1x; r.v1y = s.v1y; r.v2x = s.v2x; r.v2y = s.v2y;
-                r.invDet = ok ? s.invDet : 0.0f;
-                r.src = (srcs & 3u) | (((srcs >> (2 * (k - 1))) & 3u) << 2) | (((srcs >> (2 * k)) & 3u) << 4);
-                r.invW0 = iwA; r.invW1 = iwB; r.invW2 = iwC; r.valid = ok ? 1u : 0u;
-                for (int m = 0; m < 3; m++) { r.wt[0][m] = cur->w[0][m]; r.wt[1][m] = cur->w[k - 1][m]; r.wt[2][m] = cur->w[k][m]; }
-                r.pad[0] = r.pad[1] = r.pad[2] = 0.0f;
-                int4* dst = reinterpret_cast<int4*>(P.clipRecs + slot + (k - 2));
-                const int4* src = reinterpret_cast<const int4*>(&r);
-                #pragma unroll
-                for (int m = 0; m < 6; m++) dst[m] = src[m];
-            }
-            if (ok) route_triangle(P, s, zA, fmul(f1.z, iwB), fmul(f2.z, iwC), iwA, iwB, iwC, t * 8u + (uint32_t)(k - 2));
+            const uint32_t sb = (srcs & 3u) | (((srcs >> (2 * (k - 1))) & 3u) << 2) | (((srcs >> (2 * k)) & 3u) << 4);
+            emit_fan(P, t, k - 2, slot, haveRecs, f0, cur->p[k - 1], cur->p[k], iwA, zA, sb, cur->w[0], cur->w[k - 1], cur->w[k]);
         }
     }
 }
@@ -352,19 +468,19 @@ __device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0,
     full = e.e0(b0 ? cx0 : cx1, c0 ? cy0 : cy1) >= 0 && e.e1(b1 ? cx0 : cx1, c1 ? cy0 : cy1) >= 0 &&
            e.e2(b2 ? cx0 : cx1, c2 ? cy0 : cy1) >= 0;
     if (!wantZ) return;
-    // Depth is affine in the pixel position up to fp32 rounding: bound the exact plane over the rect in
-    // fp64, intersect with the vertex range, widen by a margin that dominates the fp32 error of
-    // barycentric()/depth_at() (<= ~1.3e-6 * max|z|).
-    const double det = (double)(int)(e.C2 * e.B1 - e.C1 * e.B2);
-    const double dz0 = (double)r.z0 - (double)r.z2, dz1 = (double)r.z1 - (double)r.z2;
-    const double B1 = (double)(int)e.B1, C1 = (double)(int)e.C1, B2 = (double)(int)e.B2, C2 = (double)(int)e.C2;
-    const double mx = 0.5 * ((double)cx0 + (double)cx1) - (double)r.v2x, my = 0.5 * ((double)cy0 + (double)cy1) - (double)r.v2y;
-    const double zc = (double)r.z2 + ((B1 * mx + C1 * my) * dz0 + (B2 * mx + C2 * my) * dz1) / det;
-    const double ext = (fabs(B1 * dz0 + B2 * dz1) * (0.5 * (double)(cx1 - cx0)) + fabs(C1 * dz0 + C2 * dz1) * (0.5 * (double)(cy1 - cy0))) / det;
+    // Depth is affine in the pixel position up to fp32 rounding. Bound the stored plane over the rect's
+    // pixel centres, intersect with the vertex range (covered pixels lie inside the triangle), and widen by
+    //   E  = the plane fit's own error bound (perr) + rounding of this evaluation (<= 2.5e-7 of the summed magnitudes)
+    //   Ed = fp32 error of barycentric()/depth_at() at a covered pixel (<= ~1.3e-6 * max|z|)
+    const float x0f = (float)px0, x1f = (float)rx1, y0f = (float)py0, y1f = (float)ry1;
+    const float ax0 = r.gx * x0f, ax1 = r.gx * x1f, ay0 = r.gy * y0f, ay1 = r.gy * y1f;
+    const float lo = r.zref + fminf(ax0, ax1) + fminf(ay0, ay1);
+    const float hi = r.zref + fmaxf(ax0, ax1) + fmaxf(ay0, ay1);
     const float vlo = fminf(r.z0, fminf(r.z1, r.z2)), vhi = fmaxf(r.z0, fmaxf(r.z1, r.z2));
-    const float margin = 1e-5f * fmaxf(fabsf(vlo), fabsf(vhi)) + 1e-30f;
-    zmin = __double2float_rd(fmax(zc - ext, (double)vlo)) - margin;
-    zmax = __double2float_ru(fmin(zc + ext, (double)vhi)) + margin;
+    const float E = r.perr + 2.5e-7f * (fabsf(r.zref) + fmaxf(fabsf(ax0), fabsf(ax1)) + fmaxf(fabsf(ay0), fabsf(ay1)));
+    const float Ed = 1e-5f * fmaxf(fabsf(vlo), fabsf(vhi)) + 1e-30f;
+    zmin = fmaxf(lo - E, vlo) - Ed;
+    zmax = fminf(hi + E, vhi) + Ed;
 }
 
 // One warp rasterises one triangle into its 16x16 tile: 8x8 block masks by ballot, then pixels.
@@ -435,7 +551,7 @@ __device__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int p
     float A[3][6];                     // position.xyz, normal.xyz of the three (fan) vertices
     if ((clip_code(c0) | clip_code(c1) | clip_code(c2)) == 0) {
         SetupTri s;
-        setup_tri(P.raster, c0, c1, c2, s);
+        setup_tri(P.raster, P.rasterAffineXY != 0, c0, c1, c2, s);
         v0x = s.v0x; v0y = s.v0y; v1x = s.v1x; v1y = s.v1y; v2x = s.v2x; v2y = s.v2y; invDet = s.invDet;
         iw0 = fdiv(1.0f, c0.w); iw1 = fdiv(1.0f, c1.w); iw2 = fdiv(1.0f, c2.w);
         A[0][0] = p0.x; A[0][1] = p0.y; A[0][2] = p0.z; A[0][3] = n0.x; A[0][4] = n0.y; A[0][5] = n0.z;
@@ -512,41 +628,68 @@ __device__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int p
 struct TileShared {
     unsigned long long keys[KEYS_PER_BIN];     // 32 KB: [tile 4x4][block 2x2][8x8]
     BigRec surv[SURV_CAP];                     // 48 KB
-    uint32_t survCount;
+    uint32_t cand[CAND_CAP];                   // 8 KB
+    uint32_t survCount, candCount;
     uint32_t binU;                             // order_f32 of the bin's depth upper bound
+    uint32_t keyMax;                           // scratch: max ordered depth currently stored in the bin
 };
 
-__device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShared& S, int ox, int oy)
+// pixel of key slot j (0..7) of this lane inside the warp's tile
+__device__ __forceinline__ void slot_pixel(int tx0, int ty0, int lane, int j, int& px, int& py)
+{
+    const int q = j >> 1, h = j & 1;
+    px = tx0 + (q & 1) * BLOCK_PX + (lane & 7);
+    py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
+}
+
+// Largest ordered depth held by the on-screen pixels of the warp's tile; 0xFFFFFFFF while any is empty.
+__device__ __forceinline__ uint32_t tile_key_max(const unsigned long long* tkeys, int tx0, int ty0, int W, int H)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t m = 0;
+    #pragma unroll
+    for (int j = 0; j < 8; j++) {
+        int px, py;
+        slot_pixel(tx0, ty0, lane, j, px, py);
+        if (px < W && py < H) m = max(m, (uint32_t)(tkeys[j * 32 + lane] >> 32));
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    return m;
+}
+
+// Rasterise the bin's survivor list: every warp walks the list for its own 16x16 tile, one lane per
+// triangle for the tile-level test (exact reject / full cover / hierarchical Z), then the whole warp per
+// surviving triangle. The Z bound tightens as the tile fills: it is the smaller of (a) the far side of
+// any triangle covering the whole tile and (b) the largest depth currently stored in the tile.
+__device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShared& S, int ox, int oy, bool hiz)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
     const int n = (int)S.survCount;
     if (tx0 >= P.width || ty0 >= P.height || n == 0) return;
     unsigned long long* tkeys = S.keys + warp * 256;
-    const bool hiz = P.hiz && P.hierarchical;
-    // pass A: depth upper bound of the tile = nearest far-side of any triangle that covers it fully
-    float U = 1.0f;
-    if (hiz) {
-        for (int b = 0; b < n; b += 32) {
-            const int j = b + lane;
-            if (j < n) {
-                bool rej, full; float zl, zh;
-                classify_rect(S.surv[j], tx0, ty0, TILE_PX, P.width, P.height, true, rej, full, zl, zh);
-                if (!rej && full && zh <= 1.0f) U = fminf(U, zh);
-            }
-        }
-        #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) U = fminf(U, __shfl_xor_sync(0xFFFFFFFFu, U, o));
-    }
-    // pass B: lane-per-triangle tile test, then warp-per-triangle rasterisation of the survivors
+    uint32_t U = order_f32(1.0f);
     for (int b = 0; b < n; b += 32) {
+        if (hiz) {
+            __syncwarp();
+            U = min(U, tile_key_max(tkeys, tx0, ty0, P.width, P.height));
+        }
         const int j = b + lane;
         bool keep = false, full = false;
+        uint32_t zlo = 0, zhi = 0xFFFFFFFFu;
         if (j < n) {
             bool rej; float zl, zh;
             classify_rect(S.surv[j], tx0, ty0, TILE_PX, P.width, P.height, hiz, rej, full, zl, zh);
-            keep = !rej && (!hiz || zl <= U);
+            keep = !rej;
+            if (hiz) { zlo = order_f32(zl); if (keep && full && zh <= 1.0f) zhi = order_f32(zh); }
             if (!P.hierarchical) full = false;
+        }
+        if (hiz) {
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) zhi = min(zhi, __shfl_xor_sync(0xFFFFFFFFu, zhi, o));
+            U = min(U, zhi);
+            keep = keep && zlo <= U;
         }
         uint32_t keepMask = __ballot_sync(0xFFFFFFFFu, keep);
         const uint32_t fullMask = __ballot_sync(0xFFFFFFFFu, keep && full);
@@ -558,85 +701,159 @@ __device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShare
     }
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 1) tile_kernel(const __grid_constant__ FrameParams P)
+__device__ __forceinline__ bool bin_in_box(uint32_t box, uint32_t bx, uint32_t by)
+{
+    return bx >= (box & 255u) && bx <= ((box >> 8) & 255u) && by >= ((box >> 16) & 255u) && by <= (box >> 24);
+}
+
+__device__ __forceinline__ void load_big(const BigRec* src, BigRec& r)
+{
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    int4* d4 = reinterpret_cast<int4*>(&r);
+    d4[0] = __ldg(s4); d4[1] = __ldg(s4 + 1); d4[2] = __ldg(s4 + 2); d4[3] = __ldg(s4 + 3);
+}
+
+// Output of one pixel: depth always, ids on request, colour unless depth-only (stages a13, a15-a17)
+__device__ __forceinline__ void resolve_pixel(const FrameParams& P, unsigned long long key, int px, int py)
+{
+    const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);   // bottom-up, FrameBuffer.cpp:41
+    const bool hit = key != KEY_EMPTY;
+    P.depth[at] = hit ? key_depth(key) : 1.0f;                                      // clear value, FrameBuffer.cpp:103
+    if (P.captureIds) P.ids[at] = hit ? key_prim(key) : 0xFFFFFFFFu;
+    if (P.shader != SH_DEPTH_ONLY)
+        P.color[at] = hit ? shade_pixel(P, key_prim(key), px, py) : make_uchar4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_constant__ FrameParams P)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     TileShared& S = *reinterpret_cast<TileShared*>(smemRaw);
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int bin = blockIdx.x;
-    const int ox = (bin % P.binsX) << BIN_LOG2, oy = (bin / P.binsX) << BIN_LOG2;
+    const uint32_t bx = (uint32_t)(bin % P.binsX), by = (uint32_t)(bin / P.binsX);
+    const int ox = (int)bx << BIN_LOG2, oy = (int)by << BIN_LOG2;
+    const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
+    const uint32_t nBig = min(P.counters->nBig, P.bigCap);
+    unsigned long long* gkeys = P.keys + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
+
+    if (nBig == 0) {
+        // Nothing on the tile path: resolve straight from the L2-resident keys, no staging, no barrier.
+        if (tx0 >= P.width || ty0 >= P.height) return;
+        unsigned long long k[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) k[j] = gkeys[j * 32 + lane];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) if (k[j] != KEY_EMPTY) gkeys[j * 32 + lane] = KEY_EMPTY;   // leave the buffer clean for the next frame
+        #pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            const int q = j >> 1, h = j & 1;
+            const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7), py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
+            if (px < P.width && py < P.height) resolve_pixel(P, k[j], px, py);
+        }
+        return;
+    }
 
     // stage the bin's keys (what the small-triangle path left in L2) and reset them for the next frame
     {
-        ulonglong2* g = reinterpret_cast<ulonglong2*>(P.keys + (size_t)bin * KEYS_PER_BIN);
-        ulonglong2* s = reinterpret_cast<ulonglong2*>(S.keys);
-        const ulonglong2 empty = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+        unsigned long long* skeys = S.keys + warp * 256;
         #pragma unroll
-        for (int k = 0; k < KEYS_PER_BIN / 2 / TILE_THREADS; k++) {
-            const int at = tid + k * TILE_THREADS;
-            s[at] = g[at];
-            g[at] = empty;
+        for (int j = 0; j < 8; j++) {
+            const unsigned long long k = gkeys[j * 32 + lane];
+            skeys[j * 32 + lane] = k;
+            if (k != KEY_EMPTY) gkeys[j * 32 + lane] = KEY_EMPTY;
         }
     }
-    if (tid == 0) { S.survCount = 0; S.binU = order_f32(1.0f); }
+    if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; }
     __syncthreads();
 
-    // sweep the large-triangle list: exact reject + hierarchical-Z against the bin, survivors to smem
-    const uint32_t nBig = min(P.counters->nBig, P.bigCap);
-    const bool hiz = P.hiz && P.hierarchical;
-    for (uint32_t base = 0; base < nBig; base += TILE_THREADS) {
-        if (S.survCount > SURV_CAP - TILE_THREADS) {          // uniform: read after a barrier
-            raster_survivors(P, S, ox, oy);
-            __syncthreads();
-            if (tid == 0) S.survCount = 0;
+    const bool hizOn = P.hiz && P.hierarchical;
+    uint32_t cursor = 0;                                       // next entry of the tile-path list (uniform)
+    while (cursor < nBig) {
+        // 1. candidates: a 4-byte bin box per triangle filters the list before any record is loaded
+        while (cursor < nBig && S.candCount <= CAND_CAP - 4 * TILE_THREADS) {     // uniform: read after a barrier
+            const uint32_t i = cursor + 4u * tid;
+            if (i < nBig) {
+                uint32_t box[4];
+                if (i + 3 < nBig) {
+                    const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(P.bigBox + i));
+                    box[0] = b4.x; box[1] = b4.y; box[2] = b4.z; box[3] = b4.w;
+                } else {
+                    #pragma unroll
+                    for (int k = 0; k < 4; k++) box[k] = (i + k < nBig) ? __ldg(P.bigBox + i + k) : 0xFFu;   // x0=255 > x1=0: never matches
+                }
+                #pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (bin_in_box(box[k], bx, by)) S.cand[atomicAdd(&S.candCount, 1u)] = i + k;
+            }
+            cursor += 4u * TILE_THREADS;
             __syncthreads();
         }
-        const uint32_t i = base + tid;
-        if (i < nBig) {
-            BigRec r;
-            const int4* src = reinterpret_cast<const int4*>(P.big + i);
-            int4* dst = reinterpret_cast<int4*>(&r);
-            dst[0] = __ldg(src); dst[1] = __ldg(src + 1); dst[2] = __ldg(src + 2);
-            bool rej, full; float zl, zh;
-            classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, rej, full, zl, zh);
-            if (!rej) {
-                bool keep = true;
+        const uint32_t nCand = S.candCount;
+        const bool hiz = hizOn && nCand >= HIZ_MIN_CAND;
+        // 2. hierarchical Z: the bin's depth upper bound = nearest far side of any candidate that covers
+        //    every pixel of the bin
+        if (hiz) {
+            uint32_t u = order_f32(1.0f);
+            for (uint32_t j = tid; j < nCand; j += TILE_THREADS) {
+                BigRec r;
+                load_big(P.big + S.cand[j], r);
+                bool rej, full; float zl, zh;
+                classify_rect(r, ox, oy, BIN, P.width, P.height, true, rej, full, zl, zh);
+                if (!rej && full && zh <= 1.0f) u = min(u, order_f32(zh));
+            }
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) u = min(u, __shfl_xor_sync(0xFFFFFFFFu, u, o));
+            if (lane == 0 && u != order_f32(1.0f)) atomicMin(&S.binU, u);
+            __syncthreads();
+        }
+        // 3. exact reject + depth cull against the bin; survivors go to shared memory and are rasterised
+        //    whenever the list fills up
+        for (uint32_t base = 0; base < nCand; base += TILE_THREADS) {
+            if (S.survCount > SURV_CAP - TILE_THREADS) {          // uniform: read after a barrier
+                raster_survivors(P, S, ox, oy, hiz);
+                __syncthreads();
                 if (hiz) {
-                    keep = order_f32(zl) <= S.binU;            // racy read of a monotonically shrinking bound: conservative
-                    if (full && zh <= 1.0f) atomicMin(&S.binU, order_f32(zh));
+                    // what is now stored in the bin bounds everything still to come
+                    if (tx0 < P.width && ty0 < P.height) {
+                        const uint32_t m = tile_key_max(S.keys + warp * 256, tx0, ty0, P.width, P.height);
+                        if (lane == 0) atomicMax(&S.keyMax, m);
+                    }
+                    __syncthreads();
+                    if (tid == 0) { S.binU = min(S.binU, S.keyMax); S.keyMax = 0; }
                 }
-                if (keep) {
+                if (tid == 0) S.survCount = 0;
+                __syncthreads();
+            }
+            const uint32_t j = base + tid;
+            if (j < nCand) {
+                BigRec r;
+                load_big(P.big + S.cand[j], r);
+                bool rej, full; float zl, zh;
+                classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, rej, full, zl, zh);
+                if (!rej && (!hiz || order_f32(zl) <= S.binU)) {
                     const uint32_t at = atomicAdd(&S.survCount, 1u);
                     int4* d2 = reinterpret_cast<int4*>(&S.surv[at]);
-                    d2[0] = dst[0]; d2[1] = dst[1]; d2[2] = dst[2];
+                    const int4* s2 = reinterpret_cast<const int4*>(&r);
+                    d2[0] = s2[0]; d2[1] = s2[1]; d2[2] = s2[2]; d2[3] = s2[3];
                 }
             }
+            __syncthreads();
         }
+        if (tid == 0) S.candCount = 0;
         __syncthreads();
     }
-    raster_survivors(P, S, ox, oy);
+    raster_survivors(P, S, ox, oy, hizOn && S.survCount >= HIZ_MIN_CAND);
     __syncwarp();
 
     // resolve: every warp finishes its own tile; each pixel is written to HBM exactly once
-    const int warp = tid >> 5, lane = tid & 31;
-    const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
     if (tx0 >= P.width || ty0 >= P.height) return;
     const unsigned long long* tkeys = S.keys + warp * 256;
     #pragma unroll 1
-    for (int q = 0; q < 4; q++) {
-        const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7);
-        #pragma unroll 1
-        for (int h = 0; h < 2; h++) {
-            const int py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
-            if (px >= P.width || py >= P.height) continue;
-            const unsigned long long key = tkeys[q * 64 + lane + 32 * h];
-            const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);   // bottom-up, FrameBuffer.cpp:41
-            const bool hit = key != KEY_EMPTY;
-            P.depth[at] = hit ? key_depth(key) : 1.0f;
-            if (P.captureIds) P.ids[at] = hit ? key_prim(key) : 0xFFFFFFFFu;
-            if (P.shader != SH_DEPTH_ONLY)
-                P.color[at] = hit ? shade_pixel(P, key_prim(key), px, py) : make_uchar4(0, 0, 0, 0);
-        }
+    for (int j = 0; j < 8; j++) {
+        const int q = j >> 1, h = j & 1;
+        const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7), py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
+        if (px < P.width && py < P.height) resolve_pixel(P, tkeys[q * 64 + lane + 32 * h], px, py);
     }
 }
 

@@ -37,13 +37,14 @@ struct edx_context {
     float eye[3], light[3], albedo[3];
     int shader = EDX_SHADER_BLINN_PHONG;
     int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
-    int smallMax = 8, hiz = 1;
+    int smallMax = 16, smallMaxClip = 8, hiz = 1;
     bool colorDirty = false;
 
     unsigned long long* keys = nullptr;
     uchar4* color = nullptr; float* depth = nullptr; uint32_t* ids = nullptr;
     uchar4* extColor = nullptr; float* extDepth = nullptr;      // caller-owned render targets (optional)
     BigRec* big = nullptr; uint32_t bigCap = 0;
+    uint32_t* bigBox = nullptr; uint32_t bigBoxCap = 0;
     uint32_t* clipQueue = nullptr; uint32_t clipQueueCap = 0;
     ClipRec* clipRecs = nullptr; uint32_t clipRecCap = 0;
     Counters* counters = nullptr;
@@ -127,12 +128,14 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     memcpy(P.raster, c->raster.m, 64);
     memcpy(P.eye, c->eye, 12); memcpy(P.light, c->light, 12); memcpy(P.albedo, c->albedo, 12);
     P.width = (int)c->width; P.height = (int)c->height; P.binsX = (int)c->binsX; P.binsY = (int)c->binsY;
-    P.shader = c->shader; P.smallMax = c->smallMax; P.hiz = c->hiz; P.hierarchical = c->hierarchical;
+    P.shader = c->shader; P.smallMax = c->smallMax; P.smallMaxClip = c->smallMaxClip; P.hiz = c->hiz; P.hierarchical = c->hierarchical;
     P.captureIds = c->captureIds; P.dump = 0;
+    const float* Rm = c->raster.m;
+    P.rasterAffineXY = (Rm[2] == 0.0f && Rm[6] == 0.0f && Rm[12] == 0.0f && Rm[13] == 0.0f && Rm[14] == 0.0f && Rm[15] == 1.0f) ? 1 : 0;
     P.pos4 = m->pos4; P.nrm4 = m->nrm4; P.i0 = m->i0; P.i1 = m->i1; P.i2 = m->i2;
     P.nTris = m->nTris; P.nVerts = m->nVerts;
     P.keys = c->keys;
-    P.big = c->big; P.bigCap = c->bigCap;
+    P.big = c->big; P.bigCap = c->bigCap; P.bigBox = c->bigBox;
     P.clipQueue = c->clipQueue; P.clipQueueCap = c->clipQueueCap;
     P.clipRecs = c->clipRecs; P.clipRecCap = c->clipRecCap;
     P.clipSlot = m->clipSlot;
@@ -145,6 +148,7 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
 {
     // initial queue sizes; grown on demand after a frame reports it needed more
     if (int r = grow(c, c->big, c->bigCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
+    if (int r = grow(c, c->bigBox, c->bigBoxCap, c->bigCap)) return r;
     if (int r = grow(c, c->clipQueue, c->clipQueueCap, std::max<uint64_t>(1u << 14, m->nTris / 32))) return r;
     if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
 
@@ -202,6 +206,7 @@ int finish_frame(edx_context* c)
         }
         // a clip-queue overflow hides fan triangles, so size the dependent queues generously too
         if (int r = grow(c, c->big, c->bigCap, (uint64_t)k.nBig + (k.nClipQueue > c->clipQueueCap ? 7ull * k.nClipQueue : 0))) return r;
+        if (int r = grow(c, c->bigBox, c->bigBoxCap, c->bigCap)) return r;
         if (int r = grow(c, c->clipQueue, c->clipQueueCap, k.nClipQueue)) return r;
         if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(k.nClipRecs, 7ull * std::min<uint64_t>(k.nClipQueue, c->clipQueueCap)))) return r;
         c->stats.regrow_count++;
@@ -276,7 +281,7 @@ void edx_destroy(edx_context* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     release_frame_buffers(c);
-    dev_free(c->big); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->counters);
+    dev_free(c->big); dev_free(c->bigBox); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& e : c->evTimer) if (e) cudaEventDestroy(e);
     for (auto& e : c->evStage) if (e) cudaEventDestroy(e);
@@ -365,6 +370,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
 {
     if (!c || !name) return EDX_ERR_INVALID;
     if (!strcmp(name, "small_max")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max in [0,64]"); c->smallMax = value; return EDX_OK; }
+    if (!strcmp(name, "small_max_clip")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max_clip in [0,64]"); c->smallMaxClip = value; return EDX_OK; }
     if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }
     return fail(c, EDX_ERR_INVALID, std::string("unknown option ") + name);
 }
