@@ -1,0 +1,51 @@
+// headless_viewer.cpp — the reference's RealtimeViewer (RealtimeViewer/Main.cpp) without the window:
+// same calls in the same order (OnInit :32-62, OnRender :65-75), frames go to a BMP instead of
+// glDrawPixels. Usage: headless_viewer [frames] [out.bmp] [dump.bin]
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../include/edxraster/Renderer.h"
+
+using namespace edx_b200;
+
+int main(int argc, char** argv)
+{
+    const int frames = argc > 1 ? std::atoi(argv[1]) : 100;
+    const char* out = argc > 2 ? argv[2] : "frame.bmp";
+    const int W = 1280, H = 720;                                   // Main.cpp:18-19
+
+    Renderer renderer;                                             // Main.cpp:37
+    renderer.Initialize(W, H);                                     // Main.cpp:38
+    if (renderer.LastStatus() != EDX_OK) { std::fprintf(stderr, "init failed: %s\n", renderer.LastError()); return 1; }
+    Camera camera;
+    camera.Init(Vector3(0, 0, -5), Vector3(0, 0, 0), Vector3(0, 1, 0), W, H, 65, 0.01f);   // Main.cpp:39
+    Mesh mesh;
+    mesh.LoadSphere(Vector3(0, 0, 0), Vector3(1, 1, 1), Vector3(0, 0, 0), 1.2f);            // Main.cpp:42
+    renderer.SetPixelShader(PixelShaderKind::BlinnPhong);
+
+    auto t0 = std::chrono::steady_clock::now();
+    for (int f = 0; f < frames; f++) {                             // OnRender
+        camera.Transform();
+        renderer.SetTransform(camera.GetViewMatrix(), camera.GetProjMatrix(), camera.GetRasterMatrix());   // Main.cpp:71
+        renderer.RenderMesh(mesh);                                 // Main.cpp:72
+        const _byte* px = renderer.GetBackBuffer();                // Main.cpp:75
+        if (!px) { std::fprintf(stderr, "frame failed: %s\n", renderer.LastError()); return 1; }
+    }
+    double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("Image Res: %i, %i\nTriangle Count: %u\n%.1f frames/s (render + read-back)\n", W, H,
+                mesh.GetIndexBuffer()->GetTriangleCount(), frames / s);
+    if (!renderer.WriteFrame(out)) { std::fprintf(stderr, "write failed: %s\n", renderer.LastError()); return 1; }
+    if (argc > 3) {                                                // raw inputs, so a test can replay them
+        FILE* f = std::fopen(argv[3], "wb");
+        uint32_t hdr[4] = { (uint32_t)W, (uint32_t)H, mesh.GetVertexBuffer()->GetVertexCount(), mesh.GetIndexBuffer()->GetTriangleCount() };
+        std::fwrite(hdr, 4, 4, f);
+        std::fwrite(camera.GetViewMatrix().Data(), 4, 16, f);
+        std::fwrite(camera.GetProjMatrix().Data(), 4, 16, f);
+        std::fwrite(camera.GetRasterMatrix().Data(), 4, 16, f);
+        std::fwrite(mesh.GetVertexBuffer()->GetBuffer(), 32, hdr[2], f);
+        std::fwrite(mesh.GetIndexBuffer()->GetBuffer(), 12, hdr[3], f);
+        std::fclose(f);
+    }
+    return 0;
+}

@@ -1,0 +1,300 @@
+// edxraster/Renderer.h — C++ host API with the reference's renderer-facing names, over the C ABI.
+//
+// Mirrors EDX::RasterRenderer::Renderer (EDXRaster/Core/Renderer.h:36-50), Mesh (Utils/Mesh.h:17-69),
+// IVertexBuffer / VertexBuffer / IndexBuffer (Utils/InputBuffer.h:43-205) and the parts of EDXUtil the
+// viewer touches (Matrix, Vector3, Camera; RealtimeViewer/Main.cpp:37-42,69-75). A program written
+// against the reference's Renderer compiles against this header by switching the namespace; everything
+// executes in libedxraster_b200.so (CUDA, sm_100a). Header-only; link with -ledxraster_b200.
+//
+// Differences, all additive: SetPixelShader (the reference hard-codes its shader, Renderer.cpp:41),
+// GetDepthBuffer, a device ordinal in the constructor, and status codes through LastStatus()/LastError()
+// (the reference has void returns and no error reporting).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../edxraster_c.h"
+
+namespace edx_b200 {
+
+typedef unsigned int uint;
+typedef unsigned char _byte;
+
+struct Vector2 { float x, y; Vector2(float x_ = 0, float y_ = 0) : x(x_), y(y_) {} };
+struct Vector3 {
+    float x, y, z;
+    Vector3(float x_ = 0, float y_ = 0, float z_ = 0) : x(x_), y(y_), z(z_) {}
+    Vector3 operator-(const Vector3& b) const { return Vector3(x - b.x, y - b.y, z - b.z); }
+    Vector3 operator+(const Vector3& b) const { return Vector3(x + b.x, y + b.y, z + b.z); }
+    Vector3 operator*(float s) const { return Vector3(x * s, y * s, z * s); }
+    static float Dot(const Vector3& a, const Vector3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+    static Vector3 Cross(const Vector3& a, const Vector3& b) { return Vector3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+    static Vector3 Normalize(const Vector3& v) { float l = std::sqrt(Dot(v, v)); return Vector3(v.x / l, v.y / l, v.z / l); }
+};
+
+// 4x4, m[row][col], column-vector convention (clip = Proj * ModelView * p; Renderer.cpp:90)
+class Matrix {
+public:
+    float m[4][4];
+    Matrix() { std::memset(m, 0, sizeof(m)); m[0][0] = m[1][1] = m[2][2] = m[3][3] = 1.0f; }
+    const float* Data() const { return &m[0][0]; }
+    Matrix operator*(const Matrix& b) const
+    {
+        Matrix r;
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++)
+                r.m[i][j] = ((m[i][0] * b.m[0][j] + m[i][1] * b.m[1][j]) + m[i][2] * b.m[2][j]) + m[i][3] * b.m[3][j];
+        return r;
+    }
+    static Matrix LookAt(const Vector3& eye, const Vector3& target, const Vector3& up)      // left-handed
+    {
+        Vector3 z = Vector3::Normalize(target - eye), x = Vector3::Normalize(Vector3::Cross(up, z)), y = Vector3::Cross(z, x);
+        Matrix r;
+        r.m[0][0] = x.x; r.m[0][1] = x.y; r.m[0][2] = x.z; r.m[0][3] = -Vector3::Dot(x, eye);
+        r.m[1][0] = y.x; r.m[1][1] = y.y; r.m[1][2] = y.z; r.m[1][3] = -Vector3::Dot(y, eye);
+        r.m[2][0] = z.x; r.m[2][1] = z.y; r.m[2][2] = z.z; r.m[2][3] = -Vector3::Dot(z, eye);
+        return r;
+    }
+    static Matrix Perspective(float fovYDeg, float aspect, float zn, float zf)            // D3D depth: z in [0, w]
+    {
+        const float ys = 1.0f / std::tan(fovYDeg * 3.14159265358979323846f / 360.0f);
+        Matrix r;
+        r.m[0][0] = ys / aspect; r.m[1][1] = ys; r.m[2][2] = zf / (zf - zn); r.m[2][3] = -zn * zf / (zf - zn);
+        r.m[3][2] = 1.0f; r.m[3][3] = 0.0f;
+        return r;
+    }
+    static Matrix Raster(int w, int h)                                                    // NDC -> pixels, y down
+    {
+        Matrix r;
+        r.m[0][0] = w * 0.5f; r.m[0][3] = w * 0.5f; r.m[1][1] = -h * 0.5f; r.m[1][3] = h * 0.5f;
+        return r;
+    }
+};
+
+// Stand-in for EDXUtil's Camera as the viewer uses it (Main.cpp:39,69-71,146)
+class Camera {
+public:
+    void Init(const Vector3& pos, const Vector3& target, const Vector3& up, int w, int h, float fov = 65.0f, float zn = 0.01f, float zf = 100.0f)
+    {
+        mPos = pos; mTarget = target; mUp = up; mFov = fov; mNear = zn; mFar = zf;
+        Resize(w, h);
+    }
+    void Resize(int w, int h)
+    {
+        mW = w; mH = h;
+        mView = Matrix::LookAt(mPos, mTarget, mUp);
+        mProj = Matrix::Perspective(mFov, float(w) / float(h), mNear, mFar);
+        mRaster = Matrix::Raster(w, h);
+    }
+    void Transform() {}
+    const Matrix& GetViewMatrix() const { return mView; }
+    const Matrix& GetProjMatrix() const { return mProj; }
+    const Matrix& GetRasterMatrix() const { return mRaster; }
+    Vector3 mPos, mTarget, mUp;
+private:
+    float mFov = 65, mNear = 0.01f, mFar = 100; int mW = 0, mH = 0;
+    Matrix mView, mProj, mRaster;
+};
+
+// ---- Utils/InputBuffer.h ---------------------------------------------------------------------
+struct Vertex_PositionNormalTex { Vector3 Position; Vector3 Normal; Vector2 TexCoord; static const int Size = 32; };
+static_assert(sizeof(Vertex_PositionNormalTex) == 32, "submission format is 32 bytes per vertex (InputBuffer.h:16-28)");
+
+class IVertexBuffer {
+public:
+    virtual ~IVertexBuffer() {}
+    virtual void* GetBuffer() const = 0;
+    virtual int GetVertexSize() const = 0;
+    virtual size_t GetBufferSize() const = 0;
+    virtual Vector3 GetPosition(uint idx) const = 0;
+    virtual Vector3 GetNormal(uint idx) const = 0;
+    virtual Vector2 GetTexCoord(uint idx) const = 0;
+    uint GetVertexCount() const { return mVertexCount; }
+protected:
+    uint mVertexCount = 0;
+};
+
+template <typename VertexType = Vertex_PositionNormalTex>
+class VertexBuffer : public IVertexBuffer {
+public:
+    void NewBuffer(uint n) { mVertexCount = n; mData.resize(n); }
+    void* GetBuffer() const override { return (void*)mData.data(); }
+    int GetVertexSize() const override { return VertexType::Size; }
+    size_t GetBufferSize() const override { return mData.size() * sizeof(VertexType); }
+    Vector3 GetPosition(uint i) const override { return mData[i].Position; }
+    Vector3 GetNormal(uint i) const override { return mData[i].Normal; }
+    Vector2 GetTexCoord(uint i) const override { return mData[i].TexCoord; }
+private:
+    std::vector<VertexType> mData;
+};
+
+template <typename VertexType = Vertex_PositionNormalTex>
+inline IVertexBuffer* CreateVertexBuffer(const void* pData, size_t vertexCount)     // InputBuffer.h:136-146
+{
+    auto* vb = new VertexBuffer<VertexType>;
+    vb->NewBuffer((uint)vertexCount);
+    std::memcpy(vb->GetBuffer(), pData, vb->GetBufferSize());
+    return vb;
+}
+
+class IndexBuffer {                                                                  // InputBuffer.h:148-194
+public:
+    void ResizeBuffer(uint triCount) { mBuffer.resize(3 * (size_t)triCount); }
+    uint* GetBuffer() { return mBuffer.data(); }
+    const uint* GetBuffer() const { return mBuffer.data(); }
+    uint GetTriangleCount() const { return (uint)(mBuffer.size() / 3); }
+    size_t GetBufferSize() const { return mBuffer.size(); }
+    const uint* GetIndex(uint idx) const { return &mBuffer[3 * (size_t)idx]; }
+    void AppendTriangle(int a, int b, int c) { mBuffer.push_back(a); mBuffer.push_back(b); mBuffer.push_back(c); }
+private:
+    std::vector<uint> mBuffer;
+};
+
+inline IndexBuffer* CreateIndexBuffer(const void* pData, size_t triCount)           // InputBuffer.h:196-205
+{
+    auto* ib = new IndexBuffer;
+    ib->ResizeBuffer((uint)triCount);
+    std::memcpy(ib->GetBuffer(), pData, ib->GetBufferSize() * sizeof(uint));
+    return ib;
+}
+
+// ---- Utils/Mesh.h ----------------------------------------------------------------------------
+class Mesh {
+public:
+    ~Mesh() { Release(); }
+    // The reference delegates these to EDXUtil's ObjMesh (Mesh.cpp:36-70), which is unavailable; the
+    // generators below are ours (UV sphere, slices x stacks quads; unit plane in the xz-plane).
+    void LoadSphere(const Vector3& pos, const Vector3& scl, const Vector3& rot, float radius, int slices = 64, int stacks = 64)
+    {
+        (void)rot;
+        std::vector<Vertex_PositionNormalTex> v;
+        std::vector<uint> idx;
+        const double PI = 3.14159265358979323846;
+        for (int i = 0; i <= stacks; i++)
+            for (int j = 0; j <= slices; j++) {
+                double t = PI * i / stacks, p = 2.0 * PI * j / slices;
+                Vector3 n((float)(std::sin(t) * std::cos(p)), (float)std::cos(t), (float)(std::sin(t) * std::sin(p)));
+                Vertex_PositionNormalTex o;
+                o.Position = Vector3(pos.x + scl.x * radius * n.x, pos.y + scl.y * radius * n.y, pos.z + scl.z * radius * n.z);
+                o.Normal = n;
+                o.TexCoord = Vector2((float)(p / (2.0 * PI)), (float)(t / PI));
+                v.push_back(o);
+            }
+        for (int i = 0; i < stacks; i++)
+            for (int j = 0; j < slices; j++) {
+                uint a = i * (slices + 1) + j, b = a + 1, c = a + slices + 1, d = c + 1;
+                idx.insert(idx.end(), { a, b, c, b, d, c });
+            }
+        SetBuffers(v.data(), v.size(), idx.data(), idx.size() / 3);
+    }
+    void LoadPlane(const Vector3& pos, const Vector3& scl, const Vector3& rot, float length)
+    {
+        (void)rot;
+        const float h = 0.5f * length;
+        Vertex_PositionNormalTex v[4];
+        const float sx[4] = { -h, h, -h, h }, sz[4] = { -h, -h, h, h };
+        for (int k = 0; k < 4; k++) {
+            v[k].Position = Vector3(pos.x + scl.x * sx[k], pos.y, pos.z + scl.z * sz[k]);
+            v[k].Normal = Vector3(0, 1, 0);
+            v[k].TexCoord = Vector2(k & 1 ? 1.0f : 0.0f, k & 2 ? 1.0f : 0.0f);
+        }
+        const uint idx[6] = { 0, 2, 1, 1, 2, 3 };
+        SetBuffers(v, 4, idx, 2);
+    }
+    // raw submission in the reference's wire format (CreateVertexBuffer / CreateIndexBuffer)
+    void SetBuffers(const void* vertices, size_t vertexCount, const uint* indices, size_t triCount)
+    {
+        Release();
+        mpVertexBuf.reset(CreateVertexBuffer<>(vertices, vertexCount));
+        mpIndexBuf.reset(CreateIndexBuffer(indices, triCount));
+        mTexIdx.assign(triCount, 0u);
+    }
+    const IVertexBuffer* GetVertexBuffer() const { return mpVertexBuf.get(); }
+    IndexBuffer* GetIndexBuffer() const { return mpIndexBuf.get(); }
+    const std::vector<uint>& GetTextureIds() const { return mTexIdx; }
+    void Release()
+    {
+        if (mDevice && mOwner) edx_mesh_destroy(mOwner, mDevice);
+        mDevice = nullptr; mOwner = nullptr;
+        mpVertexBuf.reset(); mpIndexBuf.reset(); mTexIdx.clear();
+    }
+private:
+    friend class Renderer;
+    std::unique_ptr<IVertexBuffer> mpVertexBuf;
+    std::unique_ptr<IndexBuffer> mpIndexBuf;
+    std::vector<uint> mTexIdx;
+    mutable edx_mesh* mDevice = nullptr;        // device copy, made on first RenderMesh
+    mutable edx_context* mOwner = nullptr;
+};
+
+enum class TextureFilter { Nearest = 0, Linear = 1, TriLinear = 2, Anisotropic4x = 3, Anisotropic8x = 4, Anisotropic16x = 5 };
+enum class PixelShaderKind { DepthOnly = EDX_SHADER_DEPTH_ONLY, BlinnPhong = EDX_SHADER_BLINN_PHONG, Lambertian = EDX_SHADER_LAMBERT, LambertianAlbedo = EDX_SHADER_LAMBERT_ALBEDO };
+
+// ---- Core/Renderer.h -------------------------------------------------------------------------
+class Renderer {
+public:
+    explicit Renderer(int device = 0) { mStatus = edx_create(device, &mCtx); }
+    ~Renderer() { if (mCtx) edx_destroy(mCtx); }
+    Renderer(const Renderer&) = delete;
+    Renderer& operator=(const Renderer&) = delete;
+
+    void Initialize(uint w, uint h) { mW = w; mH = h; Call(edx_initialize(mCtx, w, h)); }
+    void Resize(uint w, uint h) { mW = w; mH = h; Call(edx_resize(mCtx, w, h)); }
+    void SetTransform(const Matrix& modelView, const Matrix& proj, const Matrix& toRaster)
+    {
+        Call(edx_set_transform(mCtx, modelView.Data(), proj.Data(), toRaster.Data()));
+    }
+    void RenderMesh(const Mesh& mesh)
+    {
+        if (!mCtx) return;
+        if (!mesh.mDevice || mesh.mOwner != mCtx) {
+            if (mesh.mDevice && mesh.mOwner) edx_mesh_destroy(mesh.mOwner, mesh.mDevice);
+            mesh.mDevice = nullptr;
+            const IVertexBuffer* vb = mesh.GetVertexBuffer();
+            IndexBuffer* ib = mesh.GetIndexBuffer();
+            if (!vb || !ib) { mStatus = EDX_ERR_INVALID; return; }
+            Call(edx_mesh_create(mCtx, vb->GetBuffer(), vb->GetVertexCount(), ib->GetBuffer(), ib->GetTriangleCount(),
+                                 mesh.GetTextureIds().data(), &mesh.mDevice));
+            mesh.mOwner = mCtx;
+            if (mStatus != EDX_OK) return;
+        }
+        Call(edx_render_mesh(mCtx, mesh.mDevice));
+        if (mWriteFrames) WriteFrameToFile();
+        mFrameCount++;
+    }
+    void WriteFrameToFile() const
+    {
+        char name[64];
+        std::snprintf(name, sizeof(name), "Frame%05i.bmp", mFrameCount);      // Renderer.cpp:355
+        edx_write_frame_to_file(mCtx, name);
+    }
+    const _byte* GetBackBuffer() const { return mCtx ? edx_get_back_buffer(mCtx) : nullptr; }
+    void SetMSAAMode(int msaaCountLog2) { Call(edx_set_msaa_mode(mCtx, msaaCountLog2)); }
+    void SetTextureFilter(TextureFilter f) { Call(edx_set_texture_filter(mCtx, (int)f)); }
+    void SetHierarchicalRasterize(bool h) { Call(edx_set_hierarchical_rasterize(mCtx, h ? 1 : 0)); }
+    void SetWriteFrames(bool wf) { mWriteFrames = wf; }
+
+    // extensions
+    void SetPixelShader(PixelShaderKind k) { Call(edx_set_pixel_shader(mCtx, (int)k)); }
+    bool GetDepthBuffer(float* out) const { return mCtx && edx_read_depth(mCtx, out) == EDX_OK; }
+    bool WriteFrame(const char* path) const { return mCtx && edx_write_frame_to_file(mCtx, path) == EDX_OK; }
+    void Synchronize() { Call(edx_synchronize(mCtx)); }
+    int LastStatus() const { return mStatus; }
+    const char* LastError() const { return mCtx ? edx_last_error(mCtx) : "no CUDA device (edx_create failed)"; }
+    edx_context* Handle() const { return mCtx; }
+    uint Width() const { return mW; }
+    uint Height() const { return mH; }
+private:
+    void Call(int rc) { if (!mCtx) { mStatus = EDX_ERR_NO_DEVICE; return; } mStatus = rc; }
+    edx_context* mCtx = nullptr;
+    int mStatus = EDX_OK;
+    uint mW = 0, mH = 0;
+    bool mWriteFrames = false;
+    int mFrameCount = 0;
+};
+
+} // namespace edx_b200

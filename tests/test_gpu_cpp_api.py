@@ -1,0 +1,41 @@
+"""The C++ host API (include/edxraster/Renderer.h) through the headless viewer example: the program
+mirrors RealtimeViewer/Main.cpp call for call; its frame must match the oracle on the same inputs."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from edxraster_b200 import scenes
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_headless_viewer_matches_oracle(tmp_path):
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
+    bmp, dump = str(tmp_path / "frame.bmp"), str(tmp_path / "dump.bin")
+    out = subprocess.run([os.path.join(ROOT, "examples", "headless_viewer"), "5", bmp, dump], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "Triangle Count: 8192" in out.stdout            # LoadSphere default 64 x 64 (Mesh.h:43-44)
+    raw = open(dump, "rb").read()
+    w, h, nv, nt = struct.unpack("4I", raw[:16])
+    mats = np.frombuffer(raw, np.float32, 48, 16).reshape(3, 4, 4)
+    verts = np.frombuffer(raw, np.float32, nv * 8, 16 + 192).reshape(nv, 8)
+    idx = np.frombuffer(raw, np.uint32, nt * 3, 16 + 192 + nv * 32).reshape(nt, 3)
+    o = orc.Oracle(w, h, 0)
+    o.set_transform(mats[0], mats[1], mats[2])
+    o.set_shader(scenes.SHADER_BLINN_PHONG)
+    o.render(verts, idx)
+    ref = o.color()                                          # bottom-up RGBA
+    data = open(bmp, "rb").read()
+    assert data[:2] == b"BM"
+    off = struct.unpack("<I", data[10:14])[0]
+    bw, bh = struct.unpack("<ii", data[18:26])
+    assert (bw, bh) == (w, h)
+    pix = np.frombuffer(data, np.uint8, w * h * 3, off).reshape(h, w, 3)[..., ::-1]     # BGR -> RGB, bottom-up like ours
+    d = np.abs(pix.astype(np.int32) - ref[..., :3].astype(np.int32))
+    assert d.max() <= 1
+    assert int((ref[..., 3] == 255).sum()) > 50000           # the sphere really is on screen
