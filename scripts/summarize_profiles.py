@@ -1,0 +1,54 @@
+"""Turn gpurun_out/*.csv / *.ncu-rep into the tracked summaries under profiles/ (round-tagged)."""
+import csv, glob, io, json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out = os.path.join(ROOT, "profiles")
+os.makedirs(out, exist_ok=True)
+lines = ["# ncu summaries (%s)" % tag, "",
+         "Launch lists: `ncu --metrics gpu__time_duration.sum --clock-control none` over `scripts/profile_run.py --workload CX --frames 4`",
+         "(cold-cache, serialised: compare SHARES, not absolutes). Full captures: `ncu --set full --clock-control none --import-source on`.", ""]
+traffic = {}
+for w in ("C1", "C2", "C3", "C4"):
+    p = os.path.join(ROOT, "gpurun_out", "launches_%s.csv" % w)
+    if not os.path.exists(p):
+        continue
+    rows = [r for r in csv.reader(open(p)) if len(r) > 5]
+    h = rows[0]
+    ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+    per = {}
+    for r in rows[1:]:
+        per.setdefault(r[ki].split("(")[0], []).append(float(r[vi].replace(",", "")))
+    frame = {k: sum(v[-3:]) / len(v[-3:]) for k, v in per.items() if k in ("geom_kernel", "clip_kernel", "tile_kernel")}
+    tot = sum(frame.values()) or 1
+    lines += ["## %s launch list (ns per launch, mean of last 3 frames)" % w, "", "| kernel | ns | share of frame |", "|---|---|---|"]
+    for k, v in frame.items():
+        lines.append("| %s | %.0f | %.1f %% |" % (k, v, 100 * v / tot))
+    lines.append("| (frame) | %.0f | |" % tot)
+    lines.append("")
+for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "full_*.ncu-rep"))):
+    name = os.path.basename(rep)[5:-8]
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    if len(rows) < 3:
+        continue
+    h = rows[0]
+    want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+            "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct", "smsp__inst_executed.sum"]
+    idx = [(c, h.index(c)) for c in want if c in h]
+    units = rows[1]
+    lines += ["## full capture %s" % name, "", "| " + " | ".join(c for c, _ in idx) + " |", "|" + "---|" * len(idx)]
+    for r in rows[2:]:
+        lines.append("| " + " | ".join((r[i].split("(")[0] if c == "Kernel Name" else r[i] + " " + units[i]) for c, i in idx) + " |")
+        try:
+            kn = r[h.index("Kernel Name")].split("(")[0]
+            rd, wr = float(r[h.index("dram__bytes_read.sum")]), float(r[h.index("dram__bytes_write.sum")])
+            ur, uw = units[h.index("dram__bytes_read.sum")], units[h.index("dram__bytes_write.sum")]
+            mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            traffic.setdefault(name[:2], {})[kn] = rd * mul.get(ur, 1) + wr * mul.get(uw, 1)
+        except Exception:
+            pass
+    lines.append("")
+open(os.path.join(out, "%s_ncu_summary.md" % tag), "w").write("\n".join(lines) + "\n")
+json.dump(traffic, open(os.path.join(out, "traffic.json"), "w"), indent=1, sort_keys=True)
+print("\n".join(lines[:60]))
