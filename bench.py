@@ -164,12 +164,13 @@ def reference_arm(args):
     scene = make_scene(args.workload, args.scale)
     nt = scene.num_tris
     # calibrate: one full frame, then bound the per-step sample so K+W steps end within ~2 minutes
-    t_probe, threads, _, _ = cpu_frames(scene, 0, 1, 1)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    t_probe, threads, _, _ = cpu_frames(scene, ncpu, 1, 1)   # explicit count: torchrun exports OMP_NUM_THREADS=1
     budget = 120.0 / max(1, args.steps + args.warmup)
     limit = None
     if t_probe[0] > budget:
         limit = max(1000, int(nt * budget / t_probe[0]))
-    times, threads, used, st = cpu_frames(scene, 0, args.steps, min(args.warmup, 3), tri_limit=limit)
+    times, threads, used, st = cpu_frames(scene, ncpu, args.steps, min(args.warmup, 3), tri_limit=limit)
     total = sum(times)
     value = used * len(times) / total / 1e6
     sample = ("full frames (%d triangles each)" % used) if limit is None else \
@@ -300,13 +301,11 @@ def ours_arm(args):
     sampler = ClockSampler(local)
     with torch.cuda.stream(stream):
         works = [None, None]
-        # warm-up: at least W steps and at least ~0.3 s so clocks settle
-        t_w = time.perf_counter()
-        i = 0
-        while i < max(args.warmup, 3) or time.perf_counter() - t_w < 0.3:
+        # warm-up: W steps plus a fixed 1000 more so clocks settle (a fixed count: every rank must issue the
+        # same number of gathers)
+        for i in range(max(args.warmup, 3) + 1000):
             step(i, works)
-            i += 1
-            if i % 64 == 0:
+            if i % 64 == 63:
                 drain(works)
                 r.Synchronize()
         drain(works)
@@ -440,7 +439,8 @@ def ours_arm(args):
     if world == 1:
         # CPU baseline on this box's host cores: bounded sample of the same workload
         try:
-            times, threads, used, _ = cpu_frames(sc, 0, 3, 1)
+            ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            times, threads, used, _ = cpu_frames(sc, ncpu, 3, 1)
             v = used * len(times) / sum(times) / 1e6
             line["cpu_baseline"] = {"value": v, "unit": "Mtris/s", "cores": threads, "kind": "port",
                                     "sample": "3 full frames of the same workload after 1 warm-up (%.2f s each)" % (sum(times) / len(times)),

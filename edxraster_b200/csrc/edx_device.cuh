@@ -57,7 +57,8 @@ struct Counters {
     uint32_t nClipQueue;     // straddling triangles queued for the clipper
     uint32_t nClipRecs;      // fan-triangle records written by the clipper
     uint32_t nDump;
-    uint32_t pad[4];
+    uint32_t done;           // tile_kernel CTAs that have finished (ticket for the end-of-frame hand-off)
+    uint32_t pad[3];
 };
 
 struct FrameParams {
@@ -82,6 +83,7 @@ struct FrameParams {
     ClipRec* clipRecs; uint32_t clipRecCap;
     uint32_t* clipSlot;                  // per submitted triangle: first ClipRec of its polygon
     Counters* counters;
+    Counters* hostCounters;              // pinned, device-mapped: the frame's last CTA publishes the counters here
     uchar4* color; float* depth; uint32_t* ids;
     DumpRec* dumpBuf; uint32_t dumpCap;
 };
@@ -123,6 +125,13 @@ __device__ __forceinline__ V4 to_clip(const float* M, float x, float y, float z)
 
 // Stage a2: Clipper::ComputeClipCode, Core/Clipper.h:48-68
 enum { LEFT_BIT = 1, RIGHT_BIT = 2, BOTTOM_BIT = 4, TOP_BIT = 8, NEAR_BIT = 16, FAR_BIT = 32 };
+// true  =>  clip_code(v) == 0 (for NaN components it returns false and the caller computes the code)
+__device__ __forceinline__ bool surely_inside(const V4& v)
+{
+    return fabsf(v.x) <= v.w && fabsf(v.y) <= v.w && v.z >= 0.0f && v.z <= v.w;
+}
+// 1/w of Renderer.cpp:144 (1.0f / 1.0f == 1.0f exactly)
+__device__ __forceinline__ float inv_w(float w) { return w == 1.0f ? 1.0f : __fdiv_rn(1.0f, w); }
 __device__ __forceinline__ uint32_t clip_code(const V4& v)
 {
     uint32_t c = 0;
@@ -156,7 +165,9 @@ struct SetupTri {
 // operations are skipped; x and y are bit-identical for every finite input.
 __device__ __forceinline__ void project_snap(const float* R, bool affineXY, const V4& c, int& sx, int& sy)
 {
-    const float ax = fdiv(c.x, c.w), ay = fdiv(c.y, c.w);
+    // x / 1.0f == x exactly, so orthographic / pre-projected geometry (w == 1) skips the IEEE divisions
+    const bool unitW = c.w == 1.0f;
+    const float ax = unitW ? c.x : fdiv(c.x, c.w), ay = unitW ? c.y : fdiv(c.y, c.w);
     float x, y;
     if (affineXY) {
         x = fadd(fadd(fmul(R[0], ax), fmul(R[1], ay)), R[3]);

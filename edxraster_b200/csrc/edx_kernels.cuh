@@ -118,11 +118,13 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
             // covered pixel. Splitting keeps the long depth/key/atomic sequence out of the divergent
             // coverage loop, so lanes of a warp execute it together instead of one at a time.
             const uint32_t base1 = r1 - (uint32_t)e.bias1, base2 = r2 - (uint32_t)e.bias2;   // unbiased edge 1 / 2 at (x0, y0)
+            const int wm1 = x1 - x0;
             uint32_t lo = 0, hi = 0;
             for (int y = y0; y <= y1; y++) {
                 uint32_t a0 = r0, a1 = r1, a2 = r2, row = 0;
                 for (int x = x0; x <= x1; x++) {
-                    row |= (uint32_t)((int)(a0 | a1 | a2) >= 0) << (x - x0);
+                    // shift the coverage bit (sign of the OR clear) in from the right: pixel dx ends at bit wm1 - dx
+                    row = __funnelshift_l(~(a0 | a1 | a2), row, 1);
                     a0 += sB0; a1 += sB1; a2 += sB2;
                 }
                 const int dy = y - y0;
@@ -132,7 +134,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
             while (lo | hi) {
                 int b;
                 if (lo) { b = __ffs(lo) - 1; lo &= lo - 1; } else { b = 32 + __ffs(hi) - 1; hi &= hi - 1; }
-                const uint32_t dx = (uint32_t)(b & 7), dy = (uint32_t)(b >> 3);
+                const uint32_t dx = (uint32_t)(wm1 - (b & 7)), dy = (uint32_t)(b >> 3);
                 float l0, l1;
                 barycentric((int)(base1 + dx * sB1 + dy * sC1), (int)(base2 + dx * sB2 + dy * sC2), s.invDet, l0, l1);
                 const float d = depth_at(l0, l1, z0, z1, z2);
@@ -193,13 +195,15 @@ __global__ void __launch_bounds__(256) geom_kernel(const __grid_constant__ Frame
     V4 c0 = to_clip(P.mvp, p0.x, p0.y, p0.z);
     V4 c1 = to_clip(P.mvp, p1.x, p1.y, p1.z);
     V4 c2 = to_clip(P.mvp, p2.x, p2.y, p2.z);
-    uint32_t k0 = clip_code(c0), k1 = clip_code(c1), k2 = clip_code(c2);
-    if (k0 | k1 | k2) {
+    if (!(surely_inside(c0) && surely_inside(c1) && surely_inside(c2))) {
+        const uint32_t k0 = clip_code(c0), k1 = clip_code(c1), k2 = clip_code(c2);
+        if (k0 | k1 | k2) {
         if (!(k0 & k1 & k2)) {                       // Clipper.h:107-109: straddles the frustum
             uint32_t at = warp_append(&P.counters->nClipQueue);
             if (at < P.clipQueueCap) P.clipQueue[at] = t;
         }
         return;
+        }
     }
     SetupTri s;
     if (!P.dump) {
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(256) geom_kernel(const __grid_constant__ Frame
         if (!finish_setup(s)) return;
     } else if (!setup_tri(P.raster, P.rasterAffineXY != 0, c0, c1, c2, s)) return;
     // Renderer.cpp:139-147: invW = 1/w, z = z * invW
-    float iw0 = fdiv(1.0f, c0.w), iw1 = fdiv(1.0f, c1.w), iw2 = fdiv(1.0f, c2.w);
+    const float iw0 = inv_w(c0.w), iw1 = inv_w(c1.w), iw2 = inv_w(c2.w);
     route_triangle(P, s, fmul(c0.z, iw0), fmul(c1.z, iw1), fmul(c2.z, iw2), iw0, iw1, iw2, t * 8u, P.smallMax);
 }
 
@@ -319,7 +323,7 @@ __device__ __noinline__ void emit_fan(const FrameParams& P, uint32_t t, int fan,
 {
     SetupTri s;
     const bool ok = setup_tri(P.raster, P.rasterAffineXY != 0, f0, f1, f2, s);
-    const float iwB = fdiv(1.0f, f1.w), iwC = fdiv(1.0f, f2.w);
+    const float iwB = inv_w(f1.w), iwC = inv_w(f2.w);
     if (haveRecs) {
         ClipRec r;
         r.v0x = s.v0x; r.v0y = s.v0y; r.v1x = s.v1x; r.v1y = s.v1y; r.v2x = s.v2x; r.v2y = s.v2y;
@@ -363,23 +367,41 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
             // 3 or 4 vertices in an order fixed by which vertices are inside (Clipper.h:196-229), so it is
             // built with static indices and lives in registers.
             const int plane = (int)planes;
-            const float U[3][3] = { { 1.0f, 0.0f, 0.0f }, { 0.0f, 1.0f, 0.0f }, { 0.0f, 0.0f, 1.0f } };
             const uint32_t in = (plane_inside(plane, c[0]) ? 1u : 0u) | (plane_inside(plane, c[1]) ? 2u : 0u) | (plane_inside(plane, c[2]) ? 4u : 0u);
-            V4 v[4]; float w[4][3]; int nv = 0;
-            #define EDX_ORIG(slot_, i_) { v[slot_] = c[i_]; w[slot_][0] = U[i_][0]; w[slot_][1] = U[i_][1]; w[slot_][2] = U[i_][2]; }
-            #define EDX_CUT(slot_, i_, j_) cut_vertex(plane, c[i_], c[j_], U[i_], U[j_], v[slot_], w[slot_]);
-            switch (in) {
-            case 1: EDX_CUT(0, 0, 1) EDX_CUT(1, 2, 0) EDX_ORIG(2, 0) nv = 3; break;                    // only v0 inside
-            case 2: EDX_CUT(0, 0, 1) EDX_ORIG(1, 1) EDX_CUT(2, 1, 2) nv = 3; break;                    // only v1
-            case 4: EDX_CUT(0, 1, 2) EDX_ORIG(1, 2) EDX_CUT(2, 2, 0) nv = 3; break;                    // only v2
-            case 6: EDX_CUT(0, 0, 1) EDX_ORIG(1, 1) EDX_ORIG(2, 2) EDX_CUT(3, 2, 0) nv = 4; break;     // v0 outside
-            case 5: EDX_CUT(0, 0, 1) EDX_CUT(1, 1, 2) EDX_ORIG(2, 2) EDX_ORIG(3, 0) nv = 4; break;     // v1 outside
-            case 3: EDX_ORIG(0, 1) EDX_CUT(1, 1, 2) EDX_CUT(2, 2, 0) EDX_ORIG(3, 0) nv = 4; break;     // v2 outside
-            default: nv = 0; break;
+            // Exactly two edges cross the plane. In the order Clipper.h:196-229 visits them they are
+            //   in = 1:(0>1),(2>0)  2:(0>1),(1>2)  4:(1>2),(2>0)  6:(0>1),(2>0)  5:(0>1),(1>2)  3:(1>2),(2>0)
+            const bool firstIs01 = (in != 4u && in != 3u), secondIs20 = (in == 1u || in == 4u || in == 6u || in == 3u);
+            const uint32_t ai = firstIs01 ? 0u : 1u, aj = firstIs01 ? 1u : 2u;
+            const uint32_t bi = secondIs20 ? 2u : 1u, bj = secondIs20 ? 0u : 2u;
+            V4 cutA, cutB; float wA[3], wB[3];
+            {
+                const float ua[3] = { ai == 0u ? 1.0f : 0.0f, ai == 1u ? 1.0f : 0.0f, 0.0f };
+                const float uaj[3] = { 0.0f, aj == 1u ? 1.0f : 0.0f, aj == 2u ? 1.0f : 0.0f };
+                cut_vertex(plane, pick3(c, ai), pick3(c, aj), ua, uaj, cutA, wA);
+                const float ub[3] = { 0.0f, bi == 1u ? 1.0f : 0.0f, bi == 2u ? 1.0f : 0.0f };
+                const float ubj[3] = { bj == 0u ? 1.0f : 0.0f, 0.0f, bj == 2u ? 1.0f : 0.0f };
+                cut_vertex(plane, pick3(c, bi), pick3(c, bj), ub, ubj, cutB, wB);
             }
-            #undef EDX_ORIG
-            #undef EDX_CUT
-            if (nv == 3) { v[3] = v[2]; w[3][0] = w[2][0]; w[3][1] = w[2][1]; w[3][2] = w[2][2]; }
+            // assemble the polygon: slot pattern per inside-mask (C = cut, digits = original vertex)
+            //   1:[A,B,0]  2:[A,1,B]  4:[A,2,B]  6:[A,1,2,B]  5:[A,B,2,0]  3:[1,A,B,0]
+            V4 v[4]; float w[4][3]; int nv = (in == 1u || in == 2u || in == 4u) ? 3 : 4;
+            if (in == 0u || in == 7u) nv = 0;
+            int kind[4];           // 0..2 original vertex, 3 = cutA, 4 = cutB
+            switch (in) {
+            case 1: kind[0] = 3; kind[1] = 4; kind[2] = 0; kind[3] = 0; break;
+            case 2: kind[0] = 3; kind[1] = 1; kind[2] = 4; kind[3] = 4; break;
+            case 4: kind[0] = 3; kind[1] = 2; kind[2] = 4; kind[3] = 4; break;
+            case 6: kind[0] = 3; kind[1] = 1; kind[2] = 2; kind[3] = 4; break;
+            case 5: kind[0] = 3; kind[1] = 4; kind[2] = 2; kind[3] = 0; break;
+            default: kind[0] = 1; kind[1] = 3; kind[2] = 4; kind[3] = 0; break;
+            }
+            #pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int kd = kind[k];
+                v[k] = kd == 3 ? cutA : (kd == 4 ? cutB : pick3(c, (uint32_t)kd));
+                #pragma unroll
+                for (int m = 0; m < 3; m++) w[k][m] = kd == 3 ? wA[m] : (kd == 4 ? wB[m] : (kd == m ? 1.0f : 0.0f));
+            }
             bool drop = nv == 0;
             #pragma unroll
             for (int k = 0; k < 4; k++) if (k < nv && v[k].w <= 0.0f) drop = true;                  // Clipper.h:280-287
@@ -391,7 +413,7 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
             const uint32_t slot = atomicAdd(&P.counters->nClipRecs, nFan);
             const bool haveRecs = slot + nFan <= P.clipRecCap;
             if (haveRecs) P.clipSlot[t] = slot;
-            const float iwA = fdiv(1.0f, v[0].w), zA = fmul(v[0].z, iwA);
+            const float iwA = inv_w(v[0].w), zA = fmul(v[0].z, iwA);
             emit_fan(P, t, 0, slot, haveRecs, v[0], v[1], v[2], iwA, zA, src[0] | (src[1] << 2) | (src[2] << 4), w[0], w[1], w[2]);
             if (nv == 4)
                 emit_fan(P, t, 1, slot, haveRecs, v[0], v[2], v[3], iwA, zA, src[0] | (src[2] << 2) | (src[3] << 4), w[0], w[2], w[3]);
@@ -425,7 +447,7 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
         const bool haveRecs = slot + nFan <= P.clipRecCap;
         if (haveRecs) P.clipSlot[t] = slot;
         const V4 f0 = cur->p[0];
-        const float iwA = fdiv(1.0f, f0.w), zA = fmul(f0.z, iwA);
+        const float iwA = inv_w(f0.w), zA = fmul(f0.z, iwA);
         for (int k = 2; k < nv; k++) {                                  // Clipper.h:156-170 fan (0, k-1, k)
             const uint32_t sb = (srcs & 3u) | (((srcs >> (2 * (k - 1))) & 3u) << 2) | (((srcs >> (2 * k)) & 3u) << 4);
             emit_fan(P, t, k - 2, slot, haveRecs, f0, cur->p[k - 1], cur->p[k], iwA, zA, sb, cur->w[0], cur->w[k - 1], cur->w[k]);
@@ -553,7 +575,7 @@ __device__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int p
         SetupTri s;
         setup_tri(P.raster, P.rasterAffineXY != 0, c0, c1, c2, s);
         v0x = s.v0x; v0y = s.v0y; v1x = s.v1x; v1y = s.v1y; v2x = s.v2x; v2y = s.v2y; invDet = s.invDet;
-        iw0 = fdiv(1.0f, c0.w); iw1 = fdiv(1.0f, c1.w); iw2 = fdiv(1.0f, c2.w);
+        iw0 = inv_w(c0.w); iw1 = inv_w(c1.w); iw2 = inv_w(c2.w);
         A[0][0] = p0.x; A[0][1] = p0.y; A[0][2] = p0.z; A[0][3] = n0.x; A[0][4] = n0.y; A[0][5] = n0.z;
         A[1][0] = p1.x; A[1][1] = p1.y; A[1][2] = p1.z; A[1][3] = n1.x; A[1][4] = n1.y; A[1][5] = n1.z;
         A[2][0] = p2.x; A[2][1] = p2.y; A[2][2] = p2.z; A[2][3] = n2.x; A[2][4] = n2.y; A[2][5] = n2.z;
@@ -724,6 +746,23 @@ __device__ __forceinline__ void resolve_pixel(const FrameParams& P, unsigned lon
         P.color[at] = hit ? shade_pixel(P, key_prim(key), px, py) : make_uchar4(0, 0, 0, 0);
 }
 
+// End-of-frame hand-off, called once per CTA when it is done: the last CTA publishes the frame's counters
+// to pinned host memory (the host checks them for queue overflow) and zeroes them for the next frame, so a
+// frame needs no memset before and no copy after it. Every CTA has read nBig before it takes its ticket.
+__device__ __forceinline__ void frame_done(const FrameParams& P)
+{
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    __threadfence();
+    if (atomicAdd(&P.counters->done, 1u) != gridDim.x - 1u) return;
+    volatile Counters* d = P.counters;
+    const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump;
+    d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->done = 0;
+    volatile Counters* h = P.hostCounters;
+    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump;
+    __threadfence_system();
+}
+
 __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_constant__ FrameParams P)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -734,15 +773,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     const uint32_t bx = (uint32_t)(bin % P.binsX), by = (uint32_t)(bin / P.binsX);
     const int ox = (int)bx << BIN_LOG2, oy = (int)by << BIN_LOG2;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
-    const uint32_t nBig = min(P.counters->nBig, P.bigCap);
     unsigned long long* gkeys = P.keys + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
+    // the tile's keys are wanted on every path: issue the loads before the (dependent) counter read
+    unsigned long long k[8];
+    #pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = gkeys[j * 32 + lane];
+    const uint32_t nBig = min(P.counters->nBig, P.bigCap);
 
     if (nBig == 0) {
-        // Nothing on the tile path: resolve straight from the L2-resident keys, no staging, no barrier.
-        if (tx0 >= P.width || ty0 >= P.height) return;
-        unsigned long long k[8];
-        #pragma unroll
-        for (int j = 0; j < 8; j++) k[j] = gkeys[j * 32 + lane];
+        // Nothing on the tile path: resolve straight from the L2-resident keys, no staging.
+        if (tx0 >= P.width || ty0 >= P.height) { frame_done(P); return; }
         #pragma unroll
         for (int j = 0; j < 8; j++) if (k[j] != KEY_EMPTY) gkeys[j * 32 + lane] = KEY_EMPTY;   // leave the buffer clean for the next frame
         #pragma unroll 1
@@ -751,6 +791,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7), py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
             if (px < P.width && py < P.height) resolve_pixel(P, k[j], px, py);
         }
+        frame_done(P);
         return;
     }
 
@@ -759,9 +800,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         unsigned long long* skeys = S.keys + warp * 256;
         #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const unsigned long long k = gkeys[j * 32 + lane];
-            skeys[j * 32 + lane] = k;
-            if (k != KEY_EMPTY) gkeys[j * 32 + lane] = KEY_EMPTY;
+            skeys[j * 32 + lane] = k[j];
+            if (k[j] != KEY_EMPTY) gkeys[j * 32 + lane] = KEY_EMPTY;
         }
     }
     if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; }
@@ -847,14 +887,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     __syncwarp();
 
     // resolve: every warp finishes its own tile; each pixel is written to HBM exactly once
-    if (tx0 >= P.width || ty0 >= P.height) return;
-    const unsigned long long* tkeys = S.keys + warp * 256;
-    #pragma unroll 1
-    for (int j = 0; j < 8; j++) {
-        const int q = j >> 1, h = j & 1;
-        const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7), py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
-        if (px < P.width && py < P.height) resolve_pixel(P, tkeys[q * 64 + lane + 32 * h], px, py);
+    if (tx0 < P.width && ty0 < P.height) {
+        const unsigned long long* tkeys = S.keys + warp * 256;
+        #pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+            const int q = j >> 1, h = j & 1;
+            const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7), py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
+            if (px < P.width && py < P.height) resolve_pixel(P, tkeys[q * 64 + lane + 32 * h], px, py);
+        }
     }
+    frame_done(P);
 }
 
 } // namespace edx

@@ -48,7 +48,8 @@ struct edx_context {
     uint32_t* clipQueue = nullptr; uint32_t clipQueueCap = 0;
     ClipRec* clipRecs = nullptr; uint32_t clipRecCap = 0;
     Counters* counters = nullptr;
-    Counters* hostCounters = nullptr;        // pinned
+    Counters* hostCounters = nullptr;        // pinned + device-mapped
+    Counters* hostCountersDev = nullptr;     // device view of the same memory
     uint8_t* hostColor = nullptr;            // pinned mirror behind GetBackBuffer
     size_t hostColorBytes = 0;
 
@@ -139,7 +140,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.clipQueue = c->clipQueue; P.clipQueueCap = c->clipQueueCap;
     P.clipRecs = c->clipRecs; P.clipRecCap = c->clipRecCap;
     P.clipSlot = m->clipSlot;
-    P.counters = c->counters;
+    P.counters = c->counters; P.hostCounters = c->hostCountersDev;
     P.color = c->extColor ? c->extColor : c->color; P.depth = c->extDepth ? c->extDepth : c->depth; P.ids = c->ids;
 }
 
@@ -164,7 +165,6 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     if (c->shader != EDX_SHADER_DEPTH_ONLY) c->colorDirty = true;
 
     c->launches = 0;
-    EDX_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(Counters), c->stream));
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[0], c->stream));
     if (m->nTris) {
         geom_kernel<<<(m->nTris + 255) / 256, 256, 0, c->stream>>>(P);
@@ -180,7 +180,6 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     c->launches++;
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[3], c->stream));
     EDX_CUDA(c, cudaGetLastError());
-    EDX_CUDA(c, cudaMemcpyAsync(c->hostCounters, c->counters, sizeof(Counters), cudaMemcpyDeviceToHost, c->stream));
     return EDX_OK;
 }
 
@@ -265,7 +264,9 @@ int edx_create(int device, edx_context** out)
     bool ok = cudaSetDevice(device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&c->counters, sizeof(Counters)) == cudaSuccess &&
-              cudaMallocHost(&c->hostCounters, sizeof(Counters)) == cudaSuccess &&
+              cudaHostAlloc(&c->hostCounters, sizeof(Counters), cudaHostAllocMapped) == cudaSuccess &&
+              cudaHostGetDevicePointer((void**)&c->hostCountersDev, c->hostCounters, 0) == cudaSuccess &&
+              cudaMemset(c->counters, 0, sizeof(Counters)) == cudaSuccess &&
               cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess;
     for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&c->evTimer[i]) == cudaSuccess;
     for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&c->evStage[i]) == cudaSuccess;
