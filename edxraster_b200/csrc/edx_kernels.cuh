@@ -506,8 +506,11 @@ __device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0,
 }
 
 // One warp rasterises one triangle into its 16x16 tile: 8x8 block masks by ballot, then pixels.
-// tkeys = the tile's 256 keys in shared memory, laid out [block 2x2][8x8].
-__device__ __forceinline__ void raster_tile_tri(unsigned long long* tkeys, const BigRec& r, int tx0, int ty0,
+// k[8] = this lane's eight keys of the tile, held in REGISTERS for the whole survivor walk (the warp owns
+// the tile, so no atomics and no shared-memory round trip per pixel). Slot j = block (j >> 1), half (j & 1):
+// pixel (tx0 + 8*(q&1) + lane%8, ty0 + 8*(q>>1) + lane/8 + 4*h). The eight pixels are independent, so the
+// fully unrolled body gives the scheduler eight interleaved dependency chains.
+__device__ __forceinline__ void raster_tile_tri(unsigned long long (&k)[8], const BigRec& r, int tx0, int ty0,
                                                 int W, int H, bool full, bool hierarchical)
 {
     const int lane = threadIdx.x & 31;
@@ -521,29 +524,25 @@ __device__ __forceinline__ void raster_tile_tri(unsigned long long* tkeys, const
         rejMask = __ballot_sync(0xFFFFFFFFu, rej) & 0xFu;
         accMask = __ballot_sync(0xFFFFFFFFu, acc) & 0xFu;
     }
-    #pragma unroll 1
-    for (int q = 0; q < 4; q++) {
-        if ((rejMask >> q) & 1u) continue;
-        const bool acc = (accMask >> q) & 1u;
-        const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7);
-        #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
-            if (px < W && py < H) {
-                const int cx = (px << 4) + 8, cy = (py << 4) + 8;
-                const int a1 = e.e1(cx, cy), a2 = e.e2(cx, cy);
-                if (acc || ((e.e0(cx, cy) | a1 | a2) >= 0)) {
-                    float l0, l1;
-                    barycentric(a1 - e.bias1, a2 - e.bias2, r.invDet, l0, l1);
-                    float d = depth_at(l0, l1, r.z0, r.z1, r.z2);
-                    if (d <= 1.0f) {
-                        unsigned long long key = make_key(d, r.prim);
-                        const int at = q * 64 + lane + 32 * h;
-                        if (key < tkeys[at]) tkeys[at] = key;      // the warp owns the tile: no atomics needed
-                    }
-                }
-            }
-        }
+    // biased edge values at this lane's pixel of block 0 / half 0; other slots are integer steps away
+    const int bx = tx0 + (lane & 7), by = ty0 + (lane >> 3);
+    const int cx = (bx << 4) + 8, cy = (by << 4) + 8;
+    const uint32_t e0b = (uint32_t)e.e0(cx, cy), e1b = (uint32_t)e.e1(cx, cy), e2b = (uint32_t)e.e2(cx, cy);
+    const uint32_t lowBias1 = (uint32_t)e.bias1, lowBias2 = (uint32_t)e.bias2;
+    #pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int q = j >> 1, h = j & 1;
+        const uint32_t sx = (uint32_t)((q & 1) * BLOCK_PX * 16), sy = (uint32_t)(((q >> 1) * BLOCK_PX + 4 * h) * 16);   // sub-pixel steps
+        const bool live = !((rejMask >> q) & 1u) && (bx + (q & 1) * BLOCK_PX) < W && (by + (q >> 1) * BLOCK_PX + 4 * h) < H;
+        const uint32_t a0 = e0b + e.B0 * sx + e.C0 * sy, a1 = e1b + e.B1 * sx + e.C1 * sy, a2 = e2b + e.B2 * sx + e.C2 * sy;
+        // branch-free: everything is computed for every slot and committed with one select, so the eight
+        // chains really interleave
+        const bool covered = live && (((accMask >> q) & 1u) || (int)(a0 | a1 | a2) >= 0);
+        float l0, l1;
+        barycentric((int)(a1 - lowBias1), (int)(a2 - lowBias2), r.invDet, l0, l1);
+        const float d = depth_at(l0, l1, r.z0, r.z1, r.z2);
+        const unsigned long long key = make_key(d, r.prim);
+        k[j] = (covered && d <= 1.0f && key < k[j]) ? key : k[j];
     }
 }
 
@@ -665,7 +664,7 @@ __device__ __forceinline__ void slot_pixel(int tx0, int ty0, int lane, int j, in
 }
 
 // Largest ordered depth held by the on-screen pixels of the warp's tile; 0xFFFFFFFF while any is empty.
-__device__ __forceinline__ uint32_t tile_key_max(const unsigned long long* tkeys, int tx0, int ty0, int W, int H)
+__device__ __forceinline__ uint32_t tile_key_max(const unsigned long long (&k)[8], int tx0, int ty0, int W, int H)
 {
     const int lane = threadIdx.x & 31;
     uint32_t m = 0;
@@ -673,7 +672,7 @@ __device__ __forceinline__ uint32_t tile_key_max(const unsigned long long* tkeys
     for (int j = 0; j < 8; j++) {
         int px, py;
         slot_pixel(tx0, ty0, lane, j, px, py);
-        if (px < W && py < H) m = max(m, (uint32_t)(tkeys[j * 32 + lane] >> 32));
+        if (px < W && py < H) m = max(m, (uint32_t)(k[j] >> 32));
     }
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
@@ -691,12 +690,12 @@ __device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShare
     const int n = (int)S.survCount;
     if (tx0 >= P.width || ty0 >= P.height || n == 0) return;
     unsigned long long* tkeys = S.keys + warp * 256;
+    unsigned long long k[8];
+    #pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = tkeys[j * 32 + lane];
     uint32_t U = order_f32(1.0f);
     for (int b = 0; b < n; b += 32) {
-        if (hiz) {
-            __syncwarp();
-            U = min(U, tile_key_max(tkeys, tx0, ty0, P.width, P.height));
-        }
+        if (hiz) U = min(U, tile_key_max(k, tx0, ty0, P.width, P.height));
         const int j = b + lane;
         bool keep = false, full = false;
         uint32_t zlo = 0, zhi = 0xFFFFFFFFu;
@@ -718,9 +717,12 @@ __device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShare
         while (keepMask) {
             const int l = __ffs(keepMask) - 1;
             keepMask &= keepMask - 1;
-            raster_tile_tri(tkeys, S.surv[b + l], tx0, ty0, P.width, P.height, (fullMask >> l) & 1u, P.hierarchical != 0);
+            raster_tile_tri(k, S.surv[b + l], tx0, ty0, P.width, P.height, (fullMask >> l) & 1u, P.hierarchical != 0);
         }
     }
+    #pragma unroll
+    for (int j = 0; j < 8; j++) tkeys[j * 32 + lane] = k[j];
+    __syncwarp();
 }
 
 __device__ __forceinline__ bool bin_in_box(uint32_t box, uint32_t bx, uint32_t by)
@@ -856,7 +858,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                 if (hiz) {
                     // what is now stored in the bin bounds everything still to come
                     if (tx0 < P.width && ty0 < P.height) {
-                        const uint32_t m = tile_key_max(S.keys + warp * 256, tx0, ty0, P.width, P.height);
+                        unsigned long long kk[8];
+                        #pragma unroll
+                        for (int j = 0; j < 8; j++) kk[j] = S.keys[warp * 256 + j * 32 + lane];
+                        const uint32_t m = tile_key_max(kk, tx0, ty0, P.width, P.height);
                         if (lane == 0) atomicMax(&S.keyMax, m);
                     }
                     __syncthreads();
