@@ -15,7 +15,7 @@ SYMBOLS = [
     "edx_set_transform", "edx_set_msaa_mode", "edx_set_texture_filter", "edx_set_hierarchical_rasterize",
     "edx_write_frame_to_file", "edx_set_pixel_shader", "edx_set_albedo", "edx_mesh_create", "edx_mesh_update",
     "edx_mesh_destroy", "edx_render_mesh", "edx_get_back_buffer", "edx_synchronize", "edx_read_depth",
-    "edx_set_capture_ids", "edx_read_winner_ids", "edx_debug_clip_vertices", "edx_debug_raster_triangles",
+    "edx_set_capture_ids", "edx_read_winner_ids", "edx_read_sample", "edx_debug_clip_vertices", "edx_debug_raster_triangles",
     "edx_get_derived_state", "edx_device_color", "edx_device_depth", "edx_set_render_target", "edx_set_stream", "edx_timer_begin",
     "edx_timer_end", "edx_set_profiling", "edx_get_stats", "edx_set_option", "edx_last_launch_count",
 ]
@@ -77,6 +77,7 @@ def load():
     lib.edx_read_depth.argtypes = [vp, f32p]
     lib.edx_set_capture_ids.argtypes = [vp, C.c_int]
     lib.edx_read_winner_ids.argtypes = [vp, u32p]
+    lib.edx_read_sample.argtypes = [vp, C.c_int, f32p, u32p]
     lib.edx_debug_clip_vertices.argtypes = [vp, vp, f32p]
     lib.edx_debug_raster_triangles.argtypes = [vp, vp, C.c_uint64, i32p, f32p, C.POINTER(C.c_uint64)]
     lib.edx_get_derived_state.argtypes = [vp, f32p, f32p, f32p]

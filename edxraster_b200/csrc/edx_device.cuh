@@ -69,6 +69,8 @@ struct FrameParams {
     float albedo[3];
     int width, height, binsX, binsY;
     int shader, smallMax, smallMaxClip, hiz, hierarchical, captureIds, dump;
+    int msLevel, samples;    // Renderer::SetMSAAMode (Renderer.cpp:94-98): samples = 1 << msLevel
+    uint32_t keyStride;      // keys per sample plane
     int rasterAffineXY;      // raster matrix has no z column and w' == 1: skip the unused z/w and w' arithmetic
     // mesh (SoA streams built at upload)
     const float4* pos4;      // x, y, z, texcoord.v
@@ -272,9 +274,26 @@ __device__ __forceinline__ uint32_t key_index(int x, int y, int binsX)
     return ((bin * 16u + tile) * 4u + block) * 64u + (uint32_t)((y & 7) * 8 + (x & 7));
 }
 
+// Sample positions of FrameBuffer::MultiSampleOffsets (FrameBuffer.cpp:107-191): (x, y) pairs in 1/16 pixel
+// relative to the pixel centre, one row per SetMSAAMode level. DESIGN.md shim 17 on how the pairs are read.
+__constant__ int c_sampleOffsets[6][64] = {
+    { 0, 0 },
+    { 4, 4, -4, -4 },
+    { -2, -6, 6, -2, -6, 2, 2, 6 },
+    { 1, -3, -1, 3, 5, 1, -3, -5, -5, 5, -7, -1, 3, 7, 7, -7 },
+    { 1, 1, -1, -3, -3, 2, 4, -1, -5, -2, 2, 5, 5, 3, 3, -5, -2, 6, 0, -7, -4, -6, -6, 4, -8, 0, 7, -4, 6, 7, -7, -8 },
+    { 1, 1, -1, -3, -3, 2, 4, -1, -5, -2, 2, 5, 5, 3, 3, -5, -2, 6, 0, -7, -4, -6, -6, 4, -8, 0, 7, -4, 6, 7, -7, -8,
+      1, 3, -3, -3, -3, 0, 6, -2, -7, -1, 3, 4, 7, 3, 3, -6, -2, 7, 0, -4, -2, -5, -7, 6, -8, 3, 4, -1, 2, 7, 4, -8 },
+};
+
 // pixel-centre range covered by a snapped bounding box: centres sit at 16*i + 8 (Rasterizer.h:23)
 __device__ __forceinline__ int first_centre(int lo) { return (lo + 7) >> 4; }     // ceil((lo - 8) / 16)
 __device__ __forceinline__ int last_centre(int hi) { return (hi - 8) >> 4; }      // floor((hi - 8) / 16)
+// Pixel range that can hold a covered SAMPLE: with MSAA the samples of pixel p lie anywhere in
+// [16p, 16p + 15], so the range is the one the reference walks (Rasterizer.h:211-214); at 1x it is the
+// tighter pixel-centre range.
+__device__ __forceinline__ int first_pixel(int lo, bool ms) { return ms ? (lo >> 4) : first_centre(lo); }
+__device__ __forceinline__ int last_pixel(int hi, bool ms) { return ms ? (hi >> 4) : last_centre(hi); }
 
 __device__ __forceinline__ int min3i(int a, int b, int c) { return min(a, min(b, c)); }
 __device__ __forceinline__ int max3i(int a, int b, int c) { return max(a, max(b, c)); }

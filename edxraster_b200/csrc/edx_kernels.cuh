@@ -98,10 +98,11 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
     // Pixel centres inside the snapped bounding box, clamped to the screen. A covered centre always
     // lies inside the box, so this is the same pixel set the reference visits (Rasterizer.h:132-137)
     // minus pixels that cannot be covered; an empty range is an exact cull.
-    int x0 = max(0, first_centre(min3i(s.v0x, s.v1x, s.v2x)));
-    int x1 = min(P.width - 1, last_centre(max3i(s.v0x, s.v1x, s.v2x)));
-    int y0 = max(0, first_centre(min3i(s.v0y, s.v1y, s.v2y)));
-    int y1 = min(P.height - 1, last_centre(max3i(s.v0y, s.v1y, s.v2y)));
+    const bool ms = P.samples > 1;
+    int x0 = max(0, first_pixel(min3i(s.v0x, s.v1x, s.v2x), ms));
+    int x1 = min(P.width - 1, last_pixel(max3i(s.v0x, s.v1x, s.v2x), ms));
+    int y0 = max(0, first_pixel(min3i(s.v0y, s.v1y, s.v2y), ms));
+    int y1 = min(P.height - 1, last_pixel(max3i(s.v0y, s.v1y, s.v2y), ms));
     if (x0 > x1 || y0 > y1) return;
 
     if (x1 - x0 < smallMax && y1 - y0 < smallMax) {
@@ -113,7 +114,29 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
         uint32_t r0 = (uint32_t)e.e0(cx, cy), r1 = (uint32_t)e.e1(cx, cy), r2 = (uint32_t)e.e2(cx, cy);
         const uint32_t sB0 = e.B0 << 4, sB1 = e.B1 << 4, sB2 = e.B2 << 4;   // one pixel = 16 sub-pixels (RasterTriangle.h:53-58)
         const uint32_t sC0 = e.C0 << 4, sC1 = e.C1 << 4, sC2 = e.C2 << 4;
-        if (x1 - x0 < 8 && y1 - y0 < 8) {
+        if (ms) {
+            // Multi-sample (Rasterizer.h:202-300): every sample of every pixel in the box is an independent
+            // coverage + depth test at centre + offset; its key goes to the sample's own key plane.
+            const int* off = c_sampleOffsets[P.msLevel];
+            for (int y = y0; y <= y1; y++) {
+                uint32_t a0 = r0, a1 = r1, a2 = r2;
+                for (int x = x0; x <= x1; x++) {
+                    const uint32_t ki = key_index(x, y, P.binsX);
+                    for (int sId = 0; sId < P.samples; sId++) {
+                        const uint32_t ox = (uint32_t)off[2 * sId], oy = (uint32_t)off[2 * sId + 1];
+                        const uint32_t f0 = a0 + ox * e.B0 + oy * e.C0, f1 = a1 + ox * e.B1 + oy * e.C1, f2 = a2 + ox * e.B2 + oy * e.C2;
+                        if ((int)(f0 | f1 | f2) >= 0) {
+                            float l0, l1;
+                            barycentric((int)(f1 - (uint32_t)e.bias1), (int)(f2 - (uint32_t)e.bias2), s.invDet, l0, l1);
+                            const float d = depth_at(l0, l1, z0, z1, z2);
+                            if (d <= 1.0f) atomicMin(P.keys + (size_t)sId * P.keyStride + ki, make_key(d, prim));
+                        }
+                    }
+                    a0 += sB0; a1 += sB1; a2 += sB2;
+                }
+                r0 += sC0; r1 += sC1; r2 += sC2;
+            }
+        } else if (x1 - x0 < 8 && y1 - y0 < 8) {
             // Phase 1: coverage only, into a 64-bit mask (bit = 8*dy + dx). Phase 2: one iteration per
             // covered pixel. Splitting keeps the long depth/key/atomic sequence out of the divergent
             // coverage loop, so lanes of a warp execute it together instead of one at a time.
@@ -212,8 +235,9 @@ __global__ void __launch_bounds__(256) geom_kernel(const __grid_constant__ Frame
         project_snap(P.raster, P.rasterAffineXY != 0, c0, s.v0x, s.v0y);
         project_snap(P.raster, P.rasterAffineXY != 0, c1, s.v1x, s.v1y);
         project_snap(P.raster, P.rasterAffineXY != 0, c2, s.v2x, s.v2y);
-        if (max(0, first_centre(min3i(s.v0x, s.v1x, s.v2x))) > min(P.width - 1, last_centre(max3i(s.v0x, s.v1x, s.v2x))) ||
-            max(0, first_centre(min3i(s.v0y, s.v1y, s.v2y))) > min(P.height - 1, last_centre(max3i(s.v0y, s.v1y, s.v2y))))
+        const bool ms = P.samples > 1;
+        if (max(0, first_pixel(min3i(s.v0x, s.v1x, s.v2x), ms)) > min(P.width - 1, last_pixel(max3i(s.v0x, s.v1x, s.v2x), ms)) ||
+            max(0, first_pixel(min3i(s.v0y, s.v1y, s.v2y), ms)) > min(P.height - 1, last_pixel(max3i(s.v0y, s.v1y, s.v2y), ms)))
             return;
         if (!finish_setup(s)) return;
     } else if (!setup_tri(P.raster, P.rasterAffineXY != 0, c0, c1, c2, s)) return;
@@ -470,18 +494,22 @@ __device__ __forceinline__ uint32_t order_f32(float f)
 // corners of RasterTriangle.h:65-150, Renderer.cpp:189-224 and Rasterizer.h:42-85, evaluated at the
 // extreme pixel centres instead of the tile corners (so it is exact rather than conservative).
 // With wantZ it also returns conservative bounds of the depth the triangle can produce in the rect.
-__device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0, int size, int W, int H, bool wantZ,
+__device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0, int size, int W, int H, bool wantZ, bool ms,
                                               bool& reject, bool& full, float& zmin, float& zmax)
 {
     reject = true; full = false; zmin = 0.0f; zmax = 0.0f;
     const int rx1 = min(px0 + size - 1, W - 1), ry1 = min(py0 + size - 1, H - 1);
     if (px0 > rx1 || py0 > ry1) return;
-    const int tx0 = first_centre(min3i(r.v0x, r.v1x, r.v2x)), tx1 = last_centre(max3i(r.v0x, r.v1x, r.v2x));
-    const int ty0 = first_centre(min3i(r.v0y, r.v1y, r.v2y)), ty1 = last_centre(max3i(r.v0y, r.v1y, r.v2y));
+    const int tx0 = first_pixel(min3i(r.v0x, r.v1x, r.v2x), ms), tx1 = last_pixel(max3i(r.v0x, r.v1x, r.v2x), ms);
+    const int ty0 = first_pixel(min3i(r.v0y, r.v1y, r.v2y), ms), ty1 = last_pixel(max3i(r.v0y, r.v1y, r.v2y), ms);
     if (tx0 > rx1 || tx1 < px0 || ty0 > ry1 || ty1 < py0) return;
     Edges e;
     e.init(r.v0x, r.v0y, r.v1x, r.v1y, r.v2x, r.v2y);
-    const int cx0 = (px0 << 4) + 8, cx1 = (rx1 << 4) + 8, cy0 = (py0 << 4) + 8, cy1 = (ry1 << 4) + 8;
+    // 1x: the extreme pixel CENTRES of the rect (exact). MSAA: the extreme sub-pixel positions any sample of
+    // the rect's pixels can take, [16p, 16p + 15] (conservative: reject / full still imply the same for
+    // every sample, they are just no longer "if and only if").
+    const int subLo = ms ? 0 : 8, subHi = ms ? 15 : 8;
+    const int cx0 = (px0 << 4) + subLo, cx1 = (rx1 << 4) + subHi, cy0 = (py0 << 4) + subLo, cy1 = (ry1 << 4) + subHi;
     const bool b0 = (int)e.B0 > 0, c0 = (int)e.C0 > 0, b1 = (int)e.B1 > 0, c1 = (int)e.C1 > 0, b2 = (int)e.B2 > 0, c2 = (int)e.C2 > 0;
     if (e.e0(b0 ? cx1 : cx0, c0 ? cy1 : cy0) < 0) return;
     if (e.e1(b1 ? cx1 : cx0, c1 ? cy1 : cy0) < 0) return;
@@ -494,7 +522,8 @@ __device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0,
     // pixel centres, intersect with the vertex range (covered pixels lie inside the triangle), and widen by
     //   E  = the plane fit's own error bound (perr) + rounding of this evaluation (<= 2.5e-7 of the summed magnitudes)
     //   Ed = fp32 error of barycentric()/depth_at() at a covered pixel (<= ~1.3e-6 * max|z|)
-    const float x0f = (float)px0, x1f = (float)rx1, y0f = (float)py0, y1f = (float)ry1;
+    const float half = ms ? 0.5f : 0.0f;          // samples sit up to half a pixel away from the centre
+    const float x0f = (float)px0 - half, x1f = (float)rx1 + half, y0f = (float)py0 - half, y1f = (float)ry1 + half;
     const float ax0 = r.gx * x0f, ax1 = r.gx * x1f, ay0 = r.gy * y0f, ay1 = r.gy * y1f;
     const float lo = r.zref + fminf(ax0, ax1) + fminf(ay0, ay1);
     const float hi = r.zref + fmaxf(ax0, ax1) + fmaxf(ay0, ay1);
@@ -511,7 +540,7 @@ __device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0,
 // pixel (tx0 + 8*(q&1) + lane%8, ty0 + 8*(q>>1) + lane/8 + 4*h). The eight pixels are independent, so the
 // fully unrolled body gives the scheduler eight interleaved dependency chains.
 __device__ __forceinline__ void raster_tile_tri(unsigned long long (&k)[8], const BigRec& r, int tx0, int ty0,
-                                                int W, int H, bool full, bool hierarchical)
+                                                int W, int H, bool full, bool hierarchical, bool ms, int offX, int offY)
 {
     const int lane = threadIdx.x & 31;
     Edges e;
@@ -520,13 +549,13 @@ __device__ __forceinline__ void raster_tile_tri(unsigned long long (&k)[8], cons
     if (!full && hierarchical) {
         bool rej, acc; float zl, zh;
         const int q = lane & 3;
-        classify_rect(r, tx0 + (q & 1) * BLOCK_PX, ty0 + (q >> 1) * BLOCK_PX, BLOCK_PX, W, H, false, rej, acc, zl, zh);
+        classify_rect(r, tx0 + (q & 1) * BLOCK_PX, ty0 + (q >> 1) * BLOCK_PX, BLOCK_PX, W, H, false, ms, rej, acc, zl, zh);
         rejMask = __ballot_sync(0xFFFFFFFFu, rej) & 0xFu;
         accMask = __ballot_sync(0xFFFFFFFFu, acc) & 0xFu;
     }
     // biased edge values at this lane's pixel of block 0 / half 0; other slots are integer steps away
     const int bx = tx0 + (lane & 7), by = ty0 + (lane >> 3);
-    const int cx = (bx << 4) + 8, cy = (by << 4) + 8;
+    const int cx = (bx << 4) + 8 + offX, cy = (by << 4) + 8 + offY;     // sample position (offset 0 at 1x)
     const uint32_t e0b = (uint32_t)e.e0(cx, cy), e1b = (uint32_t)e.e1(cx, cy), e2b = (uint32_t)e.e2(cx, cy);
     const uint32_t lowBias1 = (uint32_t)e.bias1, lowBias2 = (uint32_t)e.bias2;
     #pragma unroll
@@ -683,8 +712,9 @@ __device__ __forceinline__ uint32_t tile_key_max(const unsigned long long (&k)[8
 // triangle for the tile-level test (exact reject / full cover / hierarchical Z), then the whole warp per
 // surviving triangle. The Z bound tightens as the tile fills: it is the smaller of (a) the far side of
 // any triangle covering the whole tile and (b) the largest depth currently stored in the tile.
-__device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShared& S, int ox, int oy, bool hiz)
+__device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShared& S, int ox, int oy, bool hiz, int offX, int offY)
 {
+    const bool ms = P.samples > 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
     const int n = (int)S.survCount;
@@ -701,7 +731,7 @@ __device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShare
         uint32_t zlo = 0, zhi = 0xFFFFFFFFu;
         if (j < n) {
             bool rej; float zl, zh;
-            classify_rect(S.surv[j], tx0, ty0, TILE_PX, P.width, P.height, hiz, rej, full, zl, zh);
+            classify_rect(S.surv[j], tx0, ty0, TILE_PX, P.width, P.height, hiz, ms, rej, full, zl, zh);
             keep = !rej;
             if (hiz) { zlo = order_f32(zl); if (keep && full && zh <= 1.0f) zhi = order_f32(zh); }
             if (!P.hierarchical) full = false;
@@ -717,7 +747,7 @@ __device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShare
         while (keepMask) {
             const int l = __ffs(keepMask) - 1;
             keepMask &= keepMask - 1;
-            raster_tile_tri(k, S.surv[b + l], tx0, ty0, P.width, P.height, (fullMask >> l) & 1u, P.hierarchical != 0);
+            raster_tile_tri(k, S.surv[b + l], tx0, ty0, P.width, P.height, (fullMask >> l) & 1u, P.hierarchical != 0, ms, offX, offY);
         }
     }
     #pragma unroll
@@ -756,7 +786,7 @@ __device__ __forceinline__ void frame_done(const FrameParams& P)
     __syncthreads();
     if (threadIdx.x != 0) return;
     __threadfence();
-    if (atomicAdd(&P.counters->done, 1u) != gridDim.x - 1u) return;
+    if (atomicAdd(&P.counters->done, 1u) != gridDim.x * gridDim.y - 1u) return;
     volatile Counters* d = P.counters;
     const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump;
     d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->done = 0;
@@ -772,10 +802,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int bin = blockIdx.x;
+    // MSAA: blockIdx.y is the sample; each (bin, sample) CTA works on that sample's key plane, evaluates
+    // coverage and depth at centre + offset, and leaves the keys in place for msaa_resolve_kernel.
+    const bool ms = P.samples > 1;
+    const int sId = (int)blockIdx.y;
+    const int offX = c_sampleOffsets[P.msLevel][2 * sId], offY = c_sampleOffsets[P.msLevel][2 * sId + 1];
     const uint32_t bx = (uint32_t)(bin % P.binsX), by = (uint32_t)(bin / P.binsX);
     const int ox = (int)bx << BIN_LOG2, oy = (int)by << BIN_LOG2;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
-    unsigned long long* gkeys = P.keys + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
+    unsigned long long* gkeys = P.keys + (size_t)sId * P.keyStride + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
+    if (ms && min(P.counters->nBig, P.bigCap) == 0) return;      // nothing on the tile path: the keys are already final
     // the tile's keys are wanted on every path: issue the loads before the (dependent) counter read
     unsigned long long k[8];
     #pragma unroll
@@ -803,7 +839,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         #pragma unroll
         for (int j = 0; j < 8; j++) {
             skeys[j * 32 + lane] = k[j];
-            if (k[j] != KEY_EMPTY) gkeys[j * 32 + lane] = KEY_EMPTY;
+            if (!ms && k[j] != KEY_EMPTY) gkeys[j * 32 + lane] = KEY_EMPTY;
         }
     }
     if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; }
@@ -841,7 +877,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                 BigRec r;
                 load_big(P.big + S.cand[j], r);
                 bool rej, full; float zl, zh;
-                classify_rect(r, ox, oy, BIN, P.width, P.height, true, rej, full, zl, zh);
+                classify_rect(r, ox, oy, BIN, P.width, P.height, true, ms, rej, full, zl, zh);
                 if (!rej && full && zh <= 1.0f) u = min(u, order_f32(zh));
             }
             #pragma unroll
@@ -853,7 +889,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         //    whenever the list fills up
         for (uint32_t base = 0; base < nCand; base += TILE_THREADS) {
             if (S.survCount > SURV_CAP - TILE_THREADS) {          // uniform: read after a barrier
-                raster_survivors(P, S, ox, oy, hiz);
+                raster_survivors(P, S, ox, oy, hiz, offX, offY);
                 __syncthreads();
                 if (hiz) {
                     // what is now stored in the bin bounds everything still to come
@@ -875,7 +911,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                 BigRec r;
                 load_big(P.big + S.cand[j], r);
                 bool rej, full; float zl, zh;
-                classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, rej, full, zl, zh);
+                classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, ms, rej, full, zl, zh);
                 if (!rej && (!hiz || order_f32(zl) <= S.binU)) {
                     const uint32_t at = atomicAdd(&S.survCount, 1u);
                     int4* d2 = reinterpret_cast<int4*>(&S.surv[at]);
@@ -888,9 +924,16 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         if (tid == 0) S.candCount = 0;
         __syncthreads();
     }
-    raster_survivors(P, S, ox, oy, hizOn && S.survCount >= HIZ_MIN_CAND);
+    raster_survivors(P, S, ox, oy, hizOn && S.survCount >= HIZ_MIN_CAND, offX, offY);
     __syncwarp();
 
+    if (ms) {
+        // hand the sample's keys back; msaa_resolve_kernel shades, averages and ends the frame
+        const unsigned long long* tkeys = S.keys + warp * 256;
+        #pragma unroll
+        for (int j = 0; j < 8; j++) gkeys[j * 32 + lane] = tkeys[j * 32 + lane];
+        return;
+    }
     // resolve: every warp finishes its own tile; each pixel is written to HBM exactly once
     if (tx0 < P.width && ty0 < P.height) {
         const unsigned long long* tkeys = S.keys + warp * 256;
@@ -899,6 +942,51 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             const int q = j >> 1, h = j & 1;
             const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7), py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
             if (px < P.width && py < P.height) resolve_pixel(P, tkeys[q * 64 + lane + 32 * h], px, py);
+        }
+    }
+    frame_done(P);
+}
+
+// ---------------------------------------------------------------------------------------------
+// msaa_resolve_kernel: last kernel of a multi-sample frame (Renderer::UpdateFrameBuffer per sample,
+// Renderer.cpp:309-345, then FrameBuffer::Resolve, FrameBuffer.cpp:70-87). One thread per pixel walks the
+// pixel's S keys: the owner of each sample is shaded ONCE PER FRAGMENT at the pixel centre (the reference
+// shades a fragment once and writes that colour to every sample it covers, Rasterizer.h:273-288), samples
+// of the same triangle reuse the colour; the box filter sums Color(byte)/255 in sample order and rounds
+// with FromFloats. Keys are reset for the next frame; per-sample depth and owner ids are kept for parity.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) msaa_resolve_kernel(const __grid_constant__ FrameParams P)
+{
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;            // key index inside one sample plane
+    // invert key_index: [bin][tile 4x4][block 2x2][8x8]
+    const uint32_t bin = i >> 12, tile = (i >> 8) & 15u, block = (i >> 6) & 3u, in = i & 63u;
+    const int px = (int)((bin % (uint32_t)P.binsX) * BIN + (tile & 3u) * TILE_PX + (block & 1u) * BLOCK_PX + (in & 7u));
+    const int py = (int)((bin / (uint32_t)P.binsX) * BIN + (tile >> 2) * TILE_PX + (block >> 1) * BLOCK_PX + (in >> 3));
+    if (i < P.keyStride && px < P.width && py < P.height) {
+        const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);
+        const size_t plane = (size_t)P.width * P.height;
+        float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+        uint32_t lastPrim = 0xFFFFFFFFu;
+        uchar4 lastColor = make_uchar4(0, 0, 0, 0);
+        for (int sId = 0; sId < P.samples; sId++) {
+            unsigned long long* kp = P.keys + (size_t)sId * P.keyStride + i;
+            const unsigned long long key = *kp;
+            const bool hit = key != KEY_EMPTY;
+            if (hit) *kp = KEY_EMPTY;
+            P.depth[sId * plane + at] = hit ? key_depth(key) : 1.0f;
+            if (P.captureIds) P.ids[sId * plane + at] = hit ? key_prim(key) : 0xFFFFFFFFu;
+            if (hit && P.shader != SH_DEPTH_ONLY) {
+                const uint32_t prim = key_prim(key);
+                if (prim != lastPrim) { lastColor = shade_pixel(P, prim, px, py); lastPrim = prim; }
+                acc[0] = fadd(acc[0], fmul((float)lastColor.x, 1.0f / 255.0f));
+                acc[1] = fadd(acc[1], fmul((float)lastColor.y, 1.0f / 255.0f));
+                acc[2] = fadd(acc[2], fmul((float)lastColor.z, 1.0f / 255.0f));
+                acc[3] = fadd(acc[3], fmul((float)lastColor.w, 1.0f / 255.0f));
+            }
+        }
+        if (P.shader != SH_DEPTH_ONLY) {
+            const float inv = fdiv(1.0f, (float)P.samples);
+            P.color[at] = make_uchar4(to_u8(fmul(acc[0], inv)), to_u8(fmul(acc[1], inv)), to_u8(fmul(acc[2], inv)), to_u8(fmul(acc[3], inv)));
         }
     }
     frame_done(P);

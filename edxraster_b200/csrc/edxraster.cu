@@ -29,7 +29,7 @@ struct edx_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool ownStream = true;
-    uint32_t width = 0, height = 0, binsX = 0, binsY = 0;
+    uint32_t width = 0, height = 0, binsX = 0, binsY = 0, keyStride = 0;
     bool initialized = false;
 
     // Renderer::SetTransform state (RenderStates.h:15-19)
@@ -94,19 +94,22 @@ int allocate_frame_buffers(edx_context* c, uint32_t w, uint32_t h)
     c->width = w; c->height = h;
     c->binsX = (w + BIN - 1) / BIN;                    // cf. Renderer.cpp:26-27 (32-px tiles there)
     c->binsY = (h + BIN - 1) / BIN;
-    const size_t nKeys = (size_t)c->binsX * c->binsY * KEYS_PER_BIN;
+    // one key / depth / id plane per sample (FrameBuffer::Init, FrameBuffer.cpp:12-28); colour is the resolved buffer
+    const size_t S = (size_t)1 << c->msaaLog2;
+    c->keyStride = (uint32_t)((size_t)c->binsX * c->binsY * KEYS_PER_BIN);
+    const size_t nKeys = (size_t)c->keyStride * S;
     const size_t nPix = (size_t)w * h;
     EDX_CUDA(c, cudaMalloc(&c->keys, nKeys * sizeof(unsigned long long)));
     EDX_CUDA(c, cudaMalloc(&c->color, nPix * sizeof(uchar4)));
-    EDX_CUDA(c, cudaMalloc(&c->depth, nPix * sizeof(float)));
-    EDX_CUDA(c, cudaMalloc(&c->ids, nPix * sizeof(uint32_t)));
+    EDX_CUDA(c, cudaMalloc(&c->depth, nPix * S * sizeof(float)));
+    EDX_CUDA(c, cudaMalloc(&c->ids, nPix * S * sizeof(uint32_t)));
     c->hostColorBytes = nPix * 4;
     EDX_CUDA(c, cudaMallocHost(&c->hostColor, c->hostColorBytes));
     const size_t pairs = nKeys / 2;
     fill_keys_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, c->stream>>>(reinterpret_cast<ulonglong2*>(c->keys), pairs);
     EDX_CUDA(c, cudaGetLastError());
     EDX_CUDA(c, cudaMemsetAsync(c->color, 0, nPix * sizeof(uchar4), c->stream));     // FrameBuffer.cpp:91-95
-    EDX_CUDA(c, cudaMemsetAsync(c->ids, 0xFF, nPix * sizeof(uint32_t), c->stream));
+    EDX_CUDA(c, cudaMemsetAsync(c->ids, 0xFF, nPix * S * sizeof(uint32_t), c->stream));
     c->colorDirty = false;
     return EDX_OK;
 }
@@ -131,6 +134,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.width = (int)c->width; P.height = (int)c->height; P.binsX = (int)c->binsX; P.binsY = (int)c->binsY;
     P.shader = c->shader; P.smallMax = c->smallMax; P.smallMaxClip = c->smallMaxClip; P.hiz = c->hiz; P.hierarchical = c->hierarchical;
     P.captureIds = c->captureIds; P.dump = 0;
+    P.msLevel = c->msaaLog2; P.samples = 1 << c->msaaLog2; P.keyStride = c->keyStride;
     const float* Rm = c->raster.m;
     P.rasterAffineXY = (Rm[2] == 0.0f && Rm[6] == 0.0f && Rm[12] == 0.0f && Rm[13] == 0.0f && Rm[14] == 0.0f && Rm[15] == 1.0f) ? 1 : 0;
     P.pos4 = m->pos4; P.nrm4 = m->nrm4; P.i0 = m->i0; P.i1 = m->i1; P.i2 = m->i2;
@@ -176,8 +180,15 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
         c->launches++;
     }
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[2], c->stream));
-    tile_kernel<<<c->binsX * c->binsY, TILE_THREADS, sizeof(TileShared), c->stream>>>(P);
-    c->launches++;
+    if (c->msaaLog2 == 0) {
+        tile_kernel<<<c->binsX * c->binsY, TILE_THREADS, sizeof(TileShared), c->stream>>>(P);
+        c->launches++;
+    } else {
+        // one CTA per (bin, sample), then the per-pixel resolve that also ends the frame
+        tile_kernel<<<dim3(c->binsX * c->binsY, 1u << c->msaaLog2), TILE_THREADS, sizeof(TileShared), c->stream>>>(P);
+        msaa_resolve_kernel<<<(c->keyStride + 255) / 256, 256, 0, c->stream>>>(P);
+        c->launches += 2;
+    }
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[3], c->stream));
     EDX_CUDA(c, cudaGetLastError());
     return EDX_OK;
@@ -334,9 +345,18 @@ int edx_set_transform(edx_context* c, const float mv[16], const float proj[16], 
 int edx_set_msaa_mode(edx_context* c, int log2)
 {
     if (!c) return EDX_ERR_INVALID;
-    if (log2 != 0) return fail(c, EDX_ERR_UNSUPPORTED, "MSAA above 1x is not implemented in this round (SURVEY.md §8f rank 1)");
-    c->msaaLog2 = 0;
-    return EDX_OK;
+    if (log2 < 0 || log2 > 5) return fail(c, EDX_ERR_INVALID, "sample_count_log2 must be 0..5 (FrameBuffer.cpp:107-191 has tables up to 32x)");
+    if (log2 == c->msaaLog2) return EDX_OK;          // the viewer calls this every frame (Main.cpp:97)
+    if (c->extColor || c->extDepth) {
+        if (log2 != 0) return fail(c, EDX_ERR_UNSUPPORTED, "caller-owned render targets are single-sample only");
+    }
+    c->msaaLog2 = log2;
+    if (!c->initialized) return EDX_OK;
+    // Renderer::SetMSAAMode re-creates the frame buffer (Renderer.cpp:94-98 -> Resize)
+    if (int r = bind(c)) return r;
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->framePending = false;
+    return allocate_frame_buffers(c, c->width, c->height);
 }
 
 int edx_set_texture_filter(edx_context* c, int filter)
@@ -458,6 +478,20 @@ int edx_read_depth(edx_context* c, float* out)
     return EDX_OK;
 }
 
+int edx_read_sample(edx_context* c, int sample, float* depth, uint32_t* ids)
+{
+    if (!c || !c->initialized || sample < 0 || sample >= (1 << c->msaaLog2) || (!depth && !ids)) return fail(c, EDX_ERR_INVALID, "bad argument");
+    if (ids && !c->captureIds) return fail(c, EDX_ERR_INVALID, "edx_set_capture_ids(ctx, 1) must be set before the frame");
+    if (c->extDepth && depth) return fail(c, EDX_ERR_UNSUPPORTED, "per-sample read-back needs the context's own depth buffer");
+    if (int r = bind(c)) return r;
+    if (int r = finish_frame(c)) return r;
+    const size_t plane = (size_t)c->width * c->height;
+    if (depth) EDX_CUDA(c, cudaMemcpyAsync(depth, c->depth + (size_t)sample * plane, plane * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (ids) EDX_CUDA(c, cudaMemcpyAsync(ids, c->ids + (size_t)sample * plane, plane * 4, cudaMemcpyDeviceToHost, c->stream));
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EDX_OK;
+}
+
 int edx_set_capture_ids(edx_context* c, int enabled)
 {
     if (!c) return EDX_ERR_INVALID;
@@ -549,6 +583,7 @@ void* edx_device_depth(edx_context* c) { return c ? (c->extDepth ? c->extDepth :
 int edx_set_render_target(edx_context* c, void* color, void* depth)
 {
     if (!c) return EDX_ERR_INVALID;
+    if ((color || depth) && c->msaaLog2 != 0) return fail(c, EDX_ERR_UNSUPPORTED, "caller-owned render targets are single-sample only");
     c->extColor = (uchar4*)color;
     c->extDepth = (float*)depth;
     return EDX_OK;

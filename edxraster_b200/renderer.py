@@ -132,6 +132,13 @@ class Renderer:
         self._check(self._lib.edx_read_winner_ids(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32))))
         return out
 
+    def GetSample(self, sample):
+        """(depth, owner ids) of one MSAA sample plane."""
+        d = np.empty((self.height, self.width), np.float32)
+        i = np.empty((self.height, self.width), np.uint32)
+        self._check(self._lib.edx_read_sample(self._h, int(sample), _f32(d), i.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return d, i
+
     def DebugClipVertices(self, mesh):
         out = np.empty((mesh.num_verts, 4), np.float32)
         self._check(self._lib.edx_debug_clip_vertices(self._h, mesh._h, _f32(out)))

@@ -36,7 +36,7 @@ typedef enum edx_status {
     EDX_ERR_CUDA = -2,         /* CUDA runtime error, see edx_last_error */
     EDX_ERR_OOM = -3,          /* device or pinned-host allocation failed */
     EDX_ERR_OVERFLOW = -4,     /* an internal queue could not be grown */
-    EDX_ERR_UNSUPPORTED = -5,  /* feature outside the round's scope (e.g. MSAA > 1x) */
+    EDX_ERR_UNSUPPORTED = -5,  /* feature outside the round's scope (e.g. a resolution beyond the int32 edge range) */
     EDX_ERR_NO_DEVICE = -6     /* no CUDA device / wrong architecture */
 } edx_status;
 
@@ -74,7 +74,9 @@ int edx_resize(edx_context* ctx, uint32_t width, uint32_t height);
 /* Renderer::SetTransform (Core/Renderer.cpp:85-92). Derives MVP = proj * model_view and the
  * model-view inverse exactly as the reference does. */
 int edx_set_transform(edx_context* ctx, const float model_view[16], const float proj[16], const float to_raster[16]);
-/* Renderer::SetMSAAMode (Core/Renderer.cpp:94-98). Only 0 (1x) is implemented this round. */
+/* Renderer::SetMSAAMode (Core/Renderer.cpp:94-98): 2^log2 samples per pixel, log2 in 0..5 (sample tables
+ * of Core/FrameBuffer.cpp:107-191). Re-creates the frame buffer; a no-op when the level is unchanged.
+ * With MSAA the back buffer is the box-filtered resolve (FrameBuffer.cpp:70-87). */
 int edx_set_msaa_mode(edx_context* ctx, int sample_count_log2);
 /* Renderer::SetTextureFilter (Core/Renderer.h:48). Stored; no textured shader this round. */
 int edx_set_texture_filter(edx_context* ctx, int filter);
@@ -113,6 +115,9 @@ int edx_read_depth(edx_context* ctx, float* out_w_times_h);
  * Needs edx_set_capture_ids(ctx, 1) before the frame. */
 int edx_set_capture_ids(edx_context* ctx, int enabled);
 int edx_read_winner_ids(edx_context* ctx, uint32_t* out_w_times_h);
+/* per-sample read-back with MSAA: depth and/or owner ids of sample `sample` (either pointer may be NULL);
+ * edx_read_depth / edx_read_winner_ids return sample 0 */
+int edx_read_sample(edx_context* ctx, int sample, float* depth_w_times_h, uint32_t* ids_w_times_h);
 /* stage dumps: clip-space vertices (vertex_count x 4 floats) of stage a1, Core/Renderer.cpp:120-127 */
 int edx_debug_clip_vertices(edx_context* ctx, const edx_mesh* mesh, float* out_xyzw);
 /* post-setup triangles (stages a3-a6) sorted by prim id; ints: prim,v0x,v0y,v1x,v1y,v2x,v2y;

@@ -237,7 +237,7 @@ struct Fragment {            // Shader.h:105-114 (single-sample coverage only)
     uint32_t vId0, vId1, vId2, coreId;
     uint32_t primId;
     uint16_t x, y;
-    uint8_t mask;            // bit i = lane i of the 2x2 quad
+    uint32_t mask[4];        // CoverageMask (Shader.h:52-103): bit (4*sample + lane) of a 128-bit mask
 };
 
 struct Tile {                // Tile.h:10-41
@@ -256,13 +256,15 @@ static const int TILE = 32, TILE_LOG2 = 5;
 struct Oracle {
     int W = 0, H = 0, tilesX = 0, tilesY = 0, cores = 1;
     int shader = 1;                 // 0 depth-only, 1 Blinn-Phong, 2 Lambertian, 3 Lambertian * constant albedo
+    int msLevel = 0, samples = 1;   // FrameBuffer.cpp:14-15
     bool hierarchical = true;
     float albedo[3] = { 0.9f, 0.9f, 0.9f };
     Mat4 MV, MVinv, P, MVP, R;
     std::vector<Tile> tiles;
     std::vector<__m128> depth;      // per tile 16x16 quads, FrameBuffer.cpp:25-27
-    std::vector<uint8_t> color;     // W*H*4, bottom-up (FrameBuffer.cpp:41)
-    std::vector<uint32_t> winner;   // ours: prim id of the last colour writer, bottom-up
+    std::vector<uint8_t> color;     // mColorBufferMS: [S][W][H] Color4b, sample fastest, rows bottom-up (FrameBuffer.cpp:19,41)
+    std::vector<uint8_t> resolved;  // mColorBuffer: W*H*4 after Resolve (FrameBuffer.cpp:70-87); == color when S == 1
+    std::vector<uint32_t> winner;   // ours: prim id of the last colour writer per sample, same layout as color
     std::vector<ProjVertex> projected;
     std::vector<std::vector<ProjVertex>> coreVerts;
     std::vector<std::vector<RasterTri>> coreTris;
@@ -509,26 +511,45 @@ struct TriSSE {
 };
 
 // FrameBuffer.cpp:54-68. LESS_EQUAL, masked write; returns the UNMASKED compare.
-static inline __m128 ztest_quad(Oracle& o, __m128 d, int x, int y, __m128 mask)
+static inline __m128 ztest_quad(Oracle& o, __m128 d, int x, int y, int sId, __m128 mask)
 {
     int tx = x >> TILE_LOG2, ty = y >> TILE_LOG2;
     int ix = x & (TILE - 1), iy = y & (TILE - 1);
-    __m128& cur = o.depth[(size_t)(ty * o.tilesX + tx) * 256 + (size_t)(iy >> 1) * 16 + (ix >> 1)];
+    __m128& cur = o.depth[((size_t)(ty * o.tilesX + tx) * o.samples + sId) * 256 + (size_t)(iy >> 1) * 16 + (ix >> 1)];
     __m128 ret = _mm_cmple_ps(d, cur);
     cur = _mm_blendv_ps(cur, d, _mm_and_ps(ret, mask));
     return ret;
 }
 
+// FrameBuffer.cpp:107-191. Offsets in 1/16 pixel relative to the pixel centre, (x, y) pairs.
+// shim 17: the reference binds `const Vector2i&` to element [2*sampleId] of this int table
+// (Rasterizer.h:247,382); we read that as the pair (table[2s], table[2s+1]) the table is written as.
+static const int kSampleOffsets[6][64] = {
+    { 0, 0 },
+    { 4, 4, -4, -4 },
+    { -2, -6, 6, -2, -6, 2, 2, 6 },
+    { 1, -3, -1, 3, 5, 1, -3, -5, -5, 5, -7, -1, 3, 7, 7, -7 },
+    { 1, 1, -1, -3, -3, 2, 4, -1, -5, -2, 2, 5, 5, 3, 3, -5, -2, 6, 0, -7, -4, -6, -6, 4, -8, 0, 7, -4, 6, 7, -7, -8 },
+    { 1, 1, -1, -3, -3, 2, 4, -1, -5, -2, 2, 5, 5, 3, 3, -5, -2, 6, 0, -7, -4, -6, -6, 4, -8, 0, 7, -4, 6, 7, -7, -8,
+      1, 3, -3, -3, -3, 0, 6, -2, -7, -1, 3, 4, 7, 3, 3, -6, -2, 7, 0, -4, -2, -5, -7, 6, -8, 3, 4, -1, 2, 7, 4, -8 },
+};
+
 static inline int min3(int a, int b, int c) { return std::min(a, std::min(b, c)); }
 static inline int max3(int a, int b, int c) { return std::max(a, std::max(b, c)); }
 
-static inline void emit(Tile& tile, const TriSSE& s, const RasterTri& t, int x, int y, int mask)
+static inline void emit(Tile& tile, const TriSSE& s, const RasterTri& t, int x, int y, const uint32_t mask[4])
 {
     Fragment f;
     f.l0 = s.l0; f.l1 = s.l1;
     f.vId0 = t.vId0; f.vId1 = t.vId1; f.vId2 = t.vId2; f.coreId = t.coreId; f.primId = t.primId;
-    f.x = (uint16_t)x; f.y = (uint16_t)y; f.mask = (uint8_t)mask;
+    f.x = (uint16_t)x; f.y = (uint16_t)y;
+    f.mask[0] = mask[0]; f.mask[1] = mask[1]; f.mask[2] = mask[2]; f.mask[3] = mask[3];
     tile.frags.push_back(f);
+}
+static inline void mask_set(uint32_t mask[4], int lanes4, int sampleId)      // CoverageMask::SetBit, Shader.h:73-92
+{
+    int bit = sampleId << 2;
+    mask[bit >> 5] |= (uint32_t)lanes4 << (bit & 31);
 }
 
 // Rasterizer.h:126-200
@@ -561,9 +582,9 @@ static void fine_rasterize(Oracle& o, Tile& tile, V2i bmin, V2i bmax, const Rast
                 s.bary(cx, cy);
                 __m128 covMask = _mm_castsi128_ps(_mm_cmpgt_epi32(_mm_set1_epi32(0), _mm_or_si128(_mm_or_si128(e0, e1), e2)));
                 covMask = _mm_xor_ps(covMask, _mm_castsi128_ps(_mm_set1_epi32(-1)));
-                __m128 zt = ztest_quad(o, s.depth(z0, z1, z2), x, y, covMask);
+                __m128 zt = ztest_quad(o, s.depth(z0, z1, z2), x, y, 0, covMask);
                 int vis = _mm_movemask_ps(zt) & cov;
-                if (vis) emit(tile, s, t, x, y, vis);
+                if (vis) { uint32_t m[4] = { (uint32_t)vis, 0, 0, 0 }; emit(tile, s, t, x, y, m); }
             }
             e0 = _mm_add_epi32(e0, s.sB0); e1 = _mm_add_epi32(e1, s.sB1); e2 = _mm_add_epi32(e2, s.sB2);
             cx = _mm_add_epi32(cx, step32);
@@ -590,10 +611,108 @@ static void trivial_accept(Oracle& o, Tile& tile, V2i bmin, V2i bmax, const Rast
             __m128i cx = _mm_add_epi32(_mm_set1_epi32(x << 4), offX);
             s.bary(cx, cy);
             covered += 4;
-            int vis = _mm_movemask_ps(ztest_quad(o, s.depth(z0, z1, z2), x, y, all));
-            if (vis) emit(tile, s, t, x, y, vis);
+            int vis = _mm_movemask_ps(ztest_quad(o, s.depth(z0, z1, z2), x, y, 0, all));
+            if (vis) { uint32_t m[4] = { (uint32_t)vis, 0, 0, 0 }; emit(tile, s, t, x, y, m); }
         }
     }
+}
+
+// Rasterizer.h:202-300
+static void fine_rasterize_ms(Oracle& o, Tile& tile, V2i bmin, V2i bmax, const RasterTri& t, uint64_t& covered)
+{
+    int minX = std::max(bmin.x, min3(t.v0.x, t.v1.x, t.v2.x) >> 4);
+    int maxX = std::min(bmax.x - 1, max3(t.v0.x, t.v1.x, t.v2.x) >> 4);
+    int minY = std::max(bmin.y, min3(t.v0.y, t.v1.y, t.v2.y) >> 4);
+    int maxY = std::min(bmax.y - 1, max3(t.v0.y, t.v1.y, t.v2.y) >> 4);
+    minX -= minX % 2;
+    minY -= minY % 2;
+    if (maxX < minX || maxY < minY) return;
+    TriSSE s(t);
+    const ProjVertex* vb = o.coreVerts[t.coreId].data();
+    const float z0 = vb[t.vId0].proj.z, z1 = vb[t.vId1].proj.z, z2 = vb[t.vId2].proj.z;
+    const __m128i offX = _mm_setr_epi32(8, 24, 8, 24), offY = _mm_setr_epi32(8, 8, 24, 24);
+    const int* table = kSampleOffsets[o.msLevel];
+    __m128i cy = _mm_add_epi32(_mm_set1_epi32(minY << 4), offY);
+    __m128i cx0 = _mm_add_epi32(_mm_set1_epi32(minX << 4), offX);
+    __m128i e0 = s.e0(cx0, cy), e1 = s.e1(cx0, cy), e2 = s.e2(cx0, cy);
+    const __m128i step32 = _mm_set1_epi32(32);
+    for (int y = minY; y <= maxY; y += 2) {
+        __m128i r0 = e0, r1 = e1, r2 = e2;
+        __m128i cx = cx0;
+        for (int x = minX; x <= maxX; x += 2) {
+            uint32_t mask[4] = { 0, 0, 0, 0 };
+            bool gen = false;
+            for (int sId = 0; sId < o.samples; sId++) {
+                const int ox = table[2 * sId], oy = table[2 * sId + 1];
+                const __m128i vx = _mm_set1_epi32(ox), vy = _mm_set1_epi32(oy);
+                // e = edgeVal + off.x * B + off.y * C   (Rasterizer.h:248-250)
+                __m128i f0 = _mm_add_epi32(_mm_add_epi32(e0, _mm_mullo_epi32(vx, s.B0)), _mm_mullo_epi32(vy, s.C0));
+                __m128i f1 = _mm_add_epi32(_mm_add_epi32(e1, _mm_mullo_epi32(vx, s.B1)), _mm_mullo_epi32(vy, s.C1));
+                __m128i f2 = _mm_add_epi32(_mm_add_epi32(e2, _mm_mullo_epi32(vx, s.B2)), _mm_mullo_epi32(vy, s.C2));
+                __m128i orv = _mm_or_si128(_mm_or_si128(f0, f1), f2);
+                int cov = (~_mm_movemask_ps(_mm_castsi128_ps(orv))) & 15;
+                if (cov) {
+                    covered += (uint64_t)__builtin_popcount(cov);
+                    s.bary(_mm_add_epi32(cx, vx), _mm_add_epi32(cy, vy));
+                    __m128 covMask = _mm_xor_ps(_mm_castsi128_ps(_mm_cmpgt_epi32(_mm_set1_epi32(0), orv)), _mm_castsi128_ps(_mm_set1_epi32(-1)));
+                    int vis = _mm_movemask_ps(ztest_quad(o, s.depth(z0, z1, z2), x, y, sId, covMask)) & cov;
+                    if (vis) { mask_set(mask, vis, sId); gen = true; }
+                }
+            }
+            if (gen) {
+                s.bary(cx, cy);                  // shading barycentrics at the pixel centres (Rasterizer.h:275)
+                emit(tile, s, t, x, y, mask);
+            }
+            e0 = _mm_add_epi32(e0, s.sB0); e1 = _mm_add_epi32(e1, s.sB1); e2 = _mm_add_epi32(e2, s.sB2);
+            cx = _mm_add_epi32(cx, step32);
+        }
+        e0 = _mm_add_epi32(r0, s.sC0); e1 = _mm_add_epi32(r1, s.sC1); e2 = _mm_add_epi32(r2, s.sC2);
+        cy = _mm_add_epi32(cy, step32);
+    }
+}
+
+// Rasterizer.h:355-415
+static void trivial_accept_ms(Oracle& o, Tile& tile, V2i bmin, V2i bmax, const RasterTri& t, uint64_t& covered)
+{
+    int minX = bmin.x, maxX = bmax.x - 1, minY = bmin.y, maxY = bmax.y - 1;
+    minX -= minX % 2;
+    minY -= minY % 2;
+    TriSSE s(t);
+    const ProjVertex* vb = o.coreVerts[t.coreId].data();
+    const float z0 = vb[t.vId0].proj.z, z1 = vb[t.vId1].proj.z, z2 = vb[t.vId2].proj.z;
+    const __m128i offX = _mm_setr_epi32(8, 24, 8, 24), offY = _mm_setr_epi32(8, 8, 24, 24);
+    const __m128 all = _mm_castsi128_ps(_mm_set1_epi32(-1));
+    const int* table = kSampleOffsets[o.msLevel];
+    for (int y = minY; y <= maxY; y += 2) {
+        __m128i cy = _mm_add_epi32(_mm_set1_epi32(y << 4), offY);
+        for (int x = minX; x <= maxX; x += 2) {
+            __m128i cx = _mm_add_epi32(_mm_set1_epi32(x << 4), offX);
+            uint32_t mask[4] = { 0, 0, 0, 0 };
+            bool gen = false;
+            for (int sId = 0; sId < o.samples; sId++) {
+                s.bary(_mm_add_epi32(cx, _mm_set1_epi32(table[2 * sId])), _mm_add_epi32(cy, _mm_set1_epi32(table[2 * sId + 1])));
+                covered += 4;
+                int vis = _mm_movemask_ps(ztest_quad(o, s.depth(z0, z1, z2), x, y, sId, all));
+                if (vis) { mask_set(mask, vis, sId); gen = true; }
+            }
+            if (gen) {
+                s.bary(cx, cy);
+                emit(tile, s, t, x, y, mask);
+            }
+        }
+    }
+}
+
+// Rasterizer.h:113-124, 302-308: single- vs multi-sample dispatch
+static inline void fine_dispatch(Oracle& o, Tile& tile, V2i bmin, V2i bmax, const RasterTri& t, uint64_t& covered)
+{
+    if (o.samples == 1) fine_rasterize(o, tile, bmin, bmax, t, covered);
+    else fine_rasterize_ms(o, tile, bmin, bmax, t, covered);
+}
+static inline void accept_dispatch(Oracle& o, Tile& tile, V2i bmin, V2i bmax, const RasterTri& t, uint64_t& covered)
+{
+    if (o.samples == 1) trivial_accept(o, tile, bmin, bmax, t, covered);
+    else trivial_accept_ms(o, tile, bmin, bmax, t, covered);
 }
 
 // Rasterizer.h:32-111 with RasterTriangle.h:192-255 (step vectors)
@@ -633,8 +752,8 @@ static void coarse_rasterize(Oracle& o, Tile& tile, const TriRef& ref, const Ras
         // benchmark configs reaches this case.
         qmax.x = std::min(qmax.x, bmax.x);
         qmax.y = std::min(qmax.y, bmax.y);
-        if (acc0[q] >= 0 && acc1[q] >= 0 && acc2[q] >= 0) trivial_accept(o, tile, qmin, qmax, t, covered);
-        else fine_rasterize(o, tile, qmin, qmax, t, covered);
+        if (acc0[q] >= 0 && acc1[q] >= 0 && acc2[q] >= 0) accept_dispatch(o, tile, qmin, qmax, t, covered);
+        else fine_dispatch(o, tile, qmin, qmax, t, covered);
     }
 }
 
@@ -694,9 +813,9 @@ static void tiled_rasterization(Oracle& o, double& msBin, double& msRaster)
         for (int core = 0; core < o.cores; core++) {                        // Renderer.cpp:248-270
             for (const TriRef& ref : tile.refs[core]) {
                 const RasterTri& t = o.coreTris[core][ref.triId];
-                if (ref.trivialAccept) { trivial_accept(o, tile, tile.minC, tile.maxC, t, covered); continue; }
+                if (ref.trivialAccept) { accept_dispatch(o, tile, tile.minC, tile.maxC, t, covered); continue; }
                 if (o.hierarchical && ref.big) coarse_rasterize(o, tile, ref, t, covered);
-                else fine_rasterize(o, tile, tile.minC, tile.maxC, t, covered);
+                else fine_dispatch(o, tile, tile.minC, tile.maxC, t, covered);
             }
         }
     }
@@ -797,20 +916,37 @@ static void fragment_processing(Oracle& o)
 static void update_frame_buffer(Oracle& o)
 {
     const int nTiles = (int)o.tiles.size();
+    const int S = o.samples;
     #pragma omp parallel for schedule(dynamic, 4) num_threads(o.cores)
     for (int i = 0; i < nTiles; i++) {
         const Tile& tile = o.tiles[i];
         for (size_t j = 0; j < tile.frags.size(); j++) {                    // Renderer.cpp:309-345
             const Fragment& f = tile.frags[j];
-            for (int k = 0; k < 4; k++) {
-                if (!(f.mask & (1 << k))) continue;
-                int x = f.x + (k & 1), y = f.y + (k >> 1);
-                if (x >= o.W || y >= o.H) continue;                          // odd sizes only; see DESIGN.md
-                size_t at = (size_t)x + (size_t)o.W * (size_t)(o.H - 1 - y);   // FrameBuffer.cpp:41
-                if (o.shader != 0) memcpy(&o.color[at * 4], &o.shaded[i][j * 4 + k], 4);
-                o.winner[at] = f.primId;
+            for (int sId = 0; sId < S; sId++) {
+                const int shift = sId << 2;
+                const uint32_t lanes = (f.mask[shift >> 5] >> (shift & 31)) & 15u;
+                for (int k = 0; k < 4; k++) {
+                    if (!(lanes & (1u << k))) continue;
+                    int x = f.x + (k & 1), y = f.y + (k >> 1);
+                    if (x >= o.W || y >= o.H) continue;                      // odd sizes only; see DESIGN.md
+                    size_t at = ((size_t)x + (size_t)o.W * (size_t)(o.H - 1 - y)) * S + sId;   // FrameBuffer.cpp:41
+                    if (o.shader != 0) memcpy(&o.color[at * 4], &o.shaded[i][j * 4 + k], 4);
+                    o.winner[at] = f.primId;
+                }
             }
         }
+    }
+    // FrameBuffer::Resolve, FrameBuffer.cpp:70-87. shim 18: Color(Color4b) = bytes / 255, Color4b(Color) = the
+    // FromFloats rounding of shim 13 on every channel (alpha included).
+    if (S == 1) { o.resolved = o.color; return; }
+    const float inv = 1.0f / (float)S;
+    const int64_t nPix = (int64_t)o.W * o.H;
+    #pragma omp parallel for schedule(static) num_threads(o.cores)
+    for (int64_t p = 0; p < nPix; p++) {
+        float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+        for (int sId = 0; sId < S; sId++)
+            for (int c = 0; c < 4; c++) acc[c] = acc[c] + (float)o.color[((size_t)p * S + sId) * 4 + c] * (1.0f / 255.0f);
+        for (int c = 0; c < 4; c++) o.resolved[(size_t)p * 4 + c] = to_u8(acc[c] * inv);
     }
 }
 
@@ -859,9 +995,10 @@ static void resize(Oracle& o, int w, int h)
             t.refs.resize(o.cores);
             o.tiles.push_back(std::move(t));
         }
-    o.depth.assign((size_t)o.tilesX * o.tilesY * 256, _mm_set1_ps(1.0f));
-    o.color.assign((size_t)w * h * 4, 0);
-    o.winner.assign((size_t)w * h, 0xFFFFFFFFu);
+    o.depth.assign((size_t)o.tilesX * o.tilesY * 256 * o.samples, _mm_set1_ps(1.0f));
+    o.color.assign((size_t)w * h * 4 * o.samples, 0);
+    o.resolved.assign((size_t)w * h * 4, 0);
+    o.winner.assign((size_t)w * h * o.samples, 0xFFFFFFFFu);
     o.shaded.assign(o.tiles.size(), {});
     o.coreVerts.assign(o.cores, {});
     o.coreTris.assign(o.cores, {});
@@ -917,19 +1054,36 @@ void orc_render(void* h, const float* vtx, uint32_t nv, const uint32_t* idx, uin
     render(*(Oracle*)h, vtx, nv, idx, nt);
 }
 
-const uint8_t* orc_color(void* h) { return ((Oracle*)h)->color.data(); }      // Renderer.cpp:360-363
-void orc_get_winner(void* h, uint32_t* out) { Oracle& o = *(Oracle*)h; memcpy(out, o.winner.data(), o.winner.size() * 4); }
-// depth linearised bottom-up like the colour buffer
-void orc_get_depth(void* h, float* out)
+// Renderer::SetMSAAMode, Renderer.cpp:94-98 (re-creates the frame buffer)
+void orc_set_msaa(void* h, int log2)
+{
+    Oracle& o = *(Oracle*)h;
+    o.msLevel = log2; o.samples = 1 << log2;
+    resize(o, o.W, o.H);
+}
+int orc_samples(void* h) { return ((Oracle*)h)->samples; }
+// Renderer::GetBackBuffer, Renderer.cpp:360-363 / FrameBuffer.h:55-58: the resolved buffer (== sample buffer at 1x)
+const uint8_t* orc_color(void* h) { return ((Oracle*)h)->resolved.data(); }
+// per-sample owner ids: sample sId of every pixel, bottom-up
+void orc_get_winner_sample(void* h, int sId, uint32_t* out)
+{
+    Oracle& o = *(Oracle*)h;
+    const size_t n = (size_t)o.W * o.H;
+    for (size_t p = 0; p < n; p++) out[p] = o.winner[p * o.samples + sId];
+}
+void orc_get_winner(void* h, uint32_t* out) { orc_get_winner_sample(h, 0, out); }
+// depth of one sample, linearised bottom-up like the colour buffer
+void orc_get_depth_sample(void* h, int sId, float* out)
 {
     Oracle& o = *(Oracle*)h;
     for (int y = 0; y < o.H; y++)
         for (int x = 0; x < o.W; x++) {
             int tx = x >> TILE_LOG2, ty = y >> TILE_LOG2, ix = x & (TILE - 1), iy = y & (TILE - 1);
-            const float* q = (const float*)&o.depth[(size_t)(ty * o.tilesX + tx) * 256 + (size_t)(iy >> 1) * 16 + (ix >> 1)];
+            const float* q = (const float*)&o.depth[((size_t)(ty * o.tilesX + tx) * o.samples + sId) * 256 + (size_t)(iy >> 1) * 16 + (ix >> 1)];
             out[(size_t)x + (size_t)o.W * (size_t)(o.H - 1 - y)] = q[(ix & 1) + 2 * (iy & 1)];
         }
 }
+void orc_get_depth(void* h, float* out) { orc_get_depth_sample(h, 0, out); }
 void orc_get_clip_verts(void* h, float* out)
 {
     Oracle& o = *(Oracle*)h;

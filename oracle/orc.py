@@ -44,6 +44,10 @@ def _load(timing):
     lib.orc_set_shader.argtypes = [vp, C.c_int]
     lib.orc_set_albedo.argtypes = [vp, C.c_float, C.c_float, C.c_float]
     lib.orc_set_hierarchical.argtypes = [vp, C.c_int]
+    lib.orc_set_msaa.argtypes = [vp, C.c_int]
+    lib.orc_samples.argtypes = [vp]
+    lib.orc_get_winner_sample.argtypes = [vp, C.c_int, u32p]
+    lib.orc_get_depth_sample.argtypes = [vp, C.c_int, f32p]
     lib.orc_render.argtypes = [vp, f32p, C.c_uint32, u32p, C.c_uint32]
     lib.orc_color.restype = C.POINTER(C.c_uint8)
     lib.orc_color.argtypes = [vp]
@@ -117,6 +121,14 @@ class Oracle:
     def set_albedo(self, r, g, b):
         self.lib.orc_set_albedo(self.h_, r, g, b)
 
+    def set_msaa(self, log2):
+        """Renderer::SetMSAAMode (Core/Renderer.cpp:94-98): 2^log2 samples per pixel."""
+        self.lib.orc_set_msaa(self.h_, int(log2))
+
+    @property
+    def samples(self):
+        return self.lib.orc_samples(self.h_)
+
     def set_hierarchical(self, on):
         self.lib.orc_set_hierarchical(self.h_, 1 if on else 0)
 
@@ -131,14 +143,14 @@ class Oracle:
         buf = self.lib.orc_color(self.h_)
         return np.ctypeslib.as_array(buf, shape=(self.h, self.w, 4)).copy()
 
-    def depth(self):
+    def depth(self, sample=0):
         out = np.zeros((self.h, self.w), np.float32)
-        self.lib.orc_get_depth(self.h_, _f32(out))
+        self.lib.orc_get_depth_sample(self.h_, int(sample), _f32(out))
         return out
 
-    def winner(self):
+    def winner(self, sample=0):
         out = np.zeros((self.h, self.w), np.uint32)
-        self.lib.orc_get_winner(self.h_, _u32(out))
+        self.lib.orc_get_winner_sample(self.h_, int(sample), _u32(out))
         return out
 
     def clip_verts(self):

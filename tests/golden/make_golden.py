@@ -32,6 +32,12 @@ def cases():
     }
 
 
+def msaa_cases():
+    """name -> (scene, SetMSAAMode level)"""
+    c = cases()
+    return {"C1_small_4x": (c["C1_small"], 2), "C4_small_8x": (c["C4_small"], 3)}
+
+
 def digest(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
@@ -53,10 +59,18 @@ def main():
             frames["C1_small_depth"] = ref["depth"]
             frames["C1_small_winner"] = ref["winner"]
             frames["C1_small_color"] = ref["color"]
+    for name, (sc, level) in msaa_cases().items():
+        ref = parity.render_oracle(sc, threads=2, msaa=level)
+        out[name] = {
+            "width": sc.width, "height": sc.height, "triangles": sc.num_tris, "shader": int(sc.shader), "msaa_level": level,
+            "color_sha256": digest(ref["color"]),
+            "sample_depth_sha256": digest(np.stack([d for d, _ in ref["samples"]])),
+            "sample_winner_sha256": digest(np.stack([w for _, w in ref["samples"]])),
+        }
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, "golden_frames.npz"), **frames)
-    print(json.dumps({k: v["covered_pixels"] for k, v in out.items()}))
+    print(json.dumps({k: v.get("covered_pixels") for k, v in out.items()}))
 
 
 if __name__ == "__main__":

@@ -5,21 +5,26 @@ from edxraster_b200 import renderer as R
 from oracle import orc
 
 
-def render_oracle(scene, threads=0, shader=None, hierarchical=True):
+def render_oracle(scene, threads=0, shader=None, hierarchical=True, msaa=0):
     o = orc.Oracle(scene.width, scene.height, threads)
+    if msaa:
+        o.set_msaa(msaa)
     o.set_transform(scene.mv, scene.proj, scene.raster)
     o.set_shader(scene.shader if shader is None else shader)
     o.set_hierarchical(hierarchical)
     o.render(scene.vertices, scene.indices)
     out = {"color": o.color(), "depth": o.depth(), "winner": o.winner(), "clip": o.clip_verts(),
            "tris": o.raster_tris(), "stats": o.stats(), "derived": o.derived()}
+    if msaa:
+        out["samples"] = [(o.depth(k), o.winner(k)) for k in range(1 << msaa)]
     o.close()
     return out
 
 
-def render_gpu(scene, shader=None, options=None, hierarchical=True, stages=True, renderer=None):
+def render_gpu(scene, shader=None, options=None, hierarchical=True, stages=True, renderer=None, msaa=0):
     r = renderer or R.Renderer(0)
     r.Initialize(scene.width, scene.height)
+    r.SetMSAAMode(msaa)
     r.SetTransform(scene.mv, scene.proj, scene.raster)
     r.SetPixelShader(scene.shader if shader is None else shader)
     r.SetHierarchicalRasterize(hierarchical)
@@ -30,6 +35,8 @@ def render_gpu(scene, shader=None, options=None, hierarchical=True, stages=True,
     r.RenderMesh(m)
     out = {"color": r.GetBackBuffer().copy(), "depth": r.GetDepthBuffer(), "winner": r.GetWinnerIds(),
            "stats": r.GetStats(), "derived": r.DerivedState()}
+    if msaa:
+        out["samples"] = [r.GetSample(k) for k in range(1 << msaa)]
     if stages:
         out["clip"] = r.DebugClipVertices(m)
         out["tris"] = r.DebugRasterTriangles(m)
@@ -48,6 +55,9 @@ def compare(ref, got, color_tol=1):
     rep["color_gt_tol"] = int((dc > color_tol).any(axis=-1).sum())
     rep["color_max_diff"] = int(dc.max()) if dc.size else 0
     rep["color_exact_frac"] = float((dc == 0).all(axis=-1).mean()) if dc.size else 1.0
+    if "samples" in ref and "samples" in got:
+        rep["sample_depth_bits"] = sum(int((a[0].view(np.uint32) != b[0].view(np.uint32)).sum()) for a, b in zip(ref["samples"], got["samples"]))
+        rep["sample_winner"] = sum(int((a[1] != b[1]).sum()) for a, b in zip(ref["samples"], got["samples"]))
     if "clip" in got:
         rep["clip_bits"] = int((ref["clip"].view(np.uint32) != got["clip"].view(np.uint32)).sum())
         ri, rf = ref["tris"]
@@ -67,6 +77,7 @@ def compare(ref, got, color_tol=1):
 
 def is_parity(rep):
     ok = rep["depth_bits"] == 0 and rep["winner"] == 0 and rep["color_gt_tol"] == 0 and rep["derived_bits"] == 0
+    ok = ok and rep.get("sample_depth_bits", 0) == 0 and rep.get("sample_winner", 0) == 0
     if "clip_bits" in rep:
         ok = ok and rep["clip_bits"] == 0 and rep["tri_int_mismatch"] == 0 and rep["tri_float_mismatch"] == 0
     return ok

@@ -14,7 +14,10 @@ import make_golden  # noqa: E402
 import parity  # noqa: E402
 
 with open(os.path.join(HERE, "golden", "golden.json")) as f:
-    GOLDEN = json.load(f)
+    ALL_GOLDEN = json.load(f)
+GOLDEN = {k: v for k, v in ALL_GOLDEN.items() if "msaa_level" not in v}
+GOLDEN_MS = {k: v for k, v in ALL_GOLDEN.items() if "msaa_level" in v}
+MS_CASES = make_golden.msaa_cases()
 FRAMES = np.load(os.path.join(HERE, "golden", "golden_frames.npz"))
 CASES = make_golden.cases()
 
@@ -42,6 +45,27 @@ def test_oracle_reproduces_golden(name, threads):
     out = parity.render_oracle(CASES[name], threads=threads)
     check(name, out, color_exact=True)
     assert out["stats"]["covered_samples"] == GOLDEN[name]["covered_samples"]
+
+
+def check_ms(name, out, color_exact):
+    g = GOLDEN_MS[name]
+    assert digest(np.stack([d for d, _ in out["samples"]])) == g["sample_depth_sha256"]
+    assert digest(np.stack([w for _, w in out["samples"]])) == g["sample_winner_sha256"]
+    if color_exact:
+        assert digest(out["color"]) == g["color_sha256"]
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_MS))
+def test_oracle_reproduces_msaa_golden(name):
+    sc, level = MS_CASES[name]
+    check_ms(name, parity.render_oracle(sc, threads=3, msaa=level), color_exact=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(GOLDEN_MS))
+def test_cuda_matches_msaa_golden(name):
+    sc, level = MS_CASES[name]
+    check_ms(name, parity.render_gpu(sc, msaa=level, stages=False), color_exact=False)
 
 
 @pytest.mark.gpu

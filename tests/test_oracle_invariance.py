@@ -26,6 +26,18 @@ def test_thread_count_and_hierarchy_do_not_change_the_frame(name):
         assert base["tris"][0].tolist() == other["tris"][0].tolist()
 
 
+@pytest.mark.parametrize("name", ["C1", "C3", "C4"])
+def test_msaa_frames_do_not_depend_on_threads_or_hierarchy(name):
+    sc = SCENES[name]()
+    base = parity.render_oracle(sc, threads=1, hierarchical=True, msaa=2)
+    for threads, hier in ((4, True), (3, False)):
+        other = parity.render_oracle(sc, threads=threads, hierarchical=hier, msaa=2)
+        np.testing.assert_array_equal(base["color"], other["color"])
+        for (d0, w0), (d1, w1) in zip(base["samples"], other["samples"]):
+            np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+            np.testing.assert_array_equal(w0, w1)
+
+
 def test_closed_form_of_the_depth_test():
     """Per pixel: final depth = min over covering fragments, owner = LAST fragment at that depth
     (SURVEY.md §3.3). Checked by brute force against the oracle's sequential LESS_EQUAL test."""

@@ -195,3 +195,26 @@ def test_matrix_shims():
     b = rng.random((4, 4)).astype(np.float32)
     np.testing.assert_allclose(orc.mat_mul(a, b), a @ b, rtol=1e-6)
     np.testing.assert_allclose(orc.mat_inverse(a) @ a, np.eye(4), atol=1e-5)
+
+
+def test_msaa_sample_positions_and_box_resolve():
+    # FrameBuffer.cpp:107-191 sample tables (1/16 px around the centre), Rasterizer.h:245-270 per-sample
+    # coverage, FrameBuffer.cpp:70-87 box resolve. A vertical edge through x = 5.5 (the centre column of
+    # pixel 5): samples with offset.x < 0 are left of it. 4x table: (-2,-6) (6,-2) (-6,2) (2,6) -> samples 0, 2
+    # are covered by the left half-plane; resolved alpha = 2/4 * 255 -> 128 (FromFloats rounding).
+    sc = raster_scene([[[1.5, 1.5], [5.5, 1.5], [5.5, 12.5]], [[1.5, 1.5], [5.5, 12.5], [1.5, 12.5]]], [0.5, 0.5])
+    sc["shader"] = 2
+    o = orc.Oracle(sc.width, sc.height, 1)
+    o.set_msaa(2)
+    o.set_transform(sc.mv, sc.proj, sc.raster)
+    o.set_shader(2)
+    o.render(sc.vertices, sc.indices)
+    assert o.samples == 4
+    cov = [(o.winner(k) != 0xFFFFFFFF)[::-1] for k in range(4)]
+    assert cov[0][6, 5] and cov[2][6, 5] and not cov[1][6, 5] and not cov[3][6, 5]
+    assert all(c[6, 3] for c in cov)                      # interior pixel: every sample
+    assert not any(c[6, 6] for c in cov)                  # pixel right of the edge: none
+    col = o.color()[::-1]
+    assert col[6, 3, 3] == 255 and col[6, 5, 3] == 128 and col[6, 6, 3] == 0
+    # colour is shaded once per fragment at the pixel centre, so the half-covered pixel is half the interior colour
+    assert abs(int(col[6, 5, 0]) - int(round(col[6, 3, 0] / 2))) <= 1
