@@ -117,7 +117,10 @@ class ClockSampler:
         inside = [s for s in self.samples if t0 <= s[0] <= t1]
         window = "timed"
         if len(inside) < 3:
-            inside, window = self.samples, "warmup+timed"
+            # a millisecond-scale timed region holds too few ~1 ms NVML samples: use every sample taken under
+            # load (the back-to-back warm-up frames and the timed region), dropping the idle start
+            busy = [s for s in self.samples if s[0] <= t1]
+            inside, window = busy[len(busy) // 4:], "under load: warm-up frames + timed region"
         names = {
             getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
             getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
@@ -301,6 +304,7 @@ def ours_arm(args):
     sampler = ClockSampler(local)
     with torch.cuda.stream(stream):
         works = [None, None]
+        sampler.start()                           # NVML calls take ~1 ms each: sample through warm-up and the timed region
         # warm-up: W steps plus a fixed 1000 more so clocks settle (a fixed count: every rank must issue the
         # same number of gathers)
         for i in range(max(args.warmup, 3) + 1000):
@@ -310,10 +314,6 @@ def ours_arm(args):
                 r.Synchronize()
         drain(works)
         r.Synchronize()
-        sampler.start()
-        for j in range(32):                       # keep the GPU busy while the sampler spins up
-            step(j, works)
-        drain(works)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -1,6 +1,6 @@
 // headless_viewer.cpp — the reference's RealtimeViewer (RealtimeViewer/Main.cpp) without the window:
 // same calls in the same order (OnInit :32-62, OnRender :65-75), frames go to a BMP instead of
-// glDrawPixels. Usage: headless_viewer [frames] [out.bmp] [dump.bin]
+// glDrawPixels. Usage: headless_viewer [frames] [out.bmp] [dump.bin] [mesh.obj] [msaa_log2]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -21,7 +21,15 @@ int main(int argc, char** argv)
     Camera camera;
     camera.Init(Vector3(0, 0, -5), Vector3(0, 0, 0), Vector3(0, 1, 0), W, H, 65, 0.01f);   // Main.cpp:39
     Mesh mesh;
-    mesh.LoadSphere(Vector3(0, 0, 0), Vector3(1, 1, 1), Vector3(0, 0, 0), 1.2f);            // Main.cpp:42
+    if (argc > 4 && argv[4][0]) {
+        if (!mesh.LoadMesh(Vector3(0, 0, 0), Vector3(1, 1, 1), Vector3(0, 30, 0), argv[4])) {   // Main.cpp:44-51 (LoadMesh variants)
+            std::fprintf(stderr, "cannot load %s\n", argv[4]);
+            return 1;
+        }
+    } else {
+        mesh.LoadSphere(Vector3(0, 0, 0), Vector3(1, 1, 1), Vector3(0, 0, 0), 1.2f);        // Main.cpp:42
+    }
+    if (argc > 5) renderer.SetMSAAMode(std::atoi(argv[5]));                                 // Main.cpp:97
     renderer.SetPixelShader(PixelShaderKind::BlinnPhong);
 
     auto t0 = std::chrono::steady_clock::now();

@@ -12,6 +12,10 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <tuple>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -204,6 +208,77 @@ public:
         }
         const uint idx[6] = { 0, 2, 1, 1, 2, 3 };
         SetBuffers(v, 4, idx, 2);
+    }
+    // Mesh::LoadMesh (Utils/Mesh.cpp:11-34): Wavefront OBJ. The reference delegates to EDXUtil's ObjMesh (absent);
+    // this reader handles v / vt / vn / f (polygons fanned, negative indices, v, v/vt, v//vn, v/vt/vn), builds one
+    // vertex per distinct index triple, computes area-weighted normals when the file has none, and applies
+    // scale, then rotation (degrees, about x then y then z), then translation. Materials map to texture id 0.
+    bool LoadMesh(const Vector3& pos, const Vector3& scl, const Vector3& rot, const char* path)
+    {
+        FILE* f = std::fopen(path, "r");
+        if (!f) return false;
+        std::vector<Vector3> P, N;
+        std::vector<Vector2> T;
+        std::vector<Vertex_PositionNormalTex> verts;
+        std::vector<uint> idx;
+        std::map<std::tuple<int, int, int>, uint> seen;
+        char line[1024];
+        while (std::fgets(line, sizeof(line), f)) {
+            if (line[0] == 'v' && line[1] == ' ') { Vector3 v; if (std::sscanf(line + 2, "%f %f %f", &v.x, &v.y, &v.z) == 3) P.push_back(v); }
+            else if (line[0] == 'v' && line[1] == 'n') { Vector3 v; if (std::sscanf(line + 3, "%f %f %f", &v.x, &v.y, &v.z) == 3) N.push_back(v); }
+            else if (line[0] == 'v' && line[1] == 't') { Vector2 v; if (std::sscanf(line + 3, "%f %f", &v.x, &v.y) >= 1) T.push_back(v); }
+            else if (line[0] == 'f' && line[1] == ' ') {
+                std::vector<uint> poly;
+                char* p = line + 2;
+                while (*p) {
+                    while (*p == ' ' || *p == '\t') p++;
+                    if (*p == '\0' || *p == '\n' || *p == '\r') break;
+                    int vi = 0, ti = 0, ni = 0;
+                    vi = (int)std::strtol(p, &p, 10);
+                    if (*p == '/') { p++; if (*p != '/') ti = (int)std::strtol(p, &p, 10); if (*p == '/') { p++; ni = (int)std::strtol(p, &p, 10); } }
+                    if (vi < 0) vi = (int)P.size() + vi + 1;
+                    if (ti < 0) ti = (int)T.size() + ti + 1;
+                    if (ni < 0) ni = (int)N.size() + ni + 1;
+                    if (vi < 1 || vi > (int)P.size()) continue;
+                    auto key = std::make_tuple(vi, ti, ni);
+                    auto it = seen.find(key);
+                    if (it == seen.end()) {
+                        Vertex_PositionNormalTex o;
+                        o.Position = P[vi - 1];
+                        o.Normal = (ni >= 1 && ni <= (int)N.size()) ? N[ni - 1] : Vector3(0, 0, 0);
+                        o.TexCoord = (ti >= 1 && ti <= (int)T.size()) ? T[ti - 1] : Vector2(0, 0);
+                        it = seen.emplace(key, (uint)verts.size()).first;
+                        verts.push_back(o);
+                    }
+                    poly.push_back(it->second);
+                }
+                for (size_t k = 2; k < poly.size(); k++) { idx.push_back(poly[0]); idx.push_back(poly[k - 1]); idx.push_back(poly[k]); }
+            }
+        }
+        std::fclose(f);
+        if (verts.empty() || idx.empty()) return false;
+        if (N.empty()) {                                   // area-weighted vertex normals
+            for (size_t t = 0; t + 2 < idx.size(); t += 3) {
+                Vector3 a = verts[idx[t]].Position, b = verts[idx[t + 1]].Position, c = verts[idx[t + 2]].Position;
+                Vector3 n = Vector3::Cross(b - a, c - a);
+                for (int k = 0; k < 3; k++) verts[idx[t + k]].Normal = verts[idx[t + k]].Normal + n;
+            }
+            for (auto& v : verts) { float l = std::sqrt(Vector3::Dot(v.Normal, v.Normal)); if (l > 0) v.Normal = v.Normal * (1.0f / l); }
+        }
+        const float d2r = 3.14159265358979323846f / 180.0f;
+        const float cx = std::cos(rot.x * d2r), sx = std::sin(rot.x * d2r), cy = std::cos(rot.y * d2r), sy = std::sin(rot.y * d2r);
+        const float cz = std::cos(rot.z * d2r), sz = std::sin(rot.z * d2r);
+        auto rotate = [&](Vector3 v) {
+            v = Vector3(v.x, cx * v.y - sx * v.z, sx * v.y + cx * v.z);
+            v = Vector3(cy * v.x + sy * v.z, v.y, -sy * v.x + cy * v.z);
+            return Vector3(cz * v.x - sz * v.y, sz * v.x + cz * v.y, v.z);
+        };
+        for (auto& v : verts) {
+            v.Position = rotate(Vector3(v.Position.x * scl.x, v.Position.y * scl.y, v.Position.z * scl.z)) + pos;
+            v.Normal = rotate(v.Normal);
+        }
+        SetBuffers(verts.data(), verts.size(), idx.data(), idx.size() / 3);
+        return true;
     }
     // raw submission in the reference's wire format (CreateVertexBuffer / CreateIndexBuffer)
     void SetBuffers(const void* vertices, size_t vertexCount, const uint* indices, size_t triCount)

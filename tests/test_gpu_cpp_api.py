@@ -14,6 +14,66 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+CUBE_OBJ = """# unit cube, quads, no normals
+v -1 -1 -1
+v 1 -1 -1
+v 1 1 -1
+v -1 1 -1
+v -1 -1 1
+v 1 -1 1
+v 1 1 1
+v -1 1 1
+f 1 4 3 2
+f 5 6 7 8
+f 1 2 6 5
+f 2 3 7 6
+f 3 4 8 7
+f 4 1 5 8
+"""
+
+
+def run_viewer(tmp_path, extra, msaa=0):
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
+    bmp, dump = str(tmp_path / "frame.bmp"), str(tmp_path / "dump.bin")
+    out = subprocess.run([os.path.join(ROOT, "examples", "headless_viewer"), "5", bmp, dump] + extra, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    return out, bmp, dump
+
+
+def compare_with_oracle(bmp, dump, msaa=0):
+    raw = open(dump, "rb").read()
+    w, h, nv, nt = struct.unpack("4I", raw[:16])
+    mats = np.frombuffer(raw, np.float32, 48, 16).reshape(3, 4, 4)
+    verts = np.frombuffer(raw, np.float32, nv * 8, 16 + 192).reshape(nv, 8)
+    idx = np.frombuffer(raw, np.uint32, nt * 3, 16 + 192 + nv * 32).reshape(nt, 3)
+    o = orc.Oracle(w, h, 0)
+    if msaa:
+        o.set_msaa(msaa)
+    o.set_transform(mats[0], mats[1], mats[2])
+    o.set_shader(scenes.SHADER_BLINN_PHONG)
+    o.render(verts, idx)
+    ref = o.color()
+    data = open(bmp, "rb").read()
+    assert data[:2] == b"BM"
+    off = struct.unpack("<I", data[10:14])[0]
+    bw, bh = struct.unpack("<ii", data[18:26])
+    assert (bw, bh) == (w, h)
+    pix = np.frombuffer(data, np.uint8, w * h * 3, off).reshape(h, w, 3)[..., ::-1]
+    assert np.abs(pix.astype(np.int32) - ref[..., :3].astype(np.int32)).max() <= 1
+    return ref, nt
+
+
+def test_obj_mesh_with_msaa_through_the_cpp_api(tmp_path):
+    obj = tmp_path / "cube.obj"
+    obj.write_text(CUBE_OBJ)
+    out, bmp, dump = run_viewer(tmp_path, [str(obj), "2"])
+    assert "Triangle Count: 12" in out.stdout               # 6 quads fanned into 12 triangles
+    ref, nt = compare_with_oracle(bmp, dump, msaa=2)
+    assert nt == 12
+    assert int((ref[..., 3] > 0).sum()) > 20000
+    assert len(np.unique(ref[..., 3])) > 2                   # anti-aliased silhouette: partial alpha values exist
+
+
 def test_headless_viewer_matches_oracle(tmp_path):
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
     bmp, dump = str(tmp_path / "frame.bmp"), str(tmp_path / "dump.bin")
