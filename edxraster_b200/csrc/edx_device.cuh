@@ -69,6 +69,7 @@ struct FrameParams {
     float albedo[3];
     int width, height, binsX, binsY;
     int shader, smallMax, smallMaxClip, hiz, hierarchical, captureIds, dump;
+    int fuseClip;            // clip single-plane straddlers inside geom_kernel instead of queueing them
     int msLevel, samples;    // Renderer::SetMSAAMode (Renderer.cpp:94-98): samples = 1 << msLevel
     uint32_t keyStride;      // keys per sample plane
     int rasterAffineXY;      // raster matrix has no z column and w' == 1: skip the unused z/w and w' arithmetic

@@ -209,8 +209,13 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
 // ---------------------------------------------------------------------------------------------
 // geom_kernel: stages a1, a2, a5, a6 and the small-triangle part of a10-a13
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) geom_kernel(const __grid_constant__ FrameParams P)
+__device__ void clip_single_plane(const FrameParams& P, uint32_t t, const V4& c0, const V4& c1, const V4& c2, uint32_t planes);
+
+__global__ void __launch_bounds__(256, 5) geom_kernel(const __grid_constant__ FrameParams P)
 {
+    // Programmatic dependent launch: the grid may be scheduled while the previous kernel in the stream is
+    // still draining; everything before this point touches no global memory.
+    cudaGridDependencySynchronize();
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.nTris) return;
     uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
@@ -222,8 +227,13 @@ __global__ void __launch_bounds__(256) geom_kernel(const __grid_constant__ Frame
         const uint32_t k0 = clip_code(c0), k1 = clip_code(c1), k2 = clip_code(c2);
         if (k0 | k1 | k2) {
         if (!(k0 & k1 & k2)) {                       // Clipper.h:107-109: straddles the frustum
-            uint32_t at = warp_append(&P.counters->nClipQueue);
-            if (at < P.clipQueueCap) P.clipQueue[at] = t;
+            const uint32_t planes = (k0 ^ k1) | (k1 ^ k2) | (k2 ^ k0);
+            if (P.fuseClip && __popc(planes) == 1) {
+                clip_single_plane(P, t, c0, c1, c2, planes);     // one plane: clip right here, no queue round trip
+            } else {
+                uint32_t at = warp_append(&P.counters->nClipQueue);
+                if (at < P.clipQueueCap) P.clipQueue[at] = t;
+            }
         }
         return;
         }
@@ -367,8 +377,72 @@ __device__ __noinline__ void emit_fan(const FrameParams& P, uint32_t t, int fan,
 
 __device__ __forceinline__ V4 pick3(const V4* c, uint32_t i) { return i == 0 ? c[0] : (i == 1 ? c[1] : c[2]); }
 
+// One straddler that crosses exactly ONE clip plane (the common case at screen edges): the polygon has 3 or
+// 4 vertices in an order fixed by which vertices are inside (Clipper.h:196-229), so it is built with static
+// indices and lives in registers. Not inlined: it is shared by clip_kernel and (optionally) geom_kernel,
+// where it must not raise the hot path's register count.
+__device__ __noinline__ void clip_single_plane(const FrameParams& P, uint32_t t, const V4& c0, const V4& c1, const V4& c2, uint32_t planes)
+{
+    const V4 c[3] = { c0, c1, c2 };
+    // Fast path: exactly one plane is crossed (the common case at screen edges). The polygon has
+    // 3 or 4 vertices in an order fixed by which vertices are inside (Clipper.h:196-229), so it is
+    // built with static indices and lives in registers.
+    const int plane = (int)planes;
+    const uint32_t in = (plane_inside(plane, c[0]) ? 1u : 0u) | (plane_inside(plane, c[1]) ? 2u : 0u) | (plane_inside(plane, c[2]) ? 4u : 0u);
+    // Exactly two edges cross the plane. In the order Clipper.h:196-229 visits them they are
+    //   in = 1:(0>1),(2>0)  2:(0>1),(1>2)  4:(1>2),(2>0)  6:(0>1),(2>0)  5:(0>1),(1>2)  3:(1>2),(2>0)
+    const bool firstIs01 = (in != 4u && in != 3u), secondIs20 = (in == 1u || in == 4u || in == 6u || in == 3u);
+    const uint32_t ai = firstIs01 ? 0u : 1u, aj = firstIs01 ? 1u : 2u;
+    const uint32_t bi = secondIs20 ? 2u : 1u, bj = secondIs20 ? 0u : 2u;
+    V4 cutA, cutB; float wA[3], wB[3];
+    {
+        const float ua[3] = { ai == 0u ? 1.0f : 0.0f, ai == 1u ? 1.0f : 0.0f, 0.0f };
+        const float uaj[3] = { 0.0f, aj == 1u ? 1.0f : 0.0f, aj == 2u ? 1.0f : 0.0f };
+        cut_vertex(plane, pick3(c, ai), pick3(c, aj), ua, uaj, cutA, wA);
+        const float ub[3] = { 0.0f, bi == 1u ? 1.0f : 0.0f, bi == 2u ? 1.0f : 0.0f };
+        const float ubj[3] = { bj == 0u ? 1.0f : 0.0f, 0.0f, bj == 2u ? 1.0f : 0.0f };
+        cut_vertex(plane, pick3(c, bi), pick3(c, bj), ub, ubj, cutB, wB);
+    }
+    // assemble the polygon: slot pattern per inside-mask (C = cut, digits = original vertex)
+    //   1:[A,B,0]  2:[A,1,B]  4:[A,2,B]  6:[A,1,2,B]  5:[A,B,2,0]  3:[1,A,B,0]
+    V4 v[4]; float w[4][3]; int nv = (in == 1u || in == 2u || in == 4u) ? 3 : 4;
+    if (in == 0u || in == 7u) nv = 0;
+    int kind[4];           // 0..2 original vertex, 3 = cutA, 4 = cutB
+    switch (in) {
+    case 1: kind[0] = 3; kind[1] = 4; kind[2] = 0; kind[3] = 0; break;
+    case 2: kind[0] = 3; kind[1] = 1; kind[2] = 4; kind[3] = 4; break;
+    case 4: kind[0] = 3; kind[1] = 2; kind[2] = 4; kind[3] = 4; break;
+    case 6: kind[0] = 3; kind[1] = 1; kind[2] = 2; kind[3] = 4; break;
+    case 5: kind[0] = 3; kind[1] = 4; kind[2] = 2; kind[3] = 0; break;
+    default: kind[0] = 1; kind[1] = 3; kind[2] = 4; kind[3] = 0; break;
+    }
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int kd = kind[k];
+        v[k] = kd == 3 ? cutA : (kd == 4 ? cutB : pick3(c, (uint32_t)kd));
+        #pragma unroll
+        for (int m = 0; m < 3; m++) w[k][m] = kd == 3 ? wA[m] : (kd == 4 ? wB[m] : (kd == m ? 1.0f : 0.0f));
+    }
+    bool drop = nv == 0;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) if (k < nv && v[k].w <= 0.0f) drop = true;                  // Clipper.h:280-287
+    if (drop) return;
+    uint32_t src[4];
+    #pragma unroll
+    for (int k = 0; k < 4; k++) { src[k] = vertex_source(w[k]); if (src[k] < 3) v[k] = pick3(c, src[k]); }
+    const uint32_t nFan = (uint32_t)(nv - 2);
+    const uint32_t slot = atomicAdd(&P.counters->nClipRecs, nFan);
+    const bool haveRecs = slot + nFan <= P.clipRecCap;
+    if (haveRecs) P.clipSlot[t] = slot;
+    const float iwA = inv_w(v[0].w), zA = fmul(v[0].z, iwA);
+    emit_fan(P, t, 0, slot, haveRecs, v[0], v[1], v[2], iwA, zA, src[0] | (src[1] << 2) | (src[2] << 4), w[0], w[1], w[2]);
+    if (nv == 4)
+        emit_fan(P, t, 1, slot, haveRecs, v[0], v[2], v[3], iwA, zA, src[0] | (src[2] << 2) | (src[3] << 4), w[0], w[2], w[3]);
+}
+
 __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ FrameParams P)
 {
+    cudaGridDependencySynchronize();
     const uint32_t n = min(P.counters->nClipQueue, P.clipQueueCap);
     // Work item q goes to lane q / W of warp q % W (W = warps in the grid): a short queue is spread one
     // triangle per warp over the whole chip instead of packing 32 divergent clippers into each of a
@@ -386,63 +460,7 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
         const uint32_t k0 = clip_code(c[0]), k1 = clip_code(c[1]), k2 = clip_code(c[2]);
         const uint32_t planes = (k0 ^ k1) | (k1 ^ k2) | (k2 ^ k0);           // Clipper.h:119
 
-        if (__popc(planes) == 1) {
-            // Fast path: exactly one plane is crossed (the common case at screen edges). The polygon has
-            // 3 or 4 vertices in an order fixed by which vertices are inside (Clipper.h:196-229), so it is
-            // built with static indices and lives in registers.
-            const int plane = (int)planes;
-            const uint32_t in = (plane_inside(plane, c[0]) ? 1u : 0u) | (plane_inside(plane, c[1]) ? 2u : 0u) | (plane_inside(plane, c[2]) ? 4u : 0u);
-            // Exactly two edges cross the plane. In the order Clipper.h:196-229 visits them they are
-            //   in = 1:(0>1),(2>0)  2:(0>1),(1>2)  4:(1>2),(2>0)  6:(0>1),(2>0)  5:(0>1),(1>2)  3:(1>2),(2>0)
-            const bool firstIs01 = (in != 4u && in != 3u), secondIs20 = (in == 1u || in == 4u || in == 6u || in == 3u);
-            const uint32_t ai = firstIs01 ? 0u : 1u, aj = firstIs01 ? 1u : 2u;
-            const uint32_t bi = secondIs20 ? 2u : 1u, bj = secondIs20 ? 0u : 2u;
-            V4 cutA, cutB; float wA[3], wB[3];
-            {
-                const float ua[3] = { ai == 0u ? 1.0f : 0.0f, ai == 1u ? 1.0f : 0.0f, 0.0f };
-                const float uaj[3] = { 0.0f, aj == 1u ? 1.0f : 0.0f, aj == 2u ? 1.0f : 0.0f };
-                cut_vertex(plane, pick3(c, ai), pick3(c, aj), ua, uaj, cutA, wA);
-                const float ub[3] = { 0.0f, bi == 1u ? 1.0f : 0.0f, bi == 2u ? 1.0f : 0.0f };
-                const float ubj[3] = { bj == 0u ? 1.0f : 0.0f, 0.0f, bj == 2u ? 1.0f : 0.0f };
-                cut_vertex(plane, pick3(c, bi), pick3(c, bj), ub, ubj, cutB, wB);
-            }
-            // assemble the polygon: slot pattern per inside-mask (C = cut, digits = original vertex)
-            //   1:[A,B,0]  2:[A,1,B]  4:[A,2,B]  6:[A,1,2,B]  5:[A,B,2,0]  3:[1,A,B,0]
-            V4 v[4]; float w[4][3]; int nv = (in == 1u || in == 2u || in == 4u) ? 3 : 4;
-            if (in == 0u || in == 7u) nv = 0;
-            int kind[4];           // 0..2 original vertex, 3 = cutA, 4 = cutB
-            switch (in) {
-            case 1: kind[0] = 3; kind[1] = 4; kind[2] = 0; kind[3] = 0; break;
-            case 2: kind[0] = 3; kind[1] = 1; kind[2] = 4; kind[3] = 4; break;
-            case 4: kind[0] = 3; kind[1] = 2; kind[2] = 4; kind[3] = 4; break;
-            case 6: kind[0] = 3; kind[1] = 1; kind[2] = 2; kind[3] = 4; break;
-            case 5: kind[0] = 3; kind[1] = 4; kind[2] = 2; kind[3] = 0; break;
-            default: kind[0] = 1; kind[1] = 3; kind[2] = 4; kind[3] = 0; break;
-            }
-            #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int kd = kind[k];
-                v[k] = kd == 3 ? cutA : (kd == 4 ? cutB : pick3(c, (uint32_t)kd));
-                #pragma unroll
-                for (int m = 0; m < 3; m++) w[k][m] = kd == 3 ? wA[m] : (kd == 4 ? wB[m] : (kd == m ? 1.0f : 0.0f));
-            }
-            bool drop = nv == 0;
-            #pragma unroll
-            for (int k = 0; k < 4; k++) if (k < nv && v[k].w <= 0.0f) drop = true;                  // Clipper.h:280-287
-            if (drop) continue;
-            uint32_t src[4];
-            #pragma unroll
-            for (int k = 0; k < 4; k++) { src[k] = vertex_source(w[k]); if (src[k] < 3) v[k] = pick3(c, src[k]); }
-            const uint32_t nFan = (uint32_t)(nv - 2);
-            const uint32_t slot = atomicAdd(&P.counters->nClipRecs, nFan);
-            const bool haveRecs = slot + nFan <= P.clipRecCap;
-            if (haveRecs) P.clipSlot[t] = slot;
-            const float iwA = inv_w(v[0].w), zA = fmul(v[0].z, iwA);
-            emit_fan(P, t, 0, slot, haveRecs, v[0], v[1], v[2], iwA, zA, src[0] | (src[1] << 2) | (src[2] << 4), w[0], w[1], w[2]);
-            if (nv == 4)
-                emit_fan(P, t, 1, slot, haveRecs, v[0], v[2], v[3], iwA, zA, src[0] | (src[2] << 2) | (src[3] << 4), w[0], w[2], w[3]);
-            continue;
-        }
+        if (__popc(planes) == 1) { clip_single_plane(P, t, c[0], c[1], c[2], planes); continue; }
 
         // General path: several planes, up to 9 vertices, polygon in local memory.
         Poly a, b;
@@ -810,6 +828,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     const uint32_t bx = (uint32_t)(bin % P.binsX), by = (uint32_t)(bin / P.binsX);
     const int ox = (int)bx << BIN_LOG2, oy = (int)by << BIN_LOG2;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
+    cudaGridDependencySynchronize();
     unsigned long long* gkeys = P.keys + (size_t)sId * P.keyStride + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
     if (ms && min(P.counters->nBig, P.bigCap) == 0) return;      // nothing on the tile path: the keys are already final
     // the tile's keys are wanted on every path: issue the loads before the (dependent) counter read
@@ -957,6 +976,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msaa_resolve_kernel(const __grid_constant__ FrameParams P)
 {
+    cudaGridDependencySynchronize();
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;            // key index inside one sample plane
     // invert key_index: [bin][tile 4x4][block 2x2][8x8]
     const uint32_t bin = i >> 12, tile = (i >> 8) & 15u, block = (i >> 6) & 3u, in = i & 63u;

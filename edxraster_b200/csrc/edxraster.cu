@@ -37,7 +37,7 @@ struct edx_context {
     float eye[3], light[3], albedo[3];
     int shader = EDX_SHADER_BLINN_PHONG;
     int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
-    int smallMax = 16, smallMaxClip = 8, hiz = 1;
+    int smallMax = 32, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1;
     bool colorDirty = false;
 
     unsigned long long* keys = nullptr;
@@ -134,6 +134,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.width = (int)c->width; P.height = (int)c->height; P.binsX = (int)c->binsX; P.binsY = (int)c->binsY;
     P.shader = c->shader; P.smallMax = c->smallMax; P.smallMaxClip = c->smallMaxClip; P.hiz = c->hiz; P.hierarchical = c->hierarchical;
     P.captureIds = c->captureIds; P.dump = 0;
+    P.fuseClip = c->fuseClip;
     P.msLevel = c->msaaLog2; P.samples = 1 << c->msaaLog2; P.keyStride = c->keyStride;
     const float* Rm = c->raster.m;
     P.rasterAffineXY = (Rm[2] == 0.0f && Rm[6] == 0.0f && Rm[12] == 0.0f && Rm[13] == 0.0f && Rm[14] == 0.0f && Rm[15] == 1.0f) ? 1 : 0;
@@ -169,25 +170,29 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     if (c->shader != EDX_SHADER_DEPTH_ONLY) c->colorDirty = true;
 
     c->launches = 0;
+    // Frame kernels are launched with programmatic stream serialization (PDL): each may be scheduled while
+    // its predecessor drains and blocks in cudaGridDependencySynchronize() until that one has completed.
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
+    auto launch = [&](auto kernel, dim3 grid, dim3 block, size_t smem) -> cudaError_t {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        c->launches++;
+        return cudaLaunchKernelEx(&cfg, kernel, P);
+    };
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[0], c->stream));
-    if (m->nTris) {
-        geom_kernel<<<(m->nTris + 255) / 256, 256, 0, c->stream>>>(P);
-        c->launches++;
-    }
+    if (m->nTris) EDX_CUDA(c, launch(geom_kernel, dim3((m->nTris + 255) / 256), dim3(256), 0));
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[1], c->stream));
-    if (m->nTris) {
-        clip_kernel<<<148 * 4, 128, 0, c->stream>>>(P);
-        c->launches++;
-    }
+    if (m->nTris) EDX_CUDA(c, launch(clip_kernel, dim3(148 * 4), dim3(128), 0));
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[2], c->stream));
     if (c->msaaLog2 == 0) {
-        tile_kernel<<<c->binsX * c->binsY, TILE_THREADS, sizeof(TileShared), c->stream>>>(P);
-        c->launches++;
+        EDX_CUDA(c, launch(tile_kernel, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
     } else {
         // one CTA per (bin, sample), then the per-pixel resolve that also ends the frame
-        tile_kernel<<<dim3(c->binsX * c->binsY, 1u << c->msaaLog2), TILE_THREADS, sizeof(TileShared), c->stream>>>(P);
-        msaa_resolve_kernel<<<(c->keyStride + 255) / 256, 256, 0, c->stream>>>(P);
-        c->launches += 2;
+        EDX_CUDA(c, launch(tile_kernel, dim3(c->binsX * c->binsY, 1u << c->msaaLog2), dim3(TILE_THREADS), sizeof(TileShared)));
+        EDX_CUDA(c, launch(msaa_resolve_kernel, dim3((c->keyStride + 255) / 256), dim3(256), 0));
     }
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[3], c->stream));
     EDX_CUDA(c, cudaGetLastError());
@@ -392,6 +397,8 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!c || !name) return EDX_ERR_INVALID;
     if (!strcmp(name, "small_max")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max in [0,64]"); c->smallMax = value; return EDX_OK; }
     if (!strcmp(name, "small_max_clip")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max_clip in [0,64]"); c->smallMaxClip = value; return EDX_OK; }
+    if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }
+    if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }
     return fail(c, EDX_ERR_INVALID, std::string("unknown option ") + name);
 }

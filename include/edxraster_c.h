@@ -144,7 +144,7 @@ int edx_timer_end(edx_context* ctx, float* elapsed_ms);
 int edx_set_profiling(edx_context* ctx, int enabled);
 int edx_get_stats(edx_context* ctx, edx_stats* out);
 /* tuning knobs: "small_max" / "small_max_clip" (largest pixel-centre box side rasterised directly by the
- * geometry / clip kernels, defaults 16 / 8),
+ * geometry / clip kernels, defaults 32 / 8),
  * "hiz" (hierarchical-Z culling of the tile path, default 1) */
 int edx_set_option(edx_context* ctx, const char* name, int value);
 /* number of kernel launches issued by the last RenderMesh (for bench.py's gpu_launches) */

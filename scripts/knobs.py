@@ -13,7 +13,7 @@ r.SetTransform(sc.mv, sc.proj, sc.raster)
 r.SetPixelShader(sc.shader)
 m = r.CreateMesh(sc.vertices, sc.indices)
 r.SetProfiling(True)
-for opts in ({"hiz": 1, "small_max": 16}, {"hiz": 0, "small_max": 16}, {"hiz": 1, "small_max": 8}, {"hiz": 1, "small_max": 32}, {"hiz": 1, "small_max": 32, "small_max_clip": 16}, {"hiz": 1, "small_max": 16, "small_max_clip": 4}):
+for opts in ({"pdl": 1}, {"pdl": 0}):
     for k, v in opts.items():
         r.SetOption(k, v)
     acc = {"geom": 0, "clip": 0, "tile": 0, "total": 0}
@@ -22,4 +22,10 @@ for opts in ({"hiz": 1, "small_max": 16}, {"hiz": 0, "small_max": 16}, {"hiz": 1
         if i >= 2:
             st = r.GetStats()
             for k in acc: acc[k] += st["stage_ms"][k] / 4
-    print(a.workload, opts, {k: round(v * 1000, 1) for k, v in acc.items()}, "binned", st["binned_tris"], flush=True)
+    r.SetProfiling(False)
+    for _ in range(5): r.RenderMesh(m)
+    r.Synchronize(); r.TimerBegin()
+    for _ in range(50): r.RenderMesh(m)
+    ms = r.TimerEnd() / 50
+    r.SetProfiling(True)
+    print(a.workload, opts, {k: round(v * 1000, 1) for k, v in acc.items()}, "binned", st["binned_tris"], "back-to-back us/frame %.1f" % (ms * 1000), flush=True)
