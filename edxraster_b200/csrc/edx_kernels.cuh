@@ -143,6 +143,36 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
             const uint32_t base1 = r1 - (uint32_t)e.bias1, base2 = r2 - (uint32_t)e.bias2;   // unbiased edge 1 / 2 at (x0, y0)
             const int wm1 = x1 - x0;
             uint32_t lo = 0, hi = 0;
+            if (wm1 < 5 && y1 - y0 < 5) {
+                // Tiny box (the bulk of a dense mesh): evaluate a fixed 5x5 block of pixels branch-free and
+                // mask off what lies outside the real box. Every lane of the warp executes the same ~130
+                // instructions instead of the warp iterating max(height) x max(width) times.
+                const uint32_t colMask = (1u << (wm1 + 1)) - 1u;
+                const int hgt = y1 - y0 + 1;
+                #pragma unroll
+                for (int dy = 0; dy < 5; dy++) {
+                    uint32_t a0 = r0, a1 = r1, a2 = r2, row = 0;
+                    #pragma unroll
+                    for (int dx = 0; dx < 5; dx++) {
+                        row |= (~(a0 | a1 | a2) >> 31) << dx;           // bit dx = pixel x0 + dx covered
+                        a0 += sB0; a1 += sB1; a2 += sB2;
+                    }
+                    row = dy < hgt ? (row & colMask) : 0u;
+                    if (dy < 4) lo |= row << (8 * dy); else hi |= row;
+                    r0 += sC0; r1 += sC1; r2 += sC2;
+                }
+                while (lo | hi) {
+                    int b;
+                    if (lo) { b = __ffs(lo) - 1; lo &= lo - 1; } else { b = 32 + __ffs(hi) - 1; hi &= hi - 1; }
+                    const uint32_t dx = (uint32_t)(b & 7), dy = (uint32_t)(b >> 3);
+                    float l0, l1;
+                    barycentric((int)(base1 + dx * sB1 + dy * sC1), (int)(base2 + dx * sB2 + dy * sC2), s.invDet, l0, l1);
+                    const float d = depth_at(l0, l1, z0, z1, z2);
+                    if (d <= 1.0f)
+                        atomicMin(P.keys + key_index(x0 + (int)dx, y0 + (int)dy, P.binsX), make_key(d, prim));
+                }
+                return;
+            }
             for (int y = y0; y <= y1; y++) {
                 uint32_t a0 = r0, a1 = r1, a2 = r2, row = 0;
                 for (int x = x0; x <= x1; x++) {
