@@ -69,6 +69,7 @@ struct FrameParams {
     float albedo[3];
     int width, height, binsX, binsY;
     int shader, smallMax, smallMaxClip, hiz, hierarchical, captureIds, dump;
+    int clusterCull;         // skip whole 256-triangle clusters whose bounding box is outside one clip plane
     int fuseClip;            // clip single-plane straddlers inside geom_kernel instead of queueing them
     int msLevel, samples;    // Renderer::SetMSAAMode (Renderer.cpp:94-98): samples = 1 << msLevel
     uint32_t keyStride;      // keys per sample plane
@@ -77,6 +78,7 @@ struct FrameParams {
     const float4* pos4;      // x, y, z, texcoord.v
     const float4* nrm4;      // nx, ny, nz, texcoord.u
     const uint32_t* i0; const uint32_t* i1; const uint32_t* i2;
+    const float4* clusterBox;            // per 256-triangle cluster: object-space AABB (min.xyz, max.xyz), built at upload
     uint32_t nTris, nVerts;
     // frame state
     unsigned long long* keys;            // 64-bit visibility keys, bin/tile/block-tiled, L2 resident

@@ -51,6 +51,46 @@ __global__ void __launch_bounds__(256) split_indices_kernel(const uint32_t* __re
     }
 }
 
+// Object-space bounding box of each cluster of 256 consecutive triangles (= one geom_kernel CTA). Built once
+// per mesh upload; lets a frame skip clusters that lie entirely outside one clip plane.
+__global__ void __launch_bounds__(256) cluster_bounds_kernel(const float4* __restrict__ pos4, const uint32_t* __restrict__ i0,
+                                                             const uint32_t* __restrict__ i1, const uint32_t* __restrict__ i2,
+                                                             uint32_t nTris, float4* __restrict__ boxes)
+{
+    __shared__ float red[6][8];
+    const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+    float lo[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, hi[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+    bool bad = false;
+    if (t < nTris) {
+        const uint32_t id[3] = { __ldg(i0 + t), __ldg(i1 + t), __ldg(i2 + t) };
+        #pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float4 p = __ldg(pos4 + id[k]);
+            const float v[3] = { p.x, p.y, p.z };
+            #pragma unroll
+            for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], v[a]); hi[a] = fmaxf(hi[a], v[a]); bad |= !(fabsf(v[a]) < 3.0e38f); }
+        }
+    }
+    #pragma unroll
+    for (int a = 0; a < 3; a++)
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
+        }
+    const bool anyBad = __syncthreads_or(bad);             // NaN / inf coordinates: never cull this cluster
+    if ((threadIdx.x & 31) == 0)
+        for (int a = 0; a < 3; a++) { red[a][threadIdx.x >> 5] = lo[a]; red[3 + a][threadIdx.x >> 5] = hi[a]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            for (int a = 0; a < 3; a++) { red[a][0] = fminf(red[a][0], red[a][w]); red[3 + a][0] = fmaxf(red[3 + a][0], red[3 + a][w]); }
+        // w of the min box carries a validity flag
+        boxes[2 * blockIdx.x] = make_float4(red[0][0], red[1][0], red[2][0], anyBad ? 0.0f : 1.0f);
+        boxes[2 * blockIdx.x + 1] = make_float4(red[3][0], red[4][0], red[5][0], 0.0f);
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_keys_kernel(ulonglong2* __restrict__ keys, size_t nPairs)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,6 +286,38 @@ __global__ void __launch_bounds__(256, 5) geom_kernel(const __grid_constant__ Fr
     // Programmatic dependent launch: the grid may be scheduled while the previous kernel in the stream is
     // still draining; everything before this point touches no global memory.
     cudaGridDependencySynchronize();
+    if (P.clusterCull) {
+        // Cluster cull: if all 8 corners of this CTA's 256-triangle bounding box are outside the SAME clip plane
+        // by a margin that dominates fp32 rounding of the transform, every vertex of the cluster is outside that
+        // plane too, i.e. every triangle would be rejected by Clipper.h:109. Exact, and the CTA loads nothing else.
+        // Eight lanes of warp 0 take one corner each; the verdict reaches the CTA through shared memory.
+        __shared__ uint32_t sOut;
+        if (threadIdx.x < 32) {
+            const float4 bl = __ldg(P.clusterBox + 2 * blockIdx.x), bh = __ldg(P.clusterBox + 2 * blockIdx.x + 1);
+            const float* M = P.mvp;
+            // Largest magnitude any vertex of the box can reach in each row's sum: bounds the fp32 rounding error
+            // (4 roundings, < 2.5e-7 of this) of EVERY vertex in the box; the margin is 16x that.
+            const float ax = fmaxf(fabsf(bl.x), fabsf(bh.x)), ay = fmaxf(fabsf(bl.y), fabsf(bh.y)), az = fmaxf(fabsf(bl.z), fabsf(bh.z));
+            const float mx = fabsf(M[0]) * ax + fabsf(M[1]) * ay + fabsf(M[2]) * az + fabsf(M[3]);
+            const float my = fabsf(M[4]) * ax + fabsf(M[5]) * ay + fabsf(M[6]) * az + fabsf(M[7]);
+            const float mz = fabsf(M[8]) * ax + fabsf(M[9]) * ay + fabsf(M[10]) * az + fabsf(M[11]);
+            const float mw = fabsf(M[12]) * ax + fabsf(M[13]) * ay + fabsf(M[14]) * az + fabsf(M[15]);
+            const float ex = 4e-6f * (mx + mw), ey = 4e-6f * (my + mw), ez = 4e-6f * (mz + mw);
+            const int k = threadIdx.x & 7;
+            const V4 c = to_clip(M, (k & 1) ? bh.x : bl.x, (k & 2) ? bh.y : bl.y, (k & 4) ? bh.z : bl.z);
+            uint32_t o = 0;
+            if (c.x < -c.w - ex) o |= LEFT_BIT;
+            if (c.x > c.w + ex) o |= RIGHT_BIT;
+            if (c.y < -c.w - ey) o |= BOTTOM_BIT;
+            if (c.y > c.w + ey) o |= TOP_BIT;
+            if (c.z > c.w + ez) o |= FAR_BIT;
+            if (c.z < -ez) o |= NEAR_BIT;
+            o = __reduce_and_sync(0xFFFFFFFFu, o);          // lanes 8..31 repeat corners 0..7
+            if (threadIdx.x == 0) sOut = bl.w != 0.0f ? o : 0u;
+        }
+        __syncthreads();
+        if (sOut) return;
+    }
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.nTris) return;
     uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);

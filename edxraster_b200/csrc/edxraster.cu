@@ -8,6 +8,7 @@
 #include "edx_kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,8 +22,10 @@ struct edx_mesh {
     float4* nrm4 = nullptr;
     uint32_t* i0 = nullptr; uint32_t* i1 = nullptr; uint32_t* i2 = nullptr;
     uint32_t* clipSlot = nullptr;
+    float4* clusterBox = nullptr;                          // 2 x float4 per 256-triangle cluster
     void* staging = nullptr; size_t stagingBytes = 0;     // device-side landing area for the AoS upload
     uint32_t nVerts = 0, nTris = 0, capVerts = 0, capTris = 0;
+    bool coherent = false;                                 // triangle order is spatially coherent: cluster culling pays
 };
 
 struct edx_context {
@@ -37,7 +40,7 @@ struct edx_context {
     float eye[3], light[3], albedo[3];
     int shader = EDX_SHADER_BLINN_PHONG;
     int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
-    int smallMax = 32, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1;
+    int smallMax = 32, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1;
     bool colorDirty = false;
 
     unsigned long long* keys = nullptr;
@@ -134,11 +137,11 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.width = (int)c->width; P.height = (int)c->height; P.binsX = (int)c->binsX; P.binsY = (int)c->binsY;
     P.shader = c->shader; P.smallMax = c->smallMax; P.smallMaxClip = c->smallMaxClip; P.hiz = c->hiz; P.hierarchical = c->hierarchical;
     P.captureIds = c->captureIds; P.dump = 0;
-    P.fuseClip = c->fuseClip;
+    P.fuseClip = c->fuseClip; P.clusterCull = (c->clusterCull == 1 && m->coherent) || c->clusterCull == 2;
     P.msLevel = c->msaaLog2; P.samples = 1 << c->msaaLog2; P.keyStride = c->keyStride;
     const float* Rm = c->raster.m;
     P.rasterAffineXY = (Rm[2] == 0.0f && Rm[6] == 0.0f && Rm[12] == 0.0f && Rm[13] == 0.0f && Rm[14] == 0.0f && Rm[15] == 1.0f) ? 1 : 0;
-    P.pos4 = m->pos4; P.nrm4 = m->nrm4; P.i0 = m->i0; P.i1 = m->i1; P.i2 = m->i2;
+    P.pos4 = m->pos4; P.nrm4 = m->nrm4; P.i0 = m->i0; P.i1 = m->i1; P.i2 = m->i2; P.clusterBox = m->clusterBox;
     P.nTris = m->nTris; P.nVerts = m->nVerts;
     P.keys = c->keys;
     P.big = c->big; P.bigCap = c->bigCap; P.bigBox = c->bigBox;
@@ -248,6 +251,7 @@ int upload_mesh(edx_context* c, edx_mesh* m, const void* vertices, uint32_t nv, 
     if (nt) {
         EDX_CUDA(c, cudaMemcpyAsync(m->staging, indices, ib, cudaMemcpyHostToDevice, c->stream));
         split_indices_kernel<<<(nt + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const uint32_t*>(m->staging), m->i0, m->i1, m->i2, nt);
+        cluster_bounds_kernel<<<(nt + 255) / 256, 256, 0, c->stream>>>(m->pos4, m->i0, m->i1, m->i2, nt, m->clusterBox);
     }
     EDX_CUDA(c, cudaGetLastError());
     return EDX_OK;
@@ -397,6 +401,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!c || !name) return EDX_ERR_INVALID;
     if (!strcmp(name, "small_max")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max in [0,64]"); c->smallMax = value; return EDX_OK; }
     if (!strcmp(name, "small_max_clip")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max_clip in [0,64]"); c->smallMaxClip = value; return EDX_OK; }
+    if (!strcmp(name, "cluster_cull")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "cluster_cull: 0 off, 1 auto, 2 always"); c->clusterCull = value; return EDX_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }
@@ -418,10 +423,38 @@ int edx_mesh_create(edx_context* c, const void* vertices, uint32_t nv, const uin
     if (e == cudaSuccess) e = cudaMalloc(&m->i1, (size_t)m->capTris * 4);
     if (e == cudaSuccess) e = cudaMalloc(&m->i2, (size_t)m->capTris * 4);
     if (e == cudaSuccess) e = cudaMalloc(&m->clipSlot, (size_t)m->capTris * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&m->clusterBox, (size_t)((m->capTris + 255) / 256) * 32);
     if (e != cudaSuccess) { edx_mesh_destroy(c, m); return fail(c, EDX_ERR_OOM, cudaGetErrorString(e)); }
     if (int r = upload_mesh(c, m, vertices, nv, indices, nt)) { edx_mesh_destroy(c, m); return r; }
     // copy semantics of CreateVertexBuffer / CreateIndexBuffer: the caller's arrays are free on return
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { edx_mesh_destroy(c, m); return fail(c, EDX_ERR_CUDA, "mesh upload failed"); }
+    // Is the triangle order spatially coherent? Cluster culling (geom_kernel prologue) only pays when a
+    // cluster of 256 consecutive triangles is small compared with the mesh; decided once per upload.
+    {
+        const uint32_t nc = (nt + 255) / 256;
+        std::vector<float4> boxes(2 * (size_t)nc);
+        m->coherent = false;
+        if (nc >= 8 && cudaMemcpy(boxes.data(), m->clusterBox, boxes.size() * sizeof(float4), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            float lo[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, hi[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+            for (uint32_t k = 0; k < nc; k++) {
+                const float* a = &boxes[2 * k].x; const float* b = &boxes[2 * k + 1].x;
+                for (int ax = 0; ax < 3; ax++) { lo[ax] = std::min(lo[ax], a[ax]); hi[ax] = std::max(hi[ax], b[ax]); }
+            }
+            double sum = 0.0;
+            for (uint32_t k = 0; k < nc; k++) {
+                const float* a = &boxes[2 * k].x; const float* b = &boxes[2 * k + 1].x;
+                // geometric mean of the per-axis extent ratios (a thin strip of a terrain is coherent even
+                // though it spans most of the height range)
+                double r = 1.0; int axes = 0;
+                for (int ax = 0; ax < 3; ax++) {
+                    const double ext = (double)hi[ax] - lo[ax];
+                    if (ext > 0) { r *= std::max(1e-6, ((double)b[ax] - a[ax]) / ext); axes++; }
+                }
+                sum += axes ? std::pow(r, 1.0 / axes) : 1.0;
+            }
+            m->coherent = sum / nc < 0.25;
+        }
+    }
     *out = m;
     return EDX_OK;
 }
@@ -438,7 +471,7 @@ int edx_mesh_destroy(edx_context* c, edx_mesh* m)
 {
     if (!m) return EDX_OK;
     if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->lastMesh == m) { c->lastMesh = nullptr; c->framePending = false; } }
-    dev_free(m->pos4); dev_free(m->nrm4); dev_free(m->i0); dev_free(m->i1); dev_free(m->i2); dev_free(m->clipSlot);
+    dev_free(m->pos4); dev_free(m->nrm4); dev_free(m->i0); dev_free(m->i1); dev_free(m->i2); dev_free(m->clipSlot); dev_free(m->clusterBox);
     if (m->staging) cudaFree(m->staging);
     delete m;
     return EDX_OK;

@@ -145,7 +145,9 @@ int edx_set_profiling(edx_context* ctx, int enabled);
 int edx_get_stats(edx_context* ctx, edx_stats* out);
 /* tuning knobs: "small_max" / "small_max_clip" (largest pixel-centre box side rasterised directly by the
  * geometry / clip kernels, defaults 32 / 8),
- * "hiz" (hierarchical-Z culling of the tile path, default 1) */
+ * "hiz" (hierarchical-Z culling of the tile path, default 1), "cluster_cull" (frustum-cull 256-triangle
+ * clusters: 0 off, 1 = only for meshes whose triangle order is spatially coherent (default), 2 always),
+ * "pdl" (programmatic dependent launch, default 1). None of them changes a pixel. */
 int edx_set_option(edx_context* ctx, const char* name, int value);
 /* number of kernel launches issued by the last RenderMesh (for bench.py's gpu_launches) */
 int edx_last_launch_count(const edx_context* ctx);

@@ -13,7 +13,7 @@ r.SetTransform(sc.mv, sc.proj, sc.raster)
 r.SetPixelShader(sc.shader)
 m = r.CreateMesh(sc.vertices, sc.indices)
 r.SetProfiling(True)
-for opts in ({"pdl": 1}, {"pdl": 0}):
+for opts in ({"cluster_cull": 1}, {"cluster_cull": 0}):
     for k, v in opts.items():
         r.SetOption(k, v)
     acc = {"geom": 0, "clip": 0, "tile": 0, "total": 0}
