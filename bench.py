@@ -13,7 +13,7 @@ Timing: CUDA events on the launching stream around exactly K steps, barrier + sy
 sides, max over ranks. Inputs are made larger than L2 by rotating over 4 device copies of the mesh
 (4 x 108 MB of SoA streams > 126 MB L2), so every frame reads its geometry from HBM. At N > 1 the
 frames are independent (weak scaling: one frame per rank per step) and the finished depth buffers
-are gathered to rank 0 over NCCL, overlapped with the next frame's render.
+are gathered to rank 0 over NCCL in batches of 4 frames, overlapped with the next batch's rendering.
 
 Rank 0 prints ONE JSON line on stdout; everything else goes to stderr.
 """
@@ -248,6 +248,10 @@ def secondary_config(name, device, peak):
 
 
 def ours_arm(args):
+    # stdout carries exactly one JSON line: park the real stdout and point fd 1 at stderr so that nothing a
+    # library prints (NCCL's version banner, for one) can land next to it
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from edxraster_b200 import renderer as R
@@ -260,6 +264,8 @@ def ours_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its banner / debug lines to stdout by default; stdout is reserved for the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     peak, peak_src = measured_hbm_peak()
@@ -276,24 +282,46 @@ def ours_arm(args):
     copies = 4
     meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]
 
-    # render targets as torch tensors so NCCL can send them without a copy (double-buffered)
-    tgt_color = [torch.zeros((H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
-    tgt_depth = [torch.zeros((H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+    # Render targets are torch tensors so NCCL sends them without a copy. Frames are gathered to rank 0 in
+    # batches of G (one grouped send/recv per G frames: issuing a collective costs more host time than a 60 us
+    # frame takes on the GPU), double-buffered so batch k is on the wire while batch k+1 renders. Every frame
+    # still reaches rank 0 inside the timed region.
+    G = 4
+    tgt_color = [torch.zeros((G, H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
+    tgt_depth = [torch.zeros((G, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
     result = tgt_color if shaded else tgt_depth
     recv = None
     if world > 1 and rank == 0:
         recv = [[torch.empty_like(result[0]) for _ in range(world)] for _ in range(2)]
 
+    def send_batch(b, n, works):
+        if world > 1:
+            if n == G:
+                works[b] = dist.gather(result[b], recv[b] if rank == 0 else None, dst=0, async_op=True)
+            else:                                 # last, partial batch of the timed region
+                part = result[b][:n].contiguous()
+                rbuf = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
+                works[b] = dist.gather(part, rbuf, dst=0, async_op=True)
+
     def step(i, works):
-        b = i & 1
-        if world > 1 and works[b] is not None:
-            works[b].wait()                       # the gather that still reads target b (stream-level wait)
+        b, k = (i // G) & 1, i % G
+        if k == 0 and world > 1 and works[b] is not None:
+            works[b].wait()                       # the gather that still reads buffer b (stream-level wait)
             works[b] = None
-        r.SetRenderTarget(tgt_color[b].data_ptr(), tgt_depth[b].data_ptr())
+        r.SetRenderTarget(tgt_color[b][k].data_ptr(), tgt_depth[b][k].data_ptr())
         r.SetTransform(sc.mv, sc.proj, sc.raster)
         r.RenderMesh(meshes[i % copies])
-        if world > 1:
-            works[b] = dist.gather(result[b], recv[b] if rank == 0 else None, dst=0, async_op=True)
+        if k == G - 1:
+            send_batch(b, G, works)
+
+    def flush(n_steps, works):
+        """gather the frames of a trailing partial batch, then wait for everything in flight"""
+        if n_steps % G:
+            send_batch((n_steps // G) & 1, n_steps % G, works)
+        for b in (0, 1):
+            if works[b] is not None:
+                works[b].wait()
+                works[b] = None
 
     def drain(works):
         for b in (0, 1):
@@ -307,7 +335,8 @@ def ours_arm(args):
         sampler.start()                           # NVML calls take ~1 ms each: sample through warm-up and the timed region
         # warm-up: W steps plus a fixed 1000 more so clocks settle (a fixed count: every rank must issue the
         # same number of gathers)
-        for i in range(max(args.warmup, 3) + 1000):
+        n_warm = ((max(args.warmup, 3) + 1000 + G - 1) // G) * G
+        for i in range(n_warm):
             step(i, works)
             if i % 64 == 63:
                 drain(works)
@@ -322,7 +351,7 @@ def ours_arm(args):
         ev0.record(stream)
         for i in range(args.steps):
             step(i, works)
-        drain(works)
+        flush(args.steps, works)
         ev1.record(stream)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
@@ -415,7 +444,7 @@ def ours_arm(args):
         "config": {"workload": WORKLOADS[args.workload], "triangles": nt, "vertices": nv, "resolution": [W, H],
                    "frames_per_step_per_gpu": 1,
                    "l2": "inputs larger than L2: round-robin over %d device copies of the mesh (%d MB of SoA streams)" % (copies, copies * (nv * 32 + nt * 12) // 1000000),
-                   "gather": "NCCL gather of finished %s buffers to rank 0, overlapped with the next frame" % ("colour" if shaded else "depth") if world > 1 else "none (1 GPU)"},
+                   "gather": "NCCL gather of every finished %s buffer to rank 0, issued per batch of 4 frames and overlapped with the next batch's rendering" % ("colour" if shaded else "depth") if world > 1 else "none (1 GPU)"},
         "frames_per_s": world * 1000.0 / ms_step, "gpix_per_s": world * W * H / ms_step / 1e6,
         "clocks": sampler.summary(t0, t1),
         "e2e": {"value": world * nt / e2e["stream"] / 1e3, "unit": "Mtris/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -460,7 +489,8 @@ def ours_arm(args):
     else:
         dist.barrier()
         dist.destroy_process_group()
-    print(json.dumps(line), flush=True)
+    real_stdout.write(json.dumps(line) + "\n")
+    real_stdout.flush()
     return 0
 
 
