@@ -189,6 +189,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                 // instructions instead of the warp iterating max(height) x max(width) times.
                 const uint32_t colMask = (1u << (wm1 + 1)) - 1u;
                 const int hgt = y1 - y0 + 1;
+                uint32_t m = 0;                                         // bit 5*dy + dx
                 #pragma unroll
                 for (int dy = 0; dy < 5; dy++) {
                     uint32_t a0 = r0, a1 = r1, a2 = r2, row = 0;
@@ -197,14 +198,13 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                         row |= (~(a0 | a1 | a2) >> 31) << dx;           // bit dx = pixel x0 + dx covered
                         a0 += sB0; a1 += sB1; a2 += sB2;
                     }
-                    row = dy < hgt ? (row & colMask) : 0u;
-                    if (dy < 4) lo |= row << (8 * dy); else hi |= row;
+                    m |= (dy < hgt ? (row & colMask) : 0u) << (5 * dy);
                     r0 += sC0; r1 += sC1; r2 += sC2;
                 }
-                while (lo | hi) {
-                    int b;
-                    if (lo) { b = __ffs(lo) - 1; lo &= lo - 1; } else { b = 32 + __ffs(hi) - 1; hi &= hi - 1; }
-                    const uint32_t dx = (uint32_t)(b & 7), dy = (uint32_t)(b >> 3);
+                while (m) {
+                    const uint32_t b = (uint32_t)__ffs(m) - 1u;
+                    m &= m - 1u;
+                    const uint32_t dy = (b * 13u) >> 6, dx = b - 5u * dy;       // b / 5 for b < 25
                     float l0, l1;
                     barycentric((int)(base1 + dx * sB1 + dy * sC1), (int)(base2 + dx * sB2 + dy * sC2), s.invDet, l0, l1);
                     const float d = depth_at(l0, l1, z0, z1, z2);
