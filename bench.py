@@ -36,6 +36,7 @@ WORKLOADS = {
     "C2": "C2: 1,000,000 random <=4px triangles, 1920x1080, depth test only, fixed order",
     "C3": "C3: 2,000 screen-covering triangles, 3840x2160, Blinn-Phong, perspective-correct interpolation",
     "C4": "C4: 10,000,000-triangle displaced grid, 1920x1080, near/side-plane clipping, Blinn-Phong",
+    "C5": "C5: 256 camera views of the C4 mesh (10,000,000 triangles), 1920x1080, view i on GPU i mod N, frames gathered to rank 0",
 }
 
 
@@ -59,6 +60,10 @@ def measured_hbm_peak():
 
 def make_scene(name, scale):
     from edxraster_b200 import scenes
+    if name == "C5":
+        sc = scenes.by_name("C4", scale)
+        sc["views"] = scenes.config5_views(sc, 256)
+        return sc
     return scenes.by_name(name, scale)
 
 
@@ -279,7 +284,8 @@ def ours_arm(args):
     r.Initialize(W, H)
     r.SetTransform(sc.mv, sc.proj, sc.raster)
     r.SetPixelShader(sc.shader)
-    copies = 4
+    views = sc.get("views")
+    copies = 4 if nv * 32 + nt * 12 < 200e6 else 1          # C4/C5: one 440 MB mesh already exceeds L2
     meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]
 
     # Render targets are torch tensors so NCCL sends them without a copy. Frames are gathered to rank 0 in
@@ -331,7 +337,10 @@ def ours_arm(args):
             r.SetRenderTarget(dst if shaded else tgt_color[b][k].data_ptr(), tgt_depth[b][k].data_ptr() if shaded else dst)
         else:
             r.SetRenderTarget(tgt_color[b][k].data_ptr(), tgt_depth[b][k].data_ptr())
-        r.SetTransform(sc.mv, sc.proj, sc.raster)
+        if views is not None:
+            r.SetTransform(*views[(i * world + rank) % len(views)])   # C5: view v is rendered by rank v mod N
+        else:
+            r.SetTransform(sc.mv, sc.proj, sc.raster)
         r.RenderMesh(meshes[i % copies])
         if k == G - 1:
             send_batch(b, G, works)
@@ -395,7 +404,7 @@ def ours_arm(args):
         hi = torch.from_numpy(np.ascontiguousarray(sc.indices).view(np.int32)).pin_memory()
         hout = torch.empty((H, W), dtype=torch.float32).pin_memory() if not shaded else None
         r.SetRenderTarget(0, 0)
-        e2e_steps = max(3, min(args.steps, 20))
+        e2e_steps = max(3, min(args.steps, 20 if nt < 5_000_000 else 5))
 
         def e2e_step(i, upload):
             if upload:
@@ -465,7 +474,7 @@ def ours_arm(args):
         "vs_baseline": None, "dtype": "f32 depth / i32 28.4 fixed-point coverage", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "triangles": nt, "vertices": nv, "resolution": [W, H],
                    "frames_per_step_per_gpu": 1,
-                   "l2": "inputs larger than L2: round-robin over %d device copies of the mesh (%d MB of SoA streams)" % (copies, copies * (nv * 32 + nt * 12) // 1000000),
+                   "l2": "inputs larger than L2: round-robin over %d device cop%s of the mesh (%d MB of SoA streams)" % (copies, "ies" if copies > 1 else "y", copies * (nv * 32 + nt * 12) // 1000000),
                    "gather": ("none (1 GPU)" if world == 1 else
                               ("every finished %s buffer lands on rank 0 by NVLink peer stores from the resolve kernel itself (symmetric memory), one 4-byte all-reduce per 4 frames" if peer is not None else
                                "NCCL gather of every finished %s buffer to rank 0, per batch of 4 frames, overlapped with the next batch") % ("colour" if shaded else "depth"))},
@@ -500,7 +509,7 @@ def ours_arm(args):
                                     "note": "oracle/ timing build (CPU restatement of the reference SSE path; the reference cannot be built offline)"}
         except Exception as e:       # the oracle is only a reported baseline
             line["cpu_baseline"] = {"value": None, "error": str(e)}
-        if not args.no_extra:
+        if not args.no_extra and args.workload == "C2":
             also = {}
             for name in ("C1", "C3", "C4"):
                 if name == args.workload:
