@@ -49,6 +49,13 @@ struct __align__(16) ClipRec {
     float pad[3];
 };
 
+// One straddling triangle handed from geom_kernel to clip_kernel: its clip-space vertices travel with it
+// (64 bytes, one round trip) so the clipper does not have to chase index -> position -> transform again.
+struct __align__(16) ClipItem {
+    float c[12];             // c0.xyzw, c1.xyzw, c2.xyzw
+    uint32_t tri; uint32_t pad[3];
+};
+
 // Debug dump of stages a3-a6 (edx_debug_raster_triangles).
 struct DumpRec { int i[7]; float f[7]; };
 
@@ -84,7 +91,7 @@ struct FrameParams {
     unsigned long long* keys;            // 64-bit visibility keys, bin/tile/block-tiled, L2 resident
     BigRec* big; uint32_t bigCap;
     uint32_t* bigBox;                    // per tile-path triangle: its bin bounding box, 4 x u8 (x0, x1, y0, y1)
-    uint32_t* clipQueue; uint32_t clipQueueCap;
+    ClipItem* clipQueue; uint32_t clipQueueCap;
     ClipRec* clipRecs; uint32_t clipRecCap;
     uint32_t* clipSlot;                  // per submitted triangle: first ClipRec of its polygon
     Counters* counters;

@@ -334,7 +334,11 @@ __global__ void __launch_bounds__(256, 5) geom_kernel(const __grid_constant__ Fr
                 clip_single_plane(P, t, c0, c1, c2, planes);     // one plane: clip right here, no queue round trip
             } else {
                 uint32_t at = warp_append(&P.counters->nClipQueue);
-                if (at < P.clipQueueCap) P.clipQueue[at] = t;
+                if (at < P.clipQueueCap) {
+                    float4* q = reinterpret_cast<float4*>(P.clipQueue + at);
+                    q[0] = make_float4(c0.x, c0.y, c0.z, c0.w); q[1] = make_float4(c1.x, c1.y, c1.z, c1.w);
+                    q[2] = make_float4(c2.x, c2.y, c2.z, c2.w); q[3] = make_float4(__uint_as_float(t), 0.0f, 0.0f, 0.0f);
+                }
             }
         }
         return;
@@ -552,13 +556,13 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
     const uint32_t W = gridDim.x * (blockDim.x >> 5);
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     for (uint32_t q = (threadIdx.x & 31u) * W + gw; q < n; q += 32u * W) {
-        const uint32_t t = P.clipQueue[q];
-        uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
-        float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
+        const float4* item = reinterpret_cast<const float4*>(P.clipQueue + q);
+        const float4 q0 = __ldg(item), q1 = __ldg(item + 1), q2 = __ldg(item + 2), q3 = __ldg(item + 3);
+        const uint32_t t = __float_as_uint(q3.x);
         V4 c[3];
-        c[0] = to_clip(P.mvp, p0.x, p0.y, p0.z);
-        c[1] = to_clip(P.mvp, p1.x, p1.y, p1.z);
-        c[2] = to_clip(P.mvp, p2.x, p2.y, p2.z);
+        c[0].x = q0.x; c[0].y = q0.y; c[0].z = q0.z; c[0].w = q0.w;
+        c[1].x = q1.x; c[1].y = q1.y; c[1].z = q1.z; c[1].w = q1.w;
+        c[2].x = q2.x; c[2].y = q2.y; c[2].z = q2.z; c[2].w = q2.w;
         const uint32_t k0 = clip_code(c[0]), k1 = clip_code(c[1]), k2 = clip_code(c[2]);
         const uint32_t planes = (k0 ^ k1) | (k1 ^ k2) | (k2 ^ k0);           // Clipper.h:119
 

@@ -26,6 +26,7 @@ struct edx_mesh {
     void* staging = nullptr; size_t stagingBytes = 0;     // device-side landing area for the AoS upload
     uint32_t nVerts = 0, nTris = 0, capVerts = 0, capTris = 0;
     bool coherent = false;                                 // triangle order is spatially coherent: cluster culling pays
+    int device = 0;                                        // so the mesh can be released without its context
 };
 
 struct edx_context {
@@ -48,7 +49,7 @@ struct edx_context {
     uchar4* extColor = nullptr; float* extDepth = nullptr;      // caller-owned render targets (optional)
     BigRec* big = nullptr; uint32_t bigCap = 0;
     uint32_t* bigBox = nullptr; uint32_t bigBoxCap = 0;
-    uint32_t* clipQueue = nullptr; uint32_t clipQueueCap = 0;
+    ClipItem* clipQueue = nullptr; uint32_t clipQueueCap = 0;
     ClipRec* clipRecs = nullptr; uint32_t clipRecCap = 0;
     Counters* counters = nullptr;
     Counters* hostCounters = nullptr;        // pinned + device-mapped
@@ -416,6 +417,7 @@ int edx_mesh_create(edx_context* c, const void* vertices, uint32_t nv, const uin
     if (nt > (1u << 29) - 1) return fail(c, EDX_ERR_UNSUPPORTED, "more than 2^29-1 triangles per mesh (prim id = tri*8 + fan)");
     if (int r = bind(c)) return r;
     edx_mesh* m = new edx_mesh;
+    m->device = c->device;
     m->capVerts = std::max(nv, 1u); m->capTris = std::max(nt, 1u);
     cudaError_t e = cudaMalloc(&m->pos4, (size_t)m->capVerts * 16);
     if (e == cudaSuccess) e = cudaMalloc(&m->nrm4, (size_t)m->capVerts * 16);
@@ -470,7 +472,9 @@ int edx_mesh_update(edx_context* c, edx_mesh* m, const void* vertices, uint32_t 
 int edx_mesh_destroy(edx_context* c, edx_mesh* m)
 {
     if (!m) return EDX_OK;
+    // ctx may be NULL (the mesh outlived its context, or the caller cannot tell): fall back to a device-wide wait
     if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->lastMesh == m) { c->lastMesh = nullptr; c->framePending = false; } }
+    else { cudaSetDevice(m->device); cudaDeviceSynchronize(); }
     dev_free(m->pos4); dev_free(m->nrm4); dev_free(m->i0); dev_free(m->i1); dev_free(m->i2); dev_free(m->clipSlot); dev_free(m->clusterBox);
     if (m->staging) cudaFree(m->staging);
     delete m;

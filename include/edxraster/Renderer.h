@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <set>
 #include <tuple>
 #include <cstring>
 #include <memory>
@@ -293,12 +294,13 @@ public:
     const std::vector<uint>& GetTextureIds() const { return mTexIdx; }
     void Release()
     {
-        if (mDevice && mOwner) edx_mesh_destroy(mOwner, mDevice);
+        if (mDevice) ReleaseDevice();
         mDevice = nullptr; mOwner = nullptr;
         mpVertexBuf.reset(); mpIndexBuf.reset(); mTexIdx.clear();
     }
 private:
     friend class Renderer;
+    inline void ReleaseDevice() const;           // defined after Renderer (needs its registry of live contexts)
     std::unique_ptr<IVertexBuffer> mpVertexBuf;
     std::unique_ptr<IndexBuffer> mpIndexBuf;
     std::vector<uint> mTexIdx;
@@ -312,8 +314,10 @@ enum class PixelShaderKind { DepthOnly = EDX_SHADER_DEPTH_ONLY, BlinnPhong = EDX
 // ---- Core/Renderer.h -------------------------------------------------------------------------
 class Renderer {
 public:
-    explicit Renderer(int device = 0) { mStatus = edx_create(device, &mCtx); }
-    ~Renderer() { if (mCtx) edx_destroy(mCtx); }
+    explicit Renderer(int device = 0) { mStatus = edx_create(device, &mCtx); if (mCtx) LiveContexts().insert(mCtx); }
+    // contexts that are still alive, so a Mesh that outlives its Renderer releases its device copy safely
+    static std::set<edx_context*>& LiveContexts() { static std::set<edx_context*> s; return s; }
+    ~Renderer() { if (mCtx) { LiveContexts().erase(mCtx); edx_destroy(mCtx); } }
     Renderer(const Renderer&) = delete;
     Renderer& operator=(const Renderer&) = delete;
 
@@ -327,7 +331,7 @@ public:
     {
         if (!mCtx) return;
         if (!mesh.mDevice || mesh.mOwner != mCtx) {
-            if (mesh.mDevice && mesh.mOwner) edx_mesh_destroy(mesh.mOwner, mesh.mDevice);
+            if (mesh.mDevice) mesh.ReleaseDevice();
             mesh.mDevice = nullptr;
             const IVertexBuffer* vb = mesh.GetVertexBuffer();
             IndexBuffer* ib = mesh.GetIndexBuffer();
@@ -371,5 +375,11 @@ private:
     bool mWriteFrames = false;
     int mFrameCount = 0;
 };
+
+inline void Mesh::ReleaseDevice() const
+{
+    // pass the context only if it is still alive; edx_mesh_destroy(NULL, mesh) does a device-wide wait instead
+    edx_mesh_destroy(Renderer::LiveContexts().count(mOwner) ? mOwner : nullptr, mDevice);
+}
 
 } // namespace edx_b200
