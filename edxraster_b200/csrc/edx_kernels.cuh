@@ -937,22 +937,35 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     cudaGridDependencySynchronize();
     unsigned long long* gkeys = P.keys + (size_t)sId * P.keyStride + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
     if (ms && min(P.counters->nBig, P.bigCap) == 0) return;      // nothing on the tile path: the keys are already final
-    // the tile's keys are wanted on every path: issue the loads before the (dependent) counter read
-    unsigned long long k[8];
+    // the tile's keys are wanted on every path: issue the loads (16 bytes per lane, linear key order) before
+    // the (dependent) counter read
+    ulonglong2* gk2 = reinterpret_cast<ulonglong2*>(gkeys);
+    ulonglong2 kk[4];
     #pragma unroll
-    for (int j = 0; j < 8; j++) k[j] = gkeys[j * 32 + lane];
+    for (int b4 = 0; b4 < 4; b4++) kk[b4] = gk2[b4 * 32 + lane];          // keys b4*64 + 2*lane, +1
     const uint32_t nBig = min(P.counters->nBig, P.bigCap);
+    const ulonglong2 empty2 = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
 
     if (nBig == 0) {
         // Nothing on the tile path: resolve straight from the L2-resident keys, no staging.
         if (tx0 >= P.width || ty0 >= P.height) { frame_done(P); return; }
         #pragma unroll
-        for (int j = 0; j < 8; j++) if (k[j] != KEY_EMPTY) gkeys[j * 32 + lane] = KEY_EMPTY;   // leave the buffer clean for the next frame
+        for (int b4 = 0; b4 < 4; b4++)
+            if (kk[b4].x != KEY_EMPTY || kk[b4].y != KEY_EMPTY) gk2[b4 * 32 + lane] = empty2;   // leave the buffer clean for the next frame
         #pragma unroll 1
-        for (int j = 0; j < 8; j++) {
-            const int q = j >> 1, h = j & 1;
-            const int px = tx0 + (q & 1) * BLOCK_PX + (lane & 7), py = ty0 + (q >> 1) * BLOCK_PX + (lane >> 3) + 4 * h;
-            if (px < P.width && py < P.height) resolve_pixel(P, k[j], px, py);
+        for (int b4 = 0; b4 < 4; b4++) {
+            // keys 2*lane and 2*lane + 1 of block b4 are two horizontally adjacent pixels
+            const int px = tx0 + (b4 & 1) * BLOCK_PX + ((2 * lane) & 7), py = ty0 + (b4 >> 1) * BLOCK_PX + ((2 * lane) >> 3);
+            if (py >= P.height || px >= P.width) continue;
+            if (P.shader == SH_DEPTH_ONLY && !P.captureIds && px + 1 < P.width) {
+                const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);
+                const float d0 = kk[b4].x != KEY_EMPTY ? key_depth(kk[b4].x) : 1.0f, d1 = kk[b4].y != KEY_EMPTY ? key_depth(kk[b4].y) : 1.0f;
+                if ((at & 1) == 0) *reinterpret_cast<float2*>(P.depth + at) = make_float2(d0, d1);
+                else { P.depth[at] = d0; P.depth[at + 1] = d1; }
+            } else {
+                resolve_pixel(P, kk[b4].x, px, py);
+                if (px + 1 < P.width) resolve_pixel(P, kk[b4].y, px + 1, py);
+            }
         }
         frame_done(P);
         return;
@@ -960,11 +973,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
 
     // stage the bin's keys (what the small-triangle path left in L2) and reset them for the next frame
     {
-        unsigned long long* skeys = S.keys + warp * 256;
+        ulonglong2* sk2 = reinterpret_cast<ulonglong2*>(S.keys + warp * 256);
         #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            skeys[j * 32 + lane] = k[j];
-            if (!ms && k[j] != KEY_EMPTY) gkeys[j * 32 + lane] = KEY_EMPTY;
+        for (int b4 = 0; b4 < 4; b4++) {
+            sk2[b4 * 32 + lane] = kk[b4];
+            if (!ms && (kk[b4].x != KEY_EMPTY || kk[b4].y != KEY_EMPTY)) gk2[b4 * 32 + lane] = empty2;
         }
     }
     if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; }
