@@ -76,6 +76,7 @@ struct FrameParams {
     float albedo[3];
     int width, height, binsX, binsY;
     int shader, smallMax, smallMaxClip, hiz, hierarchical, captureIds, dump;
+    int part, parts;         // sort-first split: this context owns the bins b with b % parts == part (parts = 1: all)
     int clusterCull;         // skip whole 256-triangle clusters whose bounding box is outside one clip plane
     int fuseClip;            // clip single-plane straddlers inside geom_kernel instead of queueing them
     int msLevel, samples;    // Renderer::SetMSAAMode (Renderer.cpp:94-98): samples = 1 << msLevel
@@ -295,6 +296,12 @@ __constant__ int c_sampleOffsets[6][64] = {
     { 1, 1, -1, -3, -3, 2, 4, -1, -5, -2, 2, 5, 5, 3, 3, -5, -2, 6, 0, -7, -4, -6, -6, 4, -8, 0, 7, -4, 6, 7, -7, -8,
       1, 3, -3, -3, -3, 0, 6, -2, -7, -1, 3, 4, 7, 3, 3, -6, -2, 7, 0, -4, -2, -5, -7, 6, -8, 3, 4, -1, 2, 7, 4, -8 },
 };
+
+// sort-first split: does this context own the 64x64 bin that holds pixel (x, y)?
+__device__ __forceinline__ bool owns_pixel(int x, int y, int binsX, int part, int parts)
+{
+    return parts == 1 || (uint32_t)((y >> BIN_LOG2) * binsX + (x >> BIN_LOG2)) % (uint32_t)parts == (uint32_t)part;
+}
 
 // pixel-centre range covered by a snapped bounding box: centres sit at 16*i + 8 (Rasterizer.h:23)
 __device__ __forceinline__ int first_centre(int lo) { return (lo + 7) >> 4; }     // ceil((lo - 8) / 16)

@@ -162,6 +162,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                 uint32_t a0 = r0, a1 = r1, a2 = r2;
                 for (int x = x0; x <= x1; x++) {
                     const uint32_t ki = key_index(x, y, P.binsX);
+                    const bool owned = owns_pixel(x, y, P.binsX, P.part, P.parts);
                     for (int sId = 0; sId < P.samples; sId++) {
                         const uint32_t ox = (uint32_t)off[2 * sId], oy = (uint32_t)off[2 * sId + 1];
                         const uint32_t f0 = a0 + ox * e.B0 + oy * e.C0, f1 = a1 + ox * e.B1 + oy * e.C1, f2 = a2 + ox * e.B2 + oy * e.C2;
@@ -169,7 +170,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                             float l0, l1;
                             barycentric((int)(f1 - (uint32_t)e.bias1), (int)(f2 - (uint32_t)e.bias2), s.invDet, l0, l1);
                             const float d = depth_at(l0, l1, z0, z1, z2);
-                            if (d <= 1.0f) atomicMin(P.keys + (size_t)sId * P.keyStride + ki, make_key(d, prim));
+                            if (d <= 1.0f && owned) atomicMin(P.keys + (size_t)sId * P.keyStride + ki, make_key(d, prim));
                         }
                     }
                     a0 += sB0; a1 += sB1; a2 += sB2;
@@ -208,7 +209,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                     float l0, l1;
                     barycentric((int)(base1 + dx * sB1 + dy * sC1), (int)(base2 + dx * sB2 + dy * sC2), s.invDet, l0, l1);
                     const float d = depth_at(l0, l1, z0, z1, z2);
-                    if (d <= 1.0f)
+                    if (d <= 1.0f && owns_pixel(x0 + (int)dx, y0 + (int)dy, P.binsX, P.part, P.parts))
                         atomicMin(P.keys + key_index(x0 + (int)dx, y0 + (int)dy, P.binsX), make_key(d, prim));
                 }
                 return;
@@ -231,7 +232,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                 float l0, l1;
                 barycentric((int)(base1 + dx * sB1 + dy * sC1), (int)(base2 + dx * sB2 + dy * sC2), s.invDet, l0, l1);
                 const float d = depth_at(l0, l1, z0, z1, z2);
-                if (d <= 1.0f)     // depth buffer is cleared to 1.0 and tested LESS_EQUAL (FrameBuffer.cpp:64,103)
+                if (d <= 1.0f && owns_pixel(x0 + (int)dx, y0 + (int)dy, P.binsX, P.part, P.parts))     // depth buffer is cleared to 1.0 and tested LESS_EQUAL (FrameBuffer.cpp:64,103)
                     atomicMin(P.keys + key_index(x0 + (int)dx, y0 + (int)dy, P.binsX), make_key(d, prim));
             }
         } else {
@@ -242,7 +243,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                         float l0, l1;
                         barycentric((int)(a1 - (uint32_t)e.bias1), (int)(a2 - (uint32_t)e.bias2), s.invDet, l0, l1);
                         float d = depth_at(l0, l1, z0, z1, z2);
-                        if (d <= 1.0f)
+                        if (d <= 1.0f && owns_pixel(x, y, P.binsX, P.part, P.parts))
                             atomicMin(P.keys + key_index(x, y, P.binsX), make_key(d, prim));
                     }
                     a0 += sB0; a1 += sB1; a2 += sB2;
@@ -935,6 +936,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     const int ox = (int)bx << BIN_LOG2, oy = (int)by << BIN_LOG2;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
     cudaGridDependencySynchronize();
+    if (P.parts > 1 && (uint32_t)bin % (uint32_t)P.parts != (uint32_t)P.part) {   // sort-first: not this context's bin
+        if (!ms) frame_done(P);
+        return;
+    }
     unsigned long long* gkeys = P.keys + (size_t)sId * P.keyStride + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
     if (ms && min(P.counters->nBig, P.bigCap) == 0) return;      // nothing on the tile path: the keys are already final
     // the tile's keys are wanted on every path: issue the loads (16 bytes per lane, linear key order) before
@@ -987,7 +992,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     uint32_t cursor = 0;                                       // next entry of the tile-path list (uniform)
     while (cursor < nBig) {
         // 1. candidates: a 4-byte bin box per triangle filters the list before any record is loaded
-        while (cursor < nBig && S.candCount <= CAND_CAP - 4 * TILE_THREADS) {     // uniform: read after a barrier
+        for (;;) {
+            // The loop decision must be the same for every thread: read the count, then a barrier, so no
+            // thread can start appending (and change the count) before all threads have read it.
+            const uint32_t have = S.candCount;
+            __syncthreads();
+            if (!(cursor < nBig && have <= CAND_CAP - 4 * TILE_THREADS)) break;
             const uint32_t i = cursor + 4u * tid;
             if (i < nBig) {
                 uint32_t box[4];
@@ -1026,7 +1036,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         // 3. exact reject + depth cull against the bin; survivors go to shared memory and are rasterised
         //    whenever the list fills up
         for (uint32_t base = 0; base < nCand; base += TILE_THREADS) {
-            if (S.survCount > SURV_CAP - TILE_THREADS) {          // uniform: read after a barrier
+            const uint32_t haveSurv = S.survCount;               // same rule: read, barrier, then decide
+            __syncthreads();
+            if (haveSurv > SURV_CAP - TILE_THREADS) {
                 raster_survivors(P, S, ox, oy, hiz, offX, offY);
                 __syncthreads();
                 if (hiz) {
@@ -1101,7 +1113,7 @@ __global__ void __launch_bounds__(256) msaa_resolve_kernel(const __grid_constant
     const uint32_t bin = i >> 12, tile = (i >> 8) & 15u, block = (i >> 6) & 3u, in = i & 63u;
     const int px = (int)((bin % (uint32_t)P.binsX) * BIN + (tile & 3u) * TILE_PX + (block & 1u) * BLOCK_PX + (in & 7u));
     const int py = (int)((bin / (uint32_t)P.binsX) * BIN + (tile >> 2) * TILE_PX + (block >> 1) * BLOCK_PX + (in >> 3));
-    if (i < P.keyStride && px < P.width && py < P.height) {
+    if (i < P.keyStride && px < P.width && py < P.height && owns_pixel(px, py, P.binsX, P.part, P.parts)) {
         const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);
         const size_t plane = (size_t)P.width * P.height;
         float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };

@@ -41,7 +41,7 @@ struct edx_context {
     float eye[3], light[3], albedo[3];
     int shader = EDX_SHADER_BLINN_PHONG;
     int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
-    int smallMax = 32, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1;
+    int smallMax = 32, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1, part = 0, parts = 1;
     bool colorDirty = false;
 
     unsigned long long* keys = nullptr;
@@ -138,6 +138,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.width = (int)c->width; P.height = (int)c->height; P.binsX = (int)c->binsX; P.binsY = (int)c->binsY;
     P.shader = c->shader; P.smallMax = c->smallMax; P.smallMaxClip = c->smallMaxClip; P.hiz = c->hiz; P.hierarchical = c->hierarchical;
     P.captureIds = c->captureIds; P.dump = 0;
+    P.part = c->part; P.parts = c->parts;
     P.fuseClip = c->fuseClip; P.clusterCull = (c->clusterCull == 1 && m->coherent) || c->clusterCull == 2;
     P.msLevel = c->msaaLog2; P.samples = 1 << c->msaaLog2; P.keyStride = c->keyStride;
     const float* Rm = c->raster.m;
@@ -630,6 +631,13 @@ int edx_set_render_target(edx_context* c, void* color, void* depth)
     if ((color || depth) && c->msaaLog2 != 0) return fail(c, EDX_ERR_UNSUPPORTED, "caller-owned render targets are single-sample only");
     c->extColor = (uchar4*)color;
     c->extDepth = (float*)depth;
+    return EDX_OK;
+}
+
+int edx_set_screen_partition(edx_context* c, int part, int parts)
+{
+    if (!c || parts < 1 || parts > 256 || part < 0 || part >= parts) return fail(c, EDX_ERR_INVALID, "need 0 <= part < parts <= 256");
+    c->part = part; c->parts = parts;
     return EDX_OK;
 }
 

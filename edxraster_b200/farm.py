@@ -47,3 +47,23 @@ def render_views(renderer, mesh, views, out_frames, shaded=True):
         renderer.RenderMesh(mesh)
     renderer.Synchronize()
     renderer.SetRenderTarget(0, 0)
+
+
+def bin_owner_mask(width, height, part, parts, bin_px=64, device=None):
+    """Boolean [H, W] mask (frame-buffer order: row 0 = bottom scanline) of the pixels whose 64x64 bin is owned
+    by `part` under edx_set_screen_partition(part, parts)."""
+    bins_x = (width + bin_px - 1) // bin_px
+    y = torch.arange(height, device=device).flip(0)          # raster y of each frame-buffer row
+    x = torch.arange(width, device=device)
+    b = (y[:, None] // bin_px) * bins_x + (x[None, :] // bin_px)
+    return (b % parts) == part
+
+
+def composite_sort_first(frames):
+    """frames: [parts, H, W, ...] full-size buffers, one per partition; returns the assembled frame."""
+    parts, h, w = frames.shape[0], frames.shape[1], frames.shape[2]
+    out = frames[0].clone()
+    for p in range(1, parts):
+        m = bin_owner_mask(w, h, p, parts, device=frames.device)
+        out[m] = frames[p][m]
+    return out

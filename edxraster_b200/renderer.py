@@ -170,6 +170,10 @@ class Renderer:
         """Copy the depth buffer to caller memory (pinned for full PCIe speed); synchronises."""
         self._check(self._lib.edx_read_depth(self._h, C.cast(C.c_void_p(host_ptr), C.POINTER(C.c_float))))
 
+    def SetScreenPartition(self, part, parts):
+        """Sort-first split: own only the 64x64 bins b with b % parts == part."""
+        self._check(self._lib.edx_set_screen_partition(self._h, int(part), int(parts)))
+
     def SetStream(self, cuda_stream_ptr):
         self._check(self._lib.edx_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 

@@ -135,6 +135,10 @@ void* edx_device_depth(edx_context* ctx);
 /* render into caller-owned device buffers (width*height RGBA8 / float32), e.g. torch tensors that
  * an NCCL gather then sends without a copy; NULL restores the context's own buffer. */
 int edx_set_render_target(edx_context* ctx, void* device_color, void* device_depth);
+/* Sort-first split of ONE frame over several contexts / GPUs: this context rasterises, resolves
+ * and writes only the 64x64-pixel bins b (row-major) with b % parts == part; the rest of its frame buffer is left
+ * untouched. Every context still runs the geometry stages on the whole mesh. parts = 1 restores the full frame. */
+int edx_set_screen_partition(edx_context* ctx, int part, int parts);
 /* use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own */
 int edx_set_stream(edx_context* ctx, void* cuda_stream);
 /* CUDA-event timing on the context's stream: begin, N x render, end -> elapsed ms (synchronises) */

@@ -195,3 +195,55 @@ def test_error_behaviour():
     with pytest.raises(EdxError):
         r.SetOption("nonsense", 1)
     r.close()
+
+
+@pytest.mark.parametrize("parts,msaa", [(2, 0), (3, 0), (2, 2)])
+def test_sort_first_split_composites_to_the_full_frame(parts, msaa):
+    # SURVEY.md §8e optional mode: each context owns the bins b % parts == part; together they are the frame
+    import torch
+    from edxraster_b200 import farm, renderer as R
+    sc = scenes.config4(width=640, height=360, quads_x=240, quads_z=192)
+    ref = parity.render_oracle(sc, msaa=msaa)
+    colors, depths = [], []
+    for part in range(parts):
+        r = R.Renderer(0)
+        r.Initialize(sc.width, sc.height)
+        r.SetMSAAMode(msaa)
+        r.SetTransform(sc.mv, sc.proj, sc.raster)
+        r.SetPixelShader(sc.shader)
+        r.SetScreenPartition(part, parts)
+        m = r.CreateMesh(sc.vertices, sc.indices)
+        for _ in range(2):                        # twice: the untouched foreign bins must stay untouched
+            r.RenderMesh(m)
+        colors.append(torch.from_numpy(r.GetBackBuffer().copy()))
+        depths.append(torch.from_numpy(r.GetDepthBuffer()))
+        m.Release()
+        r.close()
+    color = farm.composite_sort_first(torch.stack(colors)).numpy()
+    depth = farm.composite_sort_first(torch.stack(depths)).numpy()
+    np.testing.assert_array_equal(depth.view(np.uint32), ref["depth"].view(np.uint32))
+    assert np.abs(color.astype(np.int32) - ref["color"].astype(np.int32)).max() <= 1
+    # a partition really leaves foreign bins alone (cleared colour there)
+    foreign = ~farm.bin_owner_mask(sc.width, sc.height, 0, parts).numpy()
+    assert (colors[0].numpy()[foreign] == 0).all()
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_tile_path_stress_many_candidates_per_bin(seed):
+    # thousands of large overlapping triangles per 64x64 bin: exercises the candidate / survivor lists filling
+    # up and flushing several times per bin (a barrier-divergence race hid here once: the loop decisions must be
+    # taken from a count read before a barrier)
+    rng = np.random.default_rng(seed)
+    n = 60000
+    c = rng.random((n, 1, 2)) * np.array([512, 384])
+    p = c + (rng.random((n, 3, 2)) - 0.5) * rng.choice([40.0, 120.0, 300.0], size=(n, 1, 1))
+    a, b = p[:, 0] - p[:, 2], p[:, 1] - p[:, 2]
+    flip = (a[:, 0] * b[:, 1] - b[:, 0] * a[:, 1]) < 0
+    p[flip, 0], p[flip, 1] = p[flip, 1].copy(), p[flip, 0].copy()
+    sc = raster_scene(p, 0.05 + 0.9 * rng.random((n, 3)), 512, 384)
+    ref = parity.render_oracle(sc)
+    for opts in ({}, {"hiz": 0}, {"small_max": 4}):
+        got = parity.render_gpu(sc, options=opts, stages=False)
+        rep = parity.compare(ref, got)
+        assert parity.is_parity(rep), (opts, rep)
+        assert got["stats"]["binned_tris"] > 20000
