@@ -66,6 +66,7 @@ struct Counters {
     uint32_t nDump;
     uint32_t done;           // tile_kernel CTAs that have finished (ticket for the end-of-frame hand-off)
     uint32_t pad[3];
+    unsigned long long dbg[8];   // EDX_DEBUG_STATS builds: summed per-CTA cycle counts of the tile kernel's phases
 };
 
 struct FrameParams {

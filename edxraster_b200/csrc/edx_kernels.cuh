@@ -620,7 +620,7 @@ __device__ __forceinline__ uint32_t order_f32(float f)
 // extreme pixel centres instead of the tile corners (so it is exact rather than conservative).
 // With wantZ it also returns conservative bounds of the depth the triangle can produce in the rect.
 __device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0, int size, int W, int H, bool wantZ, bool ms,
-                                              bool& reject, bool& full, float& zmin, float& zmax)
+                                              uint32_t cullU, bool& reject, bool& full, float& zmin, float& zmax)
 {
     reject = true; full = false; zmin = 0.0f; zmax = 0.0f;
     const int rx1 = min(px0 + size - 1, W - 1), ry1 = min(py0 + size - 1, H - 1);
@@ -628,6 +628,25 @@ __device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0,
     const int tx0 = first_pixel(min3i(r.v0x, r.v1x, r.v2x), ms), tx1 = last_pixel(max3i(r.v0x, r.v1x, r.v2x), ms);
     const int ty0 = first_pixel(min3i(r.v0y, r.v1y, r.v2y), ms), ty1 = last_pixel(max3i(r.v0y, r.v1y, r.v2y), ms);
     if (tx0 > rx1 || tx1 < px0 || ty0 > ry1 || ty1 < py0) return;
+    if (wantZ) {
+        // Depth is affine in the pixel position up to fp32 rounding. Bound the stored plane over the rect's
+        // pixel centres, intersect with the vertex range (covered pixels lie inside the triangle), and widen by
+        //   E  = the plane fit's own error bound (perr) + rounding of this evaluation (<= 2.5e-7 of the summed magnitudes)
+        //   Ed = fp32 error of barycentric()/depth_at() at a covered pixel (<= ~1.3e-6 * max|z|)
+        const float half = ms ? 0.5f : 0.0f;          // samples sit up to half a pixel away from the centre
+        const float x0f = (float)px0 - half, x1f = (float)rx1 + half, y0f = (float)py0 - half, y1f = (float)ry1 + half;
+        const float ax0 = r.gx * x0f, ax1 = r.gx * x1f, ay0 = r.gy * y0f, ay1 = r.gy * y1f;
+        const float lo = r.zref + fminf(ax0, ax1) + fminf(ay0, ay1);
+        const float hi = r.zref + fmaxf(ax0, ax1) + fmaxf(ay0, ay1);
+        const float vlo = fminf(r.z0, fminf(r.z1, r.z2)), vhi = fmaxf(r.z0, fmaxf(r.z1, r.z2));
+        const float E = r.perr + 2.5e-7f * (fabsf(r.zref) + fmaxf(fabsf(ax0), fabsf(ax1)) + fmaxf(fabsf(ay0), fabsf(ay1)));
+        const float Ed = 1e-5f * fmaxf(fabsf(vlo), fabsf(vhi)) + 1e-30f;
+        zmin = fmaxf(lo - E, vlo) - Ed;
+        zmax = fminf(hi + E, vhi) + Ed;
+        // Depth cull first: a triangle whose nearest possible depth in the rect is behind the rect's current
+        // upper bound cannot own a pixel there; it is dropped before the (dearer) edge tests.
+        if (order_f32(zmin) > cullU) return;
+    }
     Edges e;
     e.init(r.v0x, r.v0y, r.v1x, r.v1y, r.v2x, r.v2y);
     // 1x: the extreme pixel CENTRES of the rect (exact). MSAA: the extreme sub-pixel positions any sample of
@@ -642,21 +661,6 @@ __device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0,
     reject = false;
     full = e.e0(b0 ? cx0 : cx1, c0 ? cy0 : cy1) >= 0 && e.e1(b1 ? cx0 : cx1, c1 ? cy0 : cy1) >= 0 &&
            e.e2(b2 ? cx0 : cx1, c2 ? cy0 : cy1) >= 0;
-    if (!wantZ) return;
-    // Depth is affine in the pixel position up to fp32 rounding. Bound the stored plane over the rect's
-    // pixel centres, intersect with the vertex range (covered pixels lie inside the triangle), and widen by
-    //   E  = the plane fit's own error bound (perr) + rounding of this evaluation (<= 2.5e-7 of the summed magnitudes)
-    //   Ed = fp32 error of barycentric()/depth_at() at a covered pixel (<= ~1.3e-6 * max|z|)
-    const float half = ms ? 0.5f : 0.0f;          // samples sit up to half a pixel away from the centre
-    const float x0f = (float)px0 - half, x1f = (float)rx1 + half, y0f = (float)py0 - half, y1f = (float)ry1 + half;
-    const float ax0 = r.gx * x0f, ax1 = r.gx * x1f, ay0 = r.gy * y0f, ay1 = r.gy * y1f;
-    const float lo = r.zref + fminf(ax0, ax1) + fminf(ay0, ay1);
-    const float hi = r.zref + fmaxf(ax0, ax1) + fmaxf(ay0, ay1);
-    const float vlo = fminf(r.z0, fminf(r.z1, r.z2)), vhi = fmaxf(r.z0, fmaxf(r.z1, r.z2));
-    const float E = r.perr + 2.5e-7f * (fabsf(r.zref) + fmaxf(fabsf(ax0), fabsf(ax1)) + fmaxf(fabsf(ay0), fabsf(ay1)));
-    const float Ed = 1e-5f * fmaxf(fabsf(vlo), fabsf(vhi)) + 1e-30f;
-    zmin = fmaxf(lo - E, vlo) - Ed;
-    zmax = fminf(hi + E, vhi) + Ed;
 }
 
 // One warp rasterises one triangle into its 16x16 tile: 8x8 block masks by ballot, then pixels.
@@ -674,7 +678,7 @@ __device__ __forceinline__ void raster_tile_tri(unsigned long long (&k)[8], cons
     if (!full && hierarchical) {
         bool rej, acc; float zl, zh;
         const int q = lane & 3;
-        classify_rect(r, tx0 + (q & 1) * BLOCK_PX, ty0 + (q >> 1) * BLOCK_PX, BLOCK_PX, W, H, false, ms, rej, acc, zl, zh);
+        classify_rect(r, tx0 + (q & 1) * BLOCK_PX, ty0 + (q >> 1) * BLOCK_PX, BLOCK_PX, W, H, false, ms, 0xFFFFFFFFu, rej, acc, zl, zh);
         rejMask = __ballot_sync(0xFFFFFFFFu, rej) & 0xFu;
         accMask = __ballot_sync(0xFFFFFFFFu, acc) & 0xFu;
     }
@@ -856,7 +860,7 @@ __device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShare
         uint32_t zlo = 0, zhi = 0xFFFFFFFFu;
         if (j < n) {
             bool rej; float zl, zh;
-            classify_rect(S.surv[j], tx0, ty0, TILE_PX, P.width, P.height, hiz, ms, rej, full, zl, zh);
+            classify_rect(S.surv[j], tx0, ty0, TILE_PX, P.width, P.height, hiz, ms, hiz ? min(U, S.binU) : 0xFFFFFFFFu, rej, full, zl, zh);
             keep = !rej;
             if (hiz) { zlo = order_f32(zl); if (keep && full && zh <= 1.0f) zhi = order_f32(zh); }
             if (!P.hierarchical) full = false;
@@ -914,6 +918,9 @@ __device__ __forceinline__ void frame_done(const FrameParams& P)
     if (atomicAdd(&P.counters->done, 1u) != gridDim.x * gridDim.y - 1u) return;
     volatile Counters* d = P.counters;
     const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump;
+#ifdef EDX_DEBUG_STATS
+    for (int i = 0; i < 8; i++) { P.hostCounters->dbg[i] = P.counters->dbg[i]; P.counters->dbg[i] = 0; }
+#endif
     d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->done = 0;
     volatile Counters* h = P.hostCounters;
     h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump;
@@ -987,6 +994,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     }
     if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; }
     __syncthreads();
+#ifdef EDX_DEBUG_STATS
+    long long tMark = clock64(), tCand = 0, tSweep = 0, tFlush = 0, nFlush = 0, nSurvTot = 0;
+#endif
 
     const bool hizOn = P.hiz && P.hierarchical;
     uint32_t cursor = 0;                                       // next entry of the tile-path list (uniform)
@@ -1015,32 +1025,25 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             cursor += 4u * TILE_THREADS;
             __syncthreads();
         }
+#ifdef EDX_DEBUG_STATS
+        tCand += clock64() - tMark; tMark = clock64();
+#endif
         const uint32_t nCand = S.candCount;
         const bool hiz = hizOn && nCand >= HIZ_MIN_CAND;
-        // 2. hierarchical Z: the bin's depth upper bound = nearest far side of any candidate that covers
-        //    every pixel of the bin
-        if (hiz) {
-            uint32_t u = order_f32(1.0f);
-            for (uint32_t j = tid; j < nCand; j += TILE_THREADS) {
-                BigRec r;
-                load_big(P.big + S.cand[j], r);
-                bool rej, full; float zl, zh;
-                classify_rect(r, ox, oy, BIN, P.width, P.height, true, ms, rej, full, zl, zh);
-                if (!rej && full && zh <= 1.0f) u = min(u, order_f32(zh));
-            }
-            #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) u = min(u, __shfl_xor_sync(0xFFFFFFFFu, u, o));
-            if (lane == 0 && u != order_f32(1.0f)) atomicMin(&S.binU, u);
-            __syncthreads();
-        }
         // 3. exact reject + depth cull against the bin; survivors go to shared memory and are rasterised
         //    whenever the list fills up
         for (uint32_t base = 0; base < nCand; base += TILE_THREADS) {
             const uint32_t haveSurv = S.survCount;               // same rule: read, barrier, then decide
             __syncthreads();
             if (haveSurv > SURV_CAP - TILE_THREADS) {
+#ifdef EDX_DEBUG_STATS
+                long long tF = clock64(); nFlush++; nSurvTot += haveSurv;
+#endif
                 raster_survivors(P, S, ox, oy, hiz, offX, offY);
                 __syncthreads();
+#ifdef EDX_DEBUG_STATS
+                tFlush += clock64() - tF;
+#endif
                 if (hiz) {
                     // what is now stored in the bin bounds everything still to come
                     if (tx0 < P.width && ty0 < P.height) {
@@ -1061,8 +1064,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                 BigRec r;
                 load_big(P.big + S.cand[j], r);
                 bool rej, full; float zl, zh;
-                classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, ms, rej, full, zl, zh);
-                if (!rej && (!hiz || order_f32(zl) <= S.binU)) {
+                // Single progressive pass (hierarchical Z): the bin's depth upper bound S.binU = nearest far side of any
+                // triangle seen so far that covers every pixel of the bin (a racy read of a bound that only shrinks is
+                // conservative); candidates behind it are dropped before their edge tests. Survivors admitted under an
+                // older, looser bound are re-checked against the final bounds tile by tile in raster_survivors.
+                classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, ms, hiz ? S.binU : 0xFFFFFFFFu, rej, full, zl, zh);
+                if (!rej && hiz && full && zh <= 1.0f) atomicMin(&S.binU, order_f32(zh));
+                if (!rej) {
                     const uint32_t at = atomicAdd(&S.survCount, 1u);
                     int4* d2 = reinterpret_cast<int4*>(&S.surv[at]);
                     const int4* s2 = reinterpret_cast<const int4*>(&r);
@@ -1073,8 +1081,25 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         }
         if (tid == 0) S.candCount = 0;
         __syncthreads();
+#ifdef EDX_DEBUG_STATS
+        tSweep += clock64() - tMark; tMark = clock64();
+#endif
     }
+#ifdef EDX_DEBUG_STATS
+    nSurvTot += S.survCount;
+#endif
     raster_survivors(P, S, ox, oy, hizOn && S.survCount >= HIZ_MIN_CAND, offX, offY);
+#ifdef EDX_DEBUG_STATS
+    __syncthreads();
+    if (tid == 0) {
+        const long long tFinal = clock64() - tMark;
+        atomicAdd(&P.counters->dbg[0], (unsigned long long)tCand); atomicAdd(&P.counters->dbg[1], (unsigned long long)(tSweep - tFlush));
+        atomicAdd(&P.counters->dbg[2], (unsigned long long)tFlush); atomicAdd(&P.counters->dbg[3], (unsigned long long)tFinal);
+        atomicAdd(&P.counters->dbg[4], (unsigned long long)nFlush); atomicAdd(&P.counters->dbg[5], (unsigned long long)nSurvTot);
+        atomicAdd(&P.counters->dbg[6], 1ull);
+    }
+    tMark = clock64();
+#endif
     __syncwarp();
 
     if (ms) {
@@ -1094,6 +1119,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             if (px < P.width && py < P.height) resolve_pixel(P, tkeys[q * 64 + lane + 32 * h], px, py);
         }
     }
+#ifdef EDX_DEBUG_STATS
+    __syncthreads();
+    if (tid == 0) atomicAdd(&P.counters->dbg[7], (unsigned long long)(clock64() - tMark));
+#endif
     frame_done(P);
 }
 

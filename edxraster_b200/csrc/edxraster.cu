@@ -213,6 +213,11 @@ int finish_frame(edx_context* c)
         const Counters& k = *c->hostCounters;
         const bool over = k.nBig > c->bigCap || k.nClipQueue > c->clipQueueCap || k.nClipRecs > c->clipRecCap;
         c->stats.binned_tris = k.nBig; c->stats.clipped_tris = k.nClipQueue; c->stats.clip_records = k.nClipRecs;
+#ifdef EDX_DEBUG_STATS
+        if (getenv("EDX_DEBUG_PRINT") && k.dbg[6])
+            fprintf(stderr, "[edx dbg] bins=%llu  mean cycles/bin: cand=%llu sweep=%llu flush=%llu final=%llu resolve=%llu | flushes=%llu survivors=%llu\n",
+                    k.dbg[6], k.dbg[0] / k.dbg[6], k.dbg[1] / k.dbg[6], k.dbg[2] / k.dbg[6], k.dbg[3] / k.dbg[6], k.dbg[7] / k.dbg[6], k.dbg[4], k.dbg[5]);
+#endif
         if (!over) {
             if (c->profiling) {
                 float ms = 0.0f;
