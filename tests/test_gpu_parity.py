@@ -247,3 +247,34 @@ def test_tile_path_stress_many_candidates_per_bin(seed):
         rep = parity.compare(ref, got)
         assert parity.is_parity(rep), (opts, rep)
         assert got["stats"]["binned_tris"] > 20000
+
+
+def _fuzz_scene(seed):
+    """Random soup: mixed sizes from sub-pixel to several screens, random depths incl. behind the camera,
+    random perspective camera, so every clip plane, the w <= 0 drop, both raster paths and HiZ get hit."""
+    from edxraster_b200 import camera as cam
+    rng = np.random.default_rng(seed)
+    w, h = int(rng.choice([160, 256, 322])), int(rng.choice([96, 192, 130]))
+    n = 2500
+    centre = (rng.random((n, 1, 3)) - 0.5) * np.array([6.0, 4.0, 10.0]) + np.array([0.0, 0.0, 3.0])
+    size = rng.choice([0.01, 0.05, 0.3, 2.0, 12.0], size=(n, 1, 1), p=[0.3, 0.3, 0.2, 0.15, 0.05])
+    pos = centre + (rng.random((n, 3, 3)) - 0.5) * size
+    v = np.zeros((n * 3, 8), np.float32)
+    v[:, 0:3] = pos.reshape(-1, 3)
+    v[:, 3:6] = rng.normal(size=(n * 3, 3))
+    v[:, 6:8] = rng.random((n * 3, 2))
+    eye = (rng.random(3) - 0.5) * np.array([2.0, 2.0, 2.0]) + np.array([0.0, 0.0, -2.0])
+    c = cam.Camera(eye, (0.0, 0.0, 3.0), (0.0, 1.0, 0.0), w, h, float(rng.choice([40.0, 65.0, 100.0])),
+                   float(rng.choice([0.05, 0.5, 2.0])), float(rng.choice([6.0, 50.0])))
+    return scenes.Scene(name="fuzz%d" % seed, width=w, height=h, vertices=v,
+                        indices=np.arange(n * 3, dtype=np.uint32).reshape(-1, 3), mv=c.view, proj=c.proj, raster=c.raster,
+                        shader=int(rng.choice([0, 1, 2, 3]))), int(rng.choice([0, 0, 1, 2, 3]))
+
+
+@pytest.mark.parametrize("seed", list(range(100, 116)))
+def test_fuzz_random_scenes(seed):
+    sc, msaa = _fuzz_scene(seed)
+    ref = parity.render_oracle(sc, msaa=msaa)
+    got = parity.render_gpu(sc, msaa=msaa, stages=(msaa == 0))
+    rep = parity.compare(ref, got)
+    assert parity.is_parity(rep), (seed, msaa, rep)
