@@ -9,11 +9,13 @@ only, fixed submission order. One step = one frame of the hot path (Renderer::Re
 /root/reference/EDXRaster/Core/Renderer.cpp:100-118) per GPU. Metric: Mtris/s (submitted triangles per
 second, whole job); Gpix/s and frames/s ride along as extra keys.
 
-Timing: CUDA events on the launching stream around exactly K steps, barrier + synchronize on both
-sides, max over ranks. Inputs are made larger than L2 by rotating over 4 device copies of the mesh
+Timing: CUDA events around exactly K steps, barrier + synchronize on both sides, max over ranks. Each GPU
+keeps --in-flight (3) independent frames in flight: lanes = edx contexts on their own streams sharing the
+meshes; the events sit on a control stream that every lane waits on at the start and that waits on every
+lane at the end. The same loop with one frame in flight is reported next to it (`one_frame_in_flight`). Inputs are made larger than L2 by rotating over 4 device copies of the mesh
 (4 x 108 MB of SoA streams > 126 MB L2), so every frame reads its geometry from HBM. At N > 1 the
 frames are independent (weak scaling: one frame per rank per step) and the finished depth buffers
-are gathered to rank 0 over NCCL in batches of 4 frames, overlapped with the next batch's rendering.
+are gathered to rank 0 over NCCL in batches of 8 frames, overlapped with the next batch's rendering.
 
 Rank 0 prints ONE JSON line on stdout; everything else goes to stderr.
 """
@@ -228,6 +230,19 @@ def secondary_config(name, device, peak):
     meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]
     frames = 30 if sc.num_tris < 5_000_000 else 10
     ms = time_frames(r, meshes, frames, 3) / frames
+    # the same frames through a FrameRing (3 in flight, meshes shared): host wall clock around a synchronised batch
+    ring = R.FrameRing(device, depth=3)
+    ring.Initialize(sc.width, sc.height)
+    ring.SetPixelShader(sc.shader)
+    nring = frames * 4
+    for rep in range(2):
+        ring.Synchronize()
+        tw = time.perf_counter()
+        for i in range(nring):
+            ring.Submit(meshes[i % copies], sc.mv, sc.proj, sc.raster)
+        ring.Synchronize()
+        ms_ring = (time.perf_counter() - tw) * 1e3 / nring
+    ring.close()
     r.SetProfiling(True)
     stage = {"geom": 0.0, "clip": 0.0, "tile": 0.0}
     for i in range(5):
@@ -240,6 +255,7 @@ def secondary_config(name, device, peak):
     st = r.GetStats()
     ab = algorithmic_bytes(sc.num_verts, sc.num_tris, sc.width, sc.height, sc.shader != 0)
     out = {"workload": WORKLOADS[name], "ms_per_frame": ms, "mtris_per_s": sc.num_tris / ms / 1e3,
+           "ms_per_frame_3_in_flight": ms_ring, "mtris_per_s_3_in_flight": sc.num_tris / ms_ring / 1e3,
            "gpix_per_s": sc.width * sc.height / ms / 1e6, "frames_per_s": 1000.0 / ms,
            "algorithmic_bytes": ab, "hbm_frac_whole_frame": ab / (ms * 1e-3) / 1e9 / peak,
            "fb_only_frac": (8 if sc.shader != 0 else 4) * sc.width * sc.height / (ms * 1e-3) / 1e9 / peak,
@@ -278,21 +294,32 @@ def ours_arm(args):
     sc = make_scene(args.workload, args.scale)
     W, H, nt, nv = sc.width, sc.height, sc.num_tris, sc.num_verts
     shaded = sc.shader != 0
+    # `stream` carries the timing events and the NCCL gathers. Frames are rendered by K lanes (edx contexts on
+    # their own streams sharing the meshes): K independent frames in flight per GPU.
     stream = torch.cuda.Stream(device=dev)
-    r = R.Renderer(local)
-    r.SetStream(stream.cuda_stream)
-    r.Initialize(W, H)
-    r.SetTransform(sc.mv, sc.proj, sc.raster)
-    r.SetPixelShader(sc.shader)
+    K = max(1, args.in_flight)
+    lanes = []
+    for _ in range(K):
+        ls = torch.cuda.Stream(device=dev)
+        lr = R.Renderer(local)
+        lr.SetStream(ls.cuda_stream)
+        lr.Initialize(W, H)
+        lr.SetTransform(sc.mv, sc.proj, sc.raster)
+        lr.SetPixelShader(sc.shader)
+        lanes.append((ls, lr))
+    r = lanes[0][1]
     views = sc.get("views")
+    xf = R.PackedTransform(sc.mv, sc.proj, sc.raster)       # marshalled once; edx_set_transform still runs every step
+    if views is not None:
+        views = [R.PackedTransform(*v) for v in views]
     copies = 4 if nv * 32 + nt * 12 < 200e6 else 1          # C4/C5: one 440 MB mesh already exceeds L2
-    meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]
+    meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]    # read-only while rendering: shared by the lanes
 
     # Render targets are torch tensors so NCCL sends them without a copy. Frames are gathered to rank 0 in
     # batches of G (one grouped send/recv per G frames: issuing a collective costs more host time than a 60 us
     # frame takes on the GPU), double-buffered so batch k is on the wire while batch k+1 renders. Every frame
     # still reaches rank 0 inside the timed region.
-    G = 4
+    G = 8
     tgt_color = [torch.zeros((G, H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
     tgt_depth = [torch.zeros((G, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
     result = tgt_color if shaded else tgt_depth
@@ -302,8 +329,11 @@ def ours_arm(args):
     # of it (edx_set_render_target with the peer pointer); one 4-byte all-reduce per batch tells rank 0 the batch
     # has landed. Measured on 4 B200s it is SLOWER than the batched NCCL gather (88 vs 73 us/step): the resolve
     # writes 32-byte row segments, poor NVLink packets. Kept as an option; the default is the NCCL gather.
+    # --gather ce: the batch is pushed into the same symmetric buffer by the COPY ENGINE (one D2D copy over NVLink
+    # per batch, no SM time at all), again followed by the 4-byte all-reduce.
     peer = None
-    if world > 1 and args.peer_stores:
+    mode = "stores" if args.peer_stores else args.gather
+    if world > 1 and mode in ("stores", "ce"):
         try:
             import torch.distributed._symmetric_memory as symm
             sbuf = symm.empty((world, 2, G) + tuple(result[0].shape[1:]), dtype=result[0].dtype, device=dev)
@@ -313,119 +343,168 @@ def ours_arm(args):
         except Exception as e:       # pragma: no cover
             log("symmetric memory unavailable (%s): using NCCL gather" % e)
             peer = None
+    if peer is None and mode != "none":
+        mode = "nccl"
     if world > 1 and rank == 0 and peer is None:
         recv = [[torch.empty_like(result[0]) for _ in range(world)] for _ in range(2)]
 
     def send_batch(b, n, works):
-        if world > 1 and peer is not None:
-            works[b] = dist.all_reduce(flag, async_op=True)       # stream-ordered after this rank's frames of the batch
-        elif world > 1:
-            if n == G:
-                works[b] = dist.gather(result[b], recv[b] if rank == 0 else None, dst=0, async_op=True)
-            else:                                 # last, partial batch of the timed region
-                part = result[b][:n].contiguous()
-                rbuf = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
-                works[b] = dist.gather(part, rbuf, dst=0, async_op=True)
-
-    def step(i, works):
-        b, k = (i // G) & 1, i % G
-        if k == 0 and world > 1 and works[b] is not None:
-            works[b].wait()                       # the gather that still reads buffer b (stream-level wait)
-            works[b] = None
+        """Issue the exchange of batch buffer b on the control stream; works[b] = an event that fires when it is done.
+        Lanes wait on that EVENT before they overwrite buffer b - not on the control stream, which by then has also
+        waited for the next batch's frames (that would drain the frames in flight at every batch boundary)."""
+        if mode == "none" or world == 1:          # "none": diagnosis only, frames stay on their GPU
+            return
         if peer is not None:
+            if mode == "ce":
+                peer[rank, b, :n].copy_(result[b][:n], non_blocking=True)     # cudaMemcpyAsync D2D into rank 0's memory
+            w = dist.all_reduce(flag, async_op=True)              # stream-ordered after this rank's frames of the batch
+        elif n == G:
+            w = dist.gather(result[b], recv[b] if rank == 0 else None, dst=0, async_op=True)
+        else:                                     # last, partial batch of the timed region
+            part = result[b][:n].contiguous()
+            rbuf = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
+            w = dist.gather(part, rbuf, dst=0, async_op=True)
+        w.wait()                                  # stream-level: the control stream continues after the exchange
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        works[b] = ev
+
+    def step(i, works, nl):
+        b, k = (i // G) & 1, i % G
+        ls, lr = lanes[i % nl]
+        if k == 0 and works[b] is not None:
+            for s2, _ in lanes[:nl]:
+                s2.wait_event(works[b])           # the gather that still reads buffer b
+            works[b] = None
+        if mode == "stores":
             dst = peer[rank, b, k].data_ptr()
-            r.SetRenderTarget(dst if shaded else tgt_color[b][k].data_ptr(), tgt_depth[b][k].data_ptr() if shaded else dst)
+            lr.SetRenderTarget(dst if shaded else tgt_color[b][k].data_ptr(), tgt_depth[b][k].data_ptr() if shaded else dst)
         else:
-            r.SetRenderTarget(tgt_color[b][k].data_ptr(), tgt_depth[b][k].data_ptr())
+            lr.SetRenderTarget(tgt_color[b][k].data_ptr(), tgt_depth[b][k].data_ptr())
         if views is not None:
-            r.SetTransform(*views[(i * world + rank) % len(views)])   # C5: view v is rendered by rank v mod N
+            lr.SetTransform(views[(i * world + rank) % len(views)])    # C5: view v is rendered by rank v mod N
         else:
-            r.SetTransform(sc.mv, sc.proj, sc.raster)
-        r.RenderMesh(meshes[i % copies])
-        if k == G - 1:
+            lr.SetTransform(xf)
+        lr.RenderMesh(meshes[i % copies])
+        if k == G - 1 and world > 1:
+            for s2, _ in lanes[:nl]:
+                stream.wait_stream(s2)            # the batch's frames, whichever lane rendered them
             send_batch(b, G, works)
 
-    def flush(n_steps, works):
+    def flush(n_steps, works, nl):
         """gather the frames of a trailing partial batch, then wait for everything in flight"""
-        if n_steps % G:
+        if n_steps % G and world > 1:
+            for s2, _ in lanes[:nl]:
+                stream.wait_stream(s2)
             send_batch((n_steps // G) & 1, n_steps % G, works)
-        for b in (0, 1):
-            if works[b] is not None:
-                works[b].wait()
-                works[b] = None
+        drain(works)
 
     def drain(works):
         for b in (0, 1):
             if works[b] is not None:
-                works[b].wait()
+                works[b].synchronize()
                 works[b] = None
 
-    sampler = ClockSampler(local)
-    with torch.cuda.stream(stream):
+    def sync_lanes():
+        for _, lr in lanes:
+            lr.Synchronize()                      # also vets the internal queues of the frames submitted so far
+
+    def timed_run(nl, steps, n_warm):
+        """n_warm untimed steps, then `steps` timed ones with `nl` frames in flight; returns (ms, t0, t1)"""
         works = [None, None]
-        sampler.start()                           # NVML calls take ~1 ms each: sample through warm-up and the timed region
-        # warm-up: W steps plus a fixed 1000 more so clocks settle (a fixed count: every rank must issue the
-        # same number of gathers)
-        n_warm = ((max(args.warmup, 3) + 1000 + G - 1) // G) * G
         for i in range(n_warm):
-            step(i, works)
+            step(i, works, nl)
             if i % 64 == 63:
                 drain(works)
-                r.Synchronize()
+                sync_lanes()
         drain(works)
-        r.Synchronize()
+        sync_lanes()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record(stream)
-        for i in range(args.steps):
-            step(i, works)
-        flush(args.steps, works)
+        for s2, _ in lanes[:nl]:
+            s2.wait_stream(stream)
+        for i in range(steps):
+            step(i, works, nl)
+        flush(steps, works, nl)
+        for s2, _ in lanes[:nl]:
+            stream.wait_stream(s2)
         ev1.record(stream)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if world > 1:
             dist.barrier()
-        sampler.stop()
-        ms_total = ev0.elapsed_time(ev1)
-        r.Synchronize()                           # vets the internal queues of the last frame
-        launches_per_step = r.LastLaunchCount()
+        ms = ev0.elapsed_time(ev1)
+        sync_lanes()
         if world > 1:
-            t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_total = float(t.item())
+            ms = float(t.item())
+        return ms, t0, t1
+
+    sampler = ClockSampler(local)
+    with torch.cuda.stream(stream):
+        sampler.start()                           # NVML calls take ~1 ms each: sample through warm-up and the timed region
+        # warm-up: W steps plus a fixed 1000 more so clocks settle (a fixed count: every rank must issue the
+        # same number of gathers)
+        n_warm = ((max(args.warmup, 3) + 1000 + G - 1) // G) * G
+        ms_total, t0, t1 = timed_run(K, args.steps, n_warm)
+        sampler.stop()
+        launches_per_step = r.LastLaunchCount()
         ms_step = ms_total / args.steps
         value = world * nt / ms_step / 1e3        # Mtris/s, whole job
+        ms_one = None
+        if K > 1:                                 # the same loop with ONE frame in flight, for the record
+            ms_one = timed_run(1, args.steps, ((max(args.warmup, 3) + G - 1) // G) * G)[0] / args.steps
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         # ---- end-to-end through the C ABI with HOST buffers: upload mesh, render, read result back ----
         hv = torch.from_numpy(np.ascontiguousarray(sc.vertices)).pin_memory()
         hi = torch.from_numpy(np.ascontiguousarray(sc.indices).view(np.int32)).pin_memory()
-        hout = torch.empty((H, W), dtype=torch.float32).pin_memory() if not shaded else None
-        r.SetRenderTarget(0, 0)
+        houts = [torch.empty((H, W), dtype=torch.float32).pin_memory() if not shaded else None for _ in lanes]
+        for _, lr in lanes:
+            lr.SetRenderTarget(0, 0)
+        # streamed geometry is written by its lane's upload: one private mesh per lane (lane 0 reuses a shared one)
+        lane_mesh = [meshes[0]] + [lr.CreateMesh(sc.vertices, sc.indices) for _, lr in lanes[1:]]
         e2e_steps = max(3, min(args.steps, 20 if nt < 5_000_000 else 5))
 
-        def e2e_step(i, upload):
+        def e2e_submit(i, upload):
+            _, lr = lanes[i % K]
             if upload:
-                meshes[i % copies].update(hv.data_ptr(), nv, hi.data_ptr(), nt)
-            r.SetTransform(sc.mv, sc.proj, sc.raster)
-            r.RenderMesh(meshes[i % copies])
+                lane_mesh[i % K].update(hv.data_ptr(), nv, hi.data_ptr(), nt)
+            lr.SetTransform(xf)
+            lr.RenderMesh(lane_mesh[i % K] if upload else meshes[i % copies])
+
+        def e2e_read(i):
+            _, lr = lanes[i % K]
             if shaded:
-                r.GetBackBuffer()                 # D2H into the pinned mirror
+                lr.GetBackBuffer()                # D2H into the lane's pinned mirror
             else:
-                r.ReadDepthInto(hout.data_ptr())
+                lr.ReadDepthInto(houts[i % K].data_ptr())
+
+        def e2e_run(n, upload):
+            """n frames, K in flight: frame i - K + 1 is read back to the host right after frame i is submitted"""
+            for i in range(n + K - 1):
+                if i < n:
+                    e2e_submit(i, upload)
+                if i >= K - 1:
+                    e2e_read(i - K + 1)
 
         e2e = {}
         for label, upload in (("stream", True), ("resident", False)):
-            for i in range(3):
-                e2e_step(i, upload)
+            e2e_run(3, upload)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             ev0.record(stream)
-            for i in range(e2e_steps):
-                e2e_step(i, upload)
+            for s2, _ in lanes:
+                s2.wait_stream(stream)
+            e2e_run(e2e_steps, upload)
+            for s2, _ in lanes:
+                stream.wait_stream(s2)
             ev1.record(stream)
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1)
@@ -473,16 +552,22 @@ def ours_arm(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 depth / i32 28.4 fixed-point coverage", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload], "triangles": nt, "vertices": nv, "resolution": [W, H],
-                   "frames_per_step_per_gpu": 1,
+                   "frames_per_step_per_gpu": 1, "frames_in_flight_per_gpu": K,
+                   "in_flight": "each GPU keeps %d independent frames in flight (contexts on their own streams sharing the meshes); "
+                                "every frame is rendered completely and, at N > 1, gathered inside the timed region" % K,
                    "l2": "inputs larger than L2: round-robin over %d device cop%s of the mesh (%d MB of SoA streams)" % (copies, "ies" if copies > 1 else "y", copies * (nv * 32 + nt * 12) // 1000000),
                    "gather": ("none (1 GPU)" if world == 1 else
-                              ("every finished %s buffer lands on rank 0 by NVLink peer stores from the resolve kernel itself (symmetric memory), one 4-byte all-reduce per 4 frames" if peer is not None else
-                               "NCCL gather of every finished %s buffer to rank 0, per batch of 4 frames, overlapped with the next batch") % ("colour" if shaded else "depth"))},
+                              ("every finished %s buffer lands on rank 0 by NVLink peer stores from the resolve kernel itself (symmetric memory), one 4-byte all-reduce per %d frames" if mode == "stores" else
+                               "every finished %s buffer is pushed into rank 0's symmetric-memory buffer over NVLink by the copy engine (one D2D copy per batch of %d frames, no SM time), then a 4-byte all-reduce" if mode == "ce" else
+                               "NOT GATHERED (--gather none, diagnosis only) %s %d" if mode == "none" else
+                               "NCCL gather of every finished %s buffer to rank 0, per batch of %d frames, overlapped with the next batch") % ("colour" if shaded else "depth", G))},
         "frames_per_s": world * 1000.0 / ms_step, "gpix_per_s": world * W * H / ms_step / 1e6,
+        "one_frame_in_flight": None if ms_one is None else {"ms_per_step": ms_one, "value": world * nt / ms_one / 1e3},
         "clocks": sampler.summary(t0, t1),
         "e2e": {"value": world * nt / e2e["stream"] / 1e3, "unit": "Mtris/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e["stream"],
-                "what": "edx_mesh_update (pinned host vertices+indices -> device) + edx_set_transform + edx_render_mesh + read-back of the frame to pinned host, every step",
+                "what": "edx_mesh_update (pinned host vertices+indices -> device) + edx_set_transform + edx_render_mesh + read-back of the frame to pinned host, every step; "
+                        "%d frames in flight: frame i-%d is read back right after frame i is submitted, the drain is inside the timed region" % (K, K - 1),
                 "resident_mesh_value": world * nt / e2e["resident"] / 1e3, "resident_mesh_ms_per_step": e2e["resident"],
                 "resident_mesh_what": "mesh uploaded once (the reference viewer's usage, Main.cpp:42,71-75); per step: transform in, render, frame read back to host"},
         "gpu_launches": launches_per_step * args.steps,
@@ -494,9 +579,10 @@ def ours_arm(args):
                      "fb_only_frac": (8 if shaded else 4) * W * H / (ms_step * 1e-3) / 1e9 / peak},
         "path_stats": {"binned_tris": stats["binned_tris"], "clipped_tris": stats["clipped_tris"], "regrows": stats["regrow_count"]},
     }
-    for m in meshes:
+    for m in meshes + lane_mesh[1:]:
         m.Release()
-    r.close()
+    for _, lr in lanes:
+        lr.close()
 
     if world == 1:
         # CPU baseline on this box's host cores: bounded sample of the same workload
@@ -534,6 +620,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--gather", default="ce", choices=["nccl", "ce", "stores", "none"], help="how finished frames reach rank 0 at N > 1")
+    ap.add_argument("--in-flight", type=int, default=3, help="independent frames in flight per GPU (1 = one frame at a time)")
     ap.add_argument("--scale", type=float, default=1.0, help="triangle-count scale (debug only; 1.0 = BASELINE size)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary C1/C3/C4 measurements")
     ap.add_argument("--peer-stores", action="store_true", help="N > 1: let every rank's resolve kernel store its pixels straight into rank 0's (symmetric) memory over NVLink instead of the NCCL gather; measured slower (32-byte row segments): 88 vs 73 us/step at N = 4")

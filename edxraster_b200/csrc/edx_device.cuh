@@ -65,6 +65,11 @@ struct Counters {
     uint32_t nClipRecs;      // fan-triangle records written by the clipper
     uint32_t nDump;
     uint32_t done;           // tile_kernel CTAs that have finished (ticket for the end-of-frame hand-off)
+    // Never reset on the device: frames whose queues overflowed, and the largest demand seen. A caller may
+    // submit several frames before the next synchronising call; that call learns from these whether any of
+    // them (not just the last) was incomplete.
+    uint32_t overFrames;
+    uint32_t maxBig, maxClipQueue, maxClipRecs;
     uint32_t pad[3];
     unsigned long long dbg[8];   // EDX_DEBUG_STATS builds: summed per-CTA cycle counts of the tile kernel's phases
 };

@@ -922,8 +922,11 @@ __device__ __forceinline__ void frame_done(const FrameParams& P)
     for (int i = 0; i < 8; i++) { P.hostCounters->dbg[i] = P.counters->dbg[i]; P.counters->dbg[i] = 0; }
 #endif
     d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->done = 0;
+    if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap) d->overFrames = d->overFrames + 1u;
+    d->maxBig = max(d->maxBig, nBig); d->maxClipQueue = max(d->maxClipQueue, nClipQueue); d->maxClipRecs = max(d->maxClipRecs, nClipRecs);
     volatile Counters* h = P.hostCounters;
     h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump;
+    h->overFrames = d->overFrames; h->maxBig = d->maxBig; h->maxClipQueue = d->maxClipQueue; h->maxClipRecs = d->maxClipRecs;
     __threadfence_system();
 }
 

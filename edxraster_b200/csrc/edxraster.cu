@@ -21,7 +21,6 @@ struct edx_mesh {
     float4* pos4 = nullptr;
     float4* nrm4 = nullptr;
     uint32_t* i0 = nullptr; uint32_t* i1 = nullptr; uint32_t* i2 = nullptr;
-    uint32_t* clipSlot = nullptr;
     float4* clusterBox = nullptr;                          // 2 x float4 per 256-triangle cluster
     void* staging = nullptr; size_t stagingBytes = 0;     // device-side landing area for the AoS upload
     uint32_t nVerts = 0, nTris = 0, capVerts = 0, capTris = 0;
@@ -57,6 +56,8 @@ struct edx_context {
     uint8_t* hostColor = nullptr;            // pinned mirror behind GetBackBuffer
     size_t hostColorBytes = 0;
 
+    uint32_t* clipSlot = nullptr; uint32_t clipSlotCap = 0;   // per triangle: first ClipRec of its fan (this frame)
+    uint32_t seenOverFrames = 0;             // Counters::overFrames already accounted for
     const edx_mesh* lastMesh = nullptr;
     bool framePending = false;
     int launches = 0;
@@ -149,7 +150,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.big = c->big; P.bigCap = c->bigCap; P.bigBox = c->bigBox;
     P.clipQueue = c->clipQueue; P.clipQueueCap = c->clipQueueCap;
     P.clipRecs = c->clipRecs; P.clipRecCap = c->clipRecCap;
-    P.clipSlot = m->clipSlot;
+    P.clipSlot = c->clipSlot;
     P.counters = c->counters; P.hostCounters = c->hostCountersDev;
     P.color = c->extColor ? c->extColor : c->color; P.depth = c->extDepth ? c->extDepth : c->depth; P.ids = c->ids;
 }
@@ -162,6 +163,7 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     if (int r = grow(c, c->bigBox, c->bigBoxCap, c->bigCap)) return r;
     if (int r = grow(c, c->clipQueue, c->clipQueueCap, std::max<uint64_t>(1u << 14, m->nTris / 32))) return r;
     if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
+    if (int r = grow(c, c->clipSlot, c->clipSlotCap, m->nTris)) return r;      // in the context, so a mesh is read-only while it renders
 
     FrameParams P;
     fill_params(c, m, P);
@@ -204,13 +206,17 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     return EDX_OK;
 }
 
-// Wait for the pending frame; if a queue overflowed, grow it and run the frame again.
+// Wait for the pending frame; if a queue overflowed, grow it and run the frame again. Frames submitted earlier
+// without a synchronising call in between cannot be run again (their transform and target are gone): if the
+// device counted more overflowed frames than the ones repaired here, the queues are grown to the largest demand
+// seen and the call reports EDX_ERR_OVERFLOW once, so the caller knows those frames are incomplete.
 int finish_frame(edx_context* c)
 {
     EDX_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!c->framePending) return EDX_OK;
+    uint32_t repaired = 0;
     for (int attempt = 0; attempt < 8; attempt++) {
-        const Counters& k = *c->hostCounters;
+        const Counters k = *c->hostCounters;
         const bool over = k.nBig > c->bigCap || k.nClipQueue > c->clipQueueCap || k.nClipRecs > c->clipRecCap;
         c->stats.binned_tris = k.nBig; c->stats.clipped_tris = k.nClipQueue; c->stats.clip_records = k.nClipRecs;
 #ifdef EDX_DEBUG_STATS
@@ -227,8 +233,20 @@ int finish_frame(edx_context* c)
                 cudaEventElapsedTime(&ms, c->evStage[0], c->evStage[3]); c->stats.stage_ms[3] = ms;
             }
             c->framePending = false;
+            const uint32_t lost = k.overFrames - c->seenOverFrames - repaired;
+            c->seenOverFrames = k.overFrames;
+            if (lost) {
+                if (int r = grow(c, c->big, c->bigCap, (uint64_t)k.maxBig + (k.maxClipQueue > c->clipQueueCap ? 7ull * k.maxClipQueue : 0))) return r;
+                if (int r = grow(c, c->bigBox, c->bigBoxCap, c->bigCap)) return r;
+                if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(k.maxClipRecs, 7ull * std::min<uint64_t>(k.maxClipQueue, c->clipQueueCap)))) return r;
+                if (int r = grow(c, c->clipQueue, c->clipQueueCap, k.maxClipQueue)) return r;
+                c->stats.regrow_count++;
+                return fail(c, EDX_ERR_OVERFLOW, std::to_string(lost) + " frame(s) submitted before the last one overflowed the internal queues and are "
+                            "incomplete (no synchronising call followed them, so they could not be re-run); the queues have been grown: render them again");
+            }
             return EDX_OK;
         }
+        repaired++;
         // a clip-queue overflow hides fan triangles, so size the dependent queues generously too
         if (int r = grow(c, c->big, c->bigCap, (uint64_t)k.nBig + (k.nClipQueue > c->clipQueueCap ? 7ull * k.nClipQueue : 0))) return r;
         if (int r = grow(c, c->bigBox, c->bigBoxCap, c->bigCap)) return r;
@@ -309,7 +327,7 @@ void edx_destroy(edx_context* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     release_frame_buffers(c);
-    dev_free(c->big); dev_free(c->bigBox); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->counters);
+    dev_free(c->big); dev_free(c->bigBox); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->clipSlot); dev_free(c->counters);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& e : c->evTimer) if (e) cudaEventDestroy(e);
     for (auto& e : c->evStage) if (e) cudaEventDestroy(e);
@@ -430,7 +448,6 @@ int edx_mesh_create(edx_context* c, const void* vertices, uint32_t nv, const uin
     if (e == cudaSuccess) e = cudaMalloc(&m->i0, (size_t)m->capTris * 4);
     if (e == cudaSuccess) e = cudaMalloc(&m->i1, (size_t)m->capTris * 4);
     if (e == cudaSuccess) e = cudaMalloc(&m->i2, (size_t)m->capTris * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&m->clipSlot, (size_t)m->capTris * 4);
     if (e == cudaSuccess) e = cudaMalloc(&m->clusterBox, (size_t)((m->capTris + 255) / 256) * 32);
     if (e != cudaSuccess) { edx_mesh_destroy(c, m); return fail(c, EDX_ERR_OOM, cudaGetErrorString(e)); }
     if (int r = upload_mesh(c, m, vertices, nv, indices, nt)) { edx_mesh_destroy(c, m); return r; }
@@ -481,7 +498,7 @@ int edx_mesh_destroy(edx_context* c, edx_mesh* m)
     // ctx may be NULL (the mesh outlived its context, or the caller cannot tell): fall back to a device-wide wait
     if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->lastMesh == m) { c->lastMesh = nullptr; c->framePending = false; } }
     else { cudaSetDevice(m->device); cudaDeviceSynchronize(); }
-    dev_free(m->pos4); dev_free(m->nrm4); dev_free(m->i0); dev_free(m->i1); dev_free(m->i2); dev_free(m->clipSlot); dev_free(m->clusterBox);
+    dev_free(m->pos4); dev_free(m->nrm4); dev_free(m->i0); dev_free(m->i1); dev_free(m->i2); dev_free(m->clusterBox);
     if (m->staging) cudaFree(m->staging);
     delete m;
     return EDX_OK;
@@ -491,6 +508,7 @@ int edx_render_mesh(edx_context* c, const edx_mesh* m)
 {
     if (!c || !m) return fail(c, EDX_ERR_INVALID, "null mesh");
     if (!c->initialized) return fail(c, EDX_ERR_INVALID, "Initialize has not been called");
+    if (m->device != c->device) return fail(c, EDX_ERR_INVALID, "the mesh lives on another device");
     if (int r = bind(c)) return r;
     c->lastMesh = m;
     c->stats.submitted_tris = m->nTris;

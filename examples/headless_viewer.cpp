@@ -1,9 +1,12 @@
 // headless_viewer.cpp — the reference's RealtimeViewer (RealtimeViewer/Main.cpp) without the window:
 // same calls in the same order (OnInit :32-62, OnRender :65-75), frames go to a BMP instead of
-// glDrawPixels. Usage: headless_viewer [frames] [out.bmp] [dump.bin] [mesh.obj] [msaa_log2]
+// glDrawPixels. Usage: headless_viewer [frames] [out.bmp] [dump.bin] [mesh.obj] [msaa_log2] [frames_in_flight]
+// With frames_in_flight > 1 the loop keeps that many frames on the GPU (FrameRing) and reads each back in order.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <vector>
 
 #include "../include/edxraster/Renderer.h"
 
@@ -32,7 +35,28 @@ int main(int argc, char** argv)
     if (argc > 5) renderer.SetMSAAMode(std::atoi(argv[5]));                                 // Main.cpp:97
     renderer.SetPixelShader(PixelShaderKind::BlinnPhong);
 
+    const int inFlight = argc > 6 ? std::atoi(argv[6]) : 1;
+    std::vector<_byte> ringFrame;                                  // last frame that came out of the ring
+    bool ringSame = true;
     auto t0 = std::chrono::steady_clock::now();
+    if (inFlight > 1) {
+        FrameRing ring(inFlight);
+        ring.Initialize(W, H);
+        if (argc > 5) ring.SetMSAAMode(std::atoi(argv[5]));
+        ring.SetPixelShader(PixelShaderKind::BlinnPhong);
+        for (int f = 0; f < frames + inFlight - 1; f++) {
+            if (f < frames) ring.Submit(mesh, camera.GetViewMatrix(), camera.GetProjMatrix(), camera.GetRasterMatrix());
+            if (f < inFlight - 1) continue;
+            const _byte* px = ring.GetBackBuffer((size_t)(f - inFlight + 1));
+            if (!px) { std::fprintf(stderr, "frame failed: %s\n", ring.Lane(f - inFlight + 1).LastError()); return 1; }
+            if (!ringFrame.empty() && std::memcmp(ringFrame.data(), px, ringFrame.size()) != 0) ringSame = false;
+            ringFrame.assign(px, px + (size_t)W * H * 4);
+        }
+        double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        std::printf("%.1f frames/s (render + read-back, %d frames in flight)\n", frames / s, inFlight);
+        // show the last frame through the plain renderer path below as well (same image)
+        t0 = std::chrono::steady_clock::now();
+    }
     for (int f = 0; f < frames; f++) {                             // OnRender
         camera.Transform();
         renderer.SetTransform(camera.GetViewMatrix(), camera.GetProjMatrix(), camera.GetRasterMatrix());   // Main.cpp:71
@@ -43,6 +67,12 @@ int main(int argc, char** argv)
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::printf("Image Res: %i, %i\nTriangle Count: %u\n%.1f frames/s (render + read-back)\n", W, H,
                 mesh.GetIndexBuffer()->GetTriangleCount(), frames / s);
+    if (inFlight > 1) {
+        const _byte* px = renderer.GetBackBuffer();
+        ringSame = ringSame && px && std::memcmp(ringFrame.data(), px, ringFrame.size()) == 0;
+        std::printf("ring frames identical to the single-frame path: %s\n", ringSame ? "yes" : "NO");
+        if (!ringSame) return 1;
+    }
     if (!renderer.WriteFrame(out)) { std::fprintf(stderr, "write failed: %s\n", renderer.LastError()); return 1; }
     if (argc > 3) {                                                // raw inputs, so a test can replay them
         FILE* f = std::fopen(argv[3], "wb");

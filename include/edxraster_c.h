@@ -35,7 +35,8 @@ typedef enum edx_status {
     EDX_ERR_INVALID = -1,      /* bad argument */
     EDX_ERR_CUDA = -2,         /* CUDA runtime error, see edx_last_error */
     EDX_ERR_OOM = -3,          /* device or pinned-host allocation failed */
-    EDX_ERR_OVERFLOW = -4,     /* an internal queue could not be grown */
+    EDX_ERR_OVERFLOW = -4,     /* an internal queue could not be grown, or frames submitted before the last one
+                                  (with no synchronising call after them) overflowed and are incomplete */
     EDX_ERR_UNSUPPORTED = -5,  /* feature outside the round's scope (e.g. a resolution beyond the int32 edge range) */
     EDX_ERR_NO_DEVICE = -6     /* no CUDA device / wrong architecture */
 } edx_status;
@@ -93,7 +94,11 @@ int edx_set_albedo(edx_context* ctx, float r, float g, float b);
  * host arrays to the device (SoA streams). tex_ids may be NULL (Mesh::GetTextureIds, Mesh.h:56-59). */
 int edx_mesh_create(edx_context* ctx, const void* vertices_pnt32, uint32_t vertex_count,
                     const uint32_t* indices, uint32_t triangle_count, const uint32_t* tex_ids, edx_mesh** out);
-/* Re-upload into an existing mesh of the same or smaller size (streaming geometry). */
+/* A mesh is read-only while it renders: after edx_mesh_create returns, any context on the same device may
+ * render it, concurrently (several frames in flight on one GPU = several contexts, each on its own stream,
+ * sharing the meshes). */
+/* Re-upload into an existing mesh of the same or smaller size (streaming geometry). Asynchronous on ctx's
+ * stream: contexts other than ctx that share the mesh must not render it until edx_synchronize(ctx). */
 int edx_mesh_update(edx_context* ctx, edx_mesh* mesh, const void* vertices_pnt32, uint32_t vertex_count,
                     const uint32_t* indices, uint32_t triangle_count);
 /* Mesh::Release (Utils/Mesh.cpp:72-78) */
@@ -106,7 +111,10 @@ int edx_render_mesh(edx_context* ctx, const edx_mesh* mesh);
 /* Renderer::GetBackBuffer (Core/Renderer.cpp:360-363): waits for the frame, copies it to a pinned
  * host mirror and returns a borrowed pointer valid until the next RenderMesh / Resize. NULL on error. */
 const uint8_t* edx_get_back_buffer(edx_context* ctx);
-/* wait for all queued work on the context's stream */
+/* Wait for all queued work on the context's stream and vet the frames submitted since the last synchronising
+ * call (edx_synchronize, edx_get_back_buffer, edx_read_*): if the last frame overflowed an internal queue the
+ * queue is grown and the frame rendered again; if an earlier one did, the queues are grown and the call
+ * returns EDX_ERR_OVERFLOW once - those frames must be submitted again. */
 int edx_synchronize(edx_context* ctx);
 
 /* ---- read-backs for parity (ours; the reference keeps depth private, FrameBuffer.h:20) ------ */

@@ -99,3 +99,11 @@ def test_headless_viewer_matches_oracle(tmp_path):
     d = np.abs(pix.astype(np.int32) - ref[..., :3].astype(np.int32))
     assert d.max() <= 1
     assert int((ref[..., 3] == 255).sum()) > 50000           # the sphere really is on screen
+
+
+def test_frame_ring_through_the_cpp_api(tmp_path):
+    # three frames in flight over a shared mesh: every frame equals the single-frame path, which equals the oracle
+    out, bmp, dump = run_viewer(tmp_path, ["", "0", "3"])
+    assert "3 frames in flight" in out.stdout
+    assert "ring frames identical to the single-frame path: yes" in out.stdout
+    compare_with_oracle(bmp, dump)

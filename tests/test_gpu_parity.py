@@ -278,3 +278,76 @@ def test_fuzz_random_scenes(seed):
     got = parity.render_gpu(sc, msaa=msaa, stages=(msaa == 0))
     rep = parity.compare(ref, got)
     assert parity.is_parity(rep), (seed, msaa, rep)
+
+
+# ---- several frames in flight (FrameRing: contexts on their own streams sharing one mesh) ----
+
+def test_frame_ring_frames_in_flight_match_the_oracle():
+    import copy
+    from edxraster_b200 import renderer as R
+    base = scenes.by_name("C4", 0.02)                   # ~100k-triangle terrain, clipped at the screen edges
+    views = scenes.config5_views(base, 7)
+    ring = R.FrameRing(0, depth=3)
+    ring.Initialize(base.width, base.height)
+    ring.SetPixelShader(base.shader)
+    mesh = ring.CreateMesh(base.vertices, base.indices)
+    for lane in ring.lanes:
+        lane.SetCaptureIds(True)
+    refs = []
+    for v in views:
+        sc = copy.copy(base)
+        sc.mv, sc.proj, sc.raster = v
+        refs.append(parity.render_oracle(sc))
+    # keep three frames in flight: read frame i - 2 back after submitting frame i
+    got = {}
+    tickets = []
+    for i, v in enumerate(views):
+        tickets.append(ring.Submit(mesh, *v))
+        if i >= 2:
+            t = tickets[i - 2]
+            lane = ring.lanes[t % 3]
+            got[t] = {"color": ring.GetBackBuffer(t).copy(), "depth": ring.GetDepthBuffer(t), "winner": lane.GetWinnerIds(), "derived": lane.DerivedState()}
+    for t in tickets[-2:]:
+        lane = ring.lanes[t % 3]
+        got[t] = {"color": ring.GetBackBuffer(t).copy(), "depth": ring.GetDepthBuffer(t), "winner": lane.GetWinnerIds(), "derived": lane.DerivedState()}
+    with pytest.raises(ValueError):
+        ring.GetBackBuffer(tickets[0])                  # left the ring long ago
+    for t, ref in zip(tickets, refs):
+        rep = parity.compare(ref, got[t])
+        assert parity.is_parity(rep), (t, rep)
+    assert len({g["depth"].tobytes() for g in got.values()}) == len(views)     # the views really differ
+    mesh.Release()
+    ring.close()
+
+
+def test_overflow_in_an_unsynchronised_earlier_frame_is_reported():
+    # frame A overflows the tile-path queue, frame B (submitted right after, no synchronising call in between)
+    # does not: the next synchronising call must say that a frame was lost, once, and rendering A again works
+    from edxraster_b200 import renderer as R
+    from edxraster_b200._lib import EdxError, EDX_ERR_OVERFLOW
+    rng = np.random.default_rng(5)
+    n = 120000
+    c = rng.random((n, 1, 2)) * np.array([1280, 720])
+    p = c + (rng.random((n, 3, 2)) - 0.5) * 90
+    a, b = p[:, 0] - p[:, 2], p[:, 1] - p[:, 2]
+    flip = (a[:, 0] * b[:, 1] - b[:, 0] * a[:, 1]) < 0
+    p[flip, 0], p[flip, 1] = p[flip, 1].copy(), p[flip, 0].copy()
+    big = raster_scene(p, 0.1 + 0.8 * rng.random((n, 3)), 1280, 720)
+    small = raster_scene(p[:50], 0.1 + 0.8 * rng.random((50, 3)), 1280, 720)
+    r = R.Renderer(0)
+    r.Initialize(1280, 720)
+    r.SetPixelShader(big.shader)
+    r.SetTransform(big.mv, big.proj, big.raster)
+    mb, msm = r.CreateMesh(big.vertices, big.indices), r.CreateMesh(small.vertices, small.indices)
+    r.RenderMesh(mb)
+    r.RenderMesh(msm)
+    with pytest.raises(EdxError) as e:
+        r.Synchronize()
+    assert e.value.code == EDX_ERR_OVERFLOW and "1 frame" in str(e.value)
+    r.Synchronize()                                     # reported once
+    r.RenderMesh(mb)                                    # the queues were grown: this time the frame is complete
+    got = r.GetDepthBuffer()
+    assert r.GetStats()["regrow_count"] == 1
+    ref = parity.render_oracle(big)
+    assert (ref["depth"].view(np.uint32) != got.view(np.uint32)).sum() == 0
+    r.close()
