@@ -295,7 +295,7 @@ def ours_arm(args):
     W, H, nt, nv = sc.width, sc.height, sc.num_tris, sc.num_verts
     shaded = sc.shader != 0
     # `stream` carries the timing events and the NCCL gathers. Frames are rendered by K lanes (edx contexts on
-    # their own streams sharing the meshes): K independent frames in flight per GPU (DESIGN.md section 8).
+    # their own streams sharing the meshes): K independent frames in flight per GPU (DESIGN.md section 7).
     stream = torch.cuda.Stream(device=dev)
     K = max(1, args.in_flight)
     lanes = []
@@ -588,10 +588,13 @@ def ours_arm(args):
         # CPU baseline on this box's host cores: bounded sample of the same workload
         try:
             ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            times, threads, used, _ = cpu_frames(sc, ncpu, 3, 1)
+            probe, threads, used, _ = cpu_frames(sc, ncpu, 1, 1)
+            # bounded sample: about 20 s of CPU work (wall time x threads), 3..40 full frames of the same workload
+            nfr = int(min(40, max(3, round(20.0 / max(probe[0] * threads, 1e-6)))))
+            times, threads, used, _ = cpu_frames(sc, ncpu, nfr, 1)
             v = used * len(times) / sum(times) / 1e6
             line["cpu_baseline"] = {"value": v, "unit": "Mtris/s", "cores": threads, "kind": "port",
-                                    "sample": "3 full frames of the same workload after 1 warm-up (%.2f s each)" % (sum(times) / len(times)),
+                                    "sample": "%d full frames of the same workload after 1 warm-up (%.3f s each, ~%.0f s of CPU work on %d threads)" % (len(times), sum(times) / len(times), sum(times) * threads, threads),
                                     "note": "oracle/ timing build (CPU restatement of the reference SSE path; the reference cannot be built offline)"}
         except Exception as e:       # the oracle is only a reported baseline
             line["cpu_baseline"] = {"value": None, "error": str(e)}

@@ -221,7 +221,7 @@ class FrameRing:
     """Several frames in flight on one GPU. A frame is three dependent kernels of very different shapes (a
     chip-wide geometry pass, a short clipper, one CTA per screen bin); alone they leave most of the B200 idle
     between and inside them, so rendering throughput rises 1.3-3x when 3-4 independent frames overlap
-    (DESIGN.md section 8). A ring is `depth` contexts on their own streams sharing the meshes; Submit() rotates
+    (DESIGN.md section 7). A ring is `depth` contexts on their own streams sharing the meshes; Submit() rotates
     over them and returns a ticket, GetBackBuffer(ticket) / ReadDepthInto(ticket, ptr) waits for that frame only.
     A ticket stays valid until `depth` more frames have been submitted. The reference renders one frame at a
     time (Core/Renderer.cpp:100-118); this is the throughput form of the same call for frame farms."""

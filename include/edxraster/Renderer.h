@@ -385,7 +385,7 @@ private:
 
 // Several frames in flight on one GPU: `depth` Renderers on their own streams that share the meshes. One frame
 // is three dependent kernels of very different shapes and leaves much of a B200 idle; 3-4 overlapping frames
-// raise rendering throughput 1.3-3x (DESIGN.md section 8). Submit() = SetTransform + RenderMesh on the next lane
+// raise rendering throughput 1.3-3x (DESIGN.md section 7). Submit() = SetTransform + RenderMesh on the next lane
 // and returns a ticket; GetBackBuffer(ticket) waits for that frame only. A ticket is valid until `depth` more
 // frames have been submitted. (The reference renders one frame at a time, Core/Renderer.cpp:100-118.)
 class FrameRing {

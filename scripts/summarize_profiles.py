@@ -52,3 +52,29 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "full_*.ncu-rep")))
 open(os.path.join(out, "%s_ncu_summary.md" % tag), "w").write("\n".join(lines) + "\n")
 json.dump(traffic, open(os.path.join(out, "traffic.json"), "w"), indent=1, sort_keys=True)
 print("\n".join(lines[:60]))
+
+# ---- launch list of the bench command itself ----
+bl = os.path.join(ROOT, "gpurun_out", "bench_launches.csv")
+if os.path.exists(bl):
+    rows = [r for r in csv.reader(open(bl)) if len(r) > 10]
+    h = rows[0]
+    ki, vi, si = h.index("Kernel Name"), h.index("Metric Value"), h.index("Stream")
+    md = ["# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-extra` (%s)" % tag, "",
+          "`ncu --metrics gpu__time_duration.sum --clock-control none -s 3030 -c 60 --csv python bench.py --steps 2 --warmup 1 --no-extra`",
+          "(-s 3030 skips the mesh uploads and most of the 1008 warm-up frames; the window covers the end of the warm-up, the two",
+          "timed frames with 3 frames in flight - three lanes = three streams - then the warm-up and the two timed frames of the",
+          "one-frame-in-flight pass and the first end-to-end steps with their mesh re-upload kernels). Times are cold-cache and",
+          "serialised by ncu: compare shares, not absolutes. Every kernel is ours; no library kernel runs in a step.", "",
+          "| # | stream | kernel | ns |", "|---|---|---|---|"]
+    tot = {}
+    for n, r in enumerate(rows[1:]):
+        k = r[ki].split("(")[0]
+        v = float(r[vi].replace(",", ""))
+        md.append("| %d | %s | %s | %.0f |" % (n, r[si], k, v))
+        tot.setdefault(k, []).append(v)
+    md += ["", "| kernel | launches | mean ns | share of the frame kernels |", "|---|---|---|---|"]
+    fsum = sum(sum(v) / len(v) for k, v in tot.items() if k in ("geom_kernel", "clip_kernel", "tile_kernel")) or 1
+    for k, v in tot.items():
+        share = "%.1f %%" % (100 * (sum(v) / len(v)) / fsum) if k in ("geom_kernel", "clip_kernel", "tile_kernel") else ""
+        md.append("| %s | %d | %.0f | %s |" % (k, len(v), sum(v) / len(v), share))
+    open(os.path.join(out, "%s_bench_launches.md" % tag), "w").write("\n".join(md) + "\n")
