@@ -18,6 +18,7 @@ SYMBOLS = [
     "edx_set_capture_ids", "edx_read_winner_ids", "edx_read_sample", "edx_debug_clip_vertices", "edx_debug_raster_triangles",
     "edx_get_derived_state", "edx_device_color", "edx_device_depth", "edx_set_render_target", "edx_set_screen_partition", "edx_set_stream", "edx_timer_begin",
     "edx_timer_end", "edx_set_profiling", "edx_get_stats", "edx_set_option", "edx_last_launch_count",
+    "edx_mesh_set_textures", "edx_mesh_read_texture_level", "edx_debug_tile_residency",
 ]
 
 EDX_OK, EDX_ERR_INVALID, EDX_ERR_CUDA, EDX_ERR_OOM, EDX_ERR_OVERFLOW, EDX_ERR_UNSUPPORTED, EDX_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5, -6
@@ -33,9 +34,13 @@ class EdxError(RuntimeError):
         self.code = code
 
 
+class TextureDesc(C.Structure):         # edx_texture_desc
+    _fields_ = [("kind", C.c_int), ("color", C.c_float * 3), ("rgba8", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("submitted_tris", C.c_uint64), ("clipped_tris", C.c_uint64), ("binned_tris", C.c_uint64),
-                ("clip_records", C.c_uint64), ("regrow_count", C.c_uint32), ("reserved", C.c_uint32),
+                ("clip_records", C.c_uint64), ("regrow_count", C.c_uint32), ("tile_pairs", C.c_uint32),
                 ("stage_ms", C.c_float * 8)]
 
 
@@ -94,5 +99,8 @@ def load():
     lib.edx_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.edx_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     lib.edx_last_launch_count.argtypes = [vp]
+    lib.edx_mesh_set_textures.argtypes = [vp, vp, C.POINTER(TextureDesc), C.c_uint32, vp]
+    lib.edx_debug_tile_residency.argtypes = [vp, C.POINTER(C.c_int)]
+    lib.edx_mesh_read_texture_level.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, u32p, u32p]
     _lib = lib
     return lib

@@ -70,8 +70,18 @@ struct Counters {
     // them (not just the last) was incomplete.
     uint32_t overFrames;
     uint32_t maxBig, maxClipQueue, maxClipRecs;
-    uint32_t pad[3];
+    uint32_t tilePairs;      // (triangle, bin) pairs that survived the bin-level culls this frame: the tile path's load
+    uint32_t pad[2];
     unsigned long long dbg[8];   // EDX_DEBUG_STATS builds: summed per-CTA cycle counts of the tile kernel's phases
+};
+
+// One texture slot of a mesh (Utils/Mesh.h:23; DESIGN.md shims 19-24): a constant colour, or an RGBA8 image with
+// its 2x2 box-filtered mip chain stored level after level in the mesh's texel pool.
+struct TexDesc {
+    uint32_t kind;           // 0 ConstantTexture2D, 1 ImageTexture
+    float r, g, b;           // the constant colour
+    uint32_t w, h, levels, pad;
+    uint32_t off[16];        // first texel of each level in the pool
 };
 
 struct FrameParams {
@@ -94,6 +104,9 @@ struct FrameParams {
     const uint32_t* i0; const uint32_t* i1; const uint32_t* i2;
     const float4* clusterBox;            // per 256-triangle cluster: object-space AABB (min.xyz, max.xyz), built at upload
     uint32_t nTris, nVerts;
+    // Mesh::mTextures / GetTextureIds (Utils/Mesh.h:23,54-59); nTex == 0: the constant `albedo`
+    const TexDesc* tex; const uchar4* texels; const uint32_t* texIds;
+    uint32_t nTex; int texFilter;        // RenderStates::TexFilter (RenderStates.h:23,60)
     // frame state
     unsigned long long* keys;            // 64-bit visibility keys, bin/tile/block-tiled, L2 resident
     BigRec* big; uint32_t bigCap;

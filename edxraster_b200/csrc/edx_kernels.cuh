@@ -623,7 +623,8 @@ __device__ __forceinline__ void classify_rect(const BigRec& r, int px0, int py0,
                                               uint32_t cullU, bool& reject, bool& full, float& zmin, float& zmax)
 {
     reject = true; full = false; zmin = 0.0f; zmax = 0.0f;
-    const int rx1 = min(px0 + size - 1, W - 1), ry1 = min(py0 + size - 1, H - 1);
+    // (W and H used as they are: operands straight from the constant bank, nothing loop-invariant to keep in a register)
+    const int rx1 = min(px0 + size, W) - 1, ry1 = min(py0 + size, H) - 1;
     if (px0 > rx1 || py0 > ry1) return;
     const int tx0 = first_pixel(min3i(r.v0x, r.v1x, r.v2x), ms), tx1 = last_pixel(max3i(r.v0x, r.v1x, r.v2x), ms);
     const int ty0 = first_pixel(min3i(r.v0y, r.v1y, r.v2y), ms), ty1 = last_pixel(max3i(r.v0y, r.v1y, r.v2y), ms);
@@ -714,10 +715,157 @@ __device__ __forceinline__ uint8_t to_u8(float c)       // Color4b::FromFloats (
 
 __device__ __forceinline__ float rsqrt_exact(float x) { return fdiv(1.0f, __fsqrt_rn(x)); }   // DESIGN.md shim 9
 
+// ---------------------------------------------------------------------------------------------
+// Texture2D<Color>::Sample (EDXUtil, absent): DESIGN.md shims 18-24, operation for operation as defined there.
+// Texels are RGBA8; every float operation is a correctly rounded IEEE one except log2f,
+// which only feeds a blend weight (continuous in its error).
+// ---------------------------------------------------------------------------------------------
+struct TexLevelRef { const uchar4* px; int w, h; };
+
+__device__ __forceinline__ TexLevelRef tex_level(const FrameParams& P, const TexDesc* t, int l)
+{
+    TexLevelRef r;
+    r.px = P.texels + __ldg(&t->off[l]);
+    r.w = max(1, (int)(__ldg(&t->w) >> l));
+    r.h = max(1, (int)(__ldg(&t->h) >> l));
+    return r;
+}
+
+__device__ __forceinline__ int tex_wrap(int i, int n) { const int m = i % n; return m < 0 ? m + n : m; }   // shim 20
+
+__device__ __forceinline__ void tex_texel(const TexLevelRef& L, int x, int y, float& r, float& g, float& b)
+{
+    const uchar4 c = __ldg(L.px + (size_t)tex_wrap(y, L.h) * L.w + tex_wrap(x, L.w));
+    const float k = 1.0f / 255.0f;                                                        // shim 18
+    r = fmul((float)c.x, k); g = fmul((float)c.y, k); b = fmul((float)c.z, k);
+}
+
+__device__ __forceinline__ float tex_coord(float u, int n, float bias)
+{
+    const float x = fsub(fmul(u, (float)n), bias);
+    return fabsf(x) < 1.0e9f ? x : 0.0f;
+}
+
+__device__ __noinline__ void tex_bilinear(const TexLevelRef L, float u, float v, float& r, float& g, float& b)    // shim 22
+{
+    const float x = tex_coord(u, L.w, 0.5f), y = tex_coord(v, L.h, 0.5f);
+    const float x0 = floorf(x), y0 = floorf(y);
+    const float fx = fsub(x, x0), fy = fsub(y, y0);
+    const int ix = (int)x0, iy = (int)y0;
+    float r00, g00, b00, r10, g10, b10, r01, g01, b01, r11, g11, b11;
+    tex_texel(L, ix, iy, r00, g00, b00); tex_texel(L, ix + 1, iy, r10, g10, b10);
+    tex_texel(L, ix, iy + 1, r01, g01, b01); tex_texel(L, ix + 1, iy + 1, r11, g11, b11);
+    const float gx = fsub(1.0f, fx), gy = fsub(1.0f, fy);
+    const float w00 = fmul(gx, gy), w10 = fmul(fx, gy), w01 = fmul(gx, fy), w11 = fmul(fx, fy);
+    r = fadd(fadd(fadd(fmul(w00, r00), fmul(w10, r10)), fmul(w01, r01)), fmul(w11, r11));
+    g = fadd(fadd(fadd(fmul(w00, g00), fmul(w10, g10)), fmul(w01, g01)), fmul(w11, g11));
+    b = fadd(fadd(fadd(fmul(w00, b00), fmul(w10, b10)), fmul(w01, b01)), fmul(w11, b11));
+}
+
+__device__ __forceinline__ void tex_trilinear(const FrameParams& P, const TexDesc* t, float u, float v, float width, float& r, float& g, float& b)   // shim 23
+{
+    const int L = (int)__ldg(&t->levels);
+    const float level = fadd((float)(L - 1), log2f(fmaxf(width, 1.0e-8f)));
+    if (!(level >= 0.0f)) { tex_bilinear(tex_level(P, t, 0), u, v, r, g, b); return; }
+    if (level >= (float)(L - 1)) { tex_texel(tex_level(P, t, L - 1), 0, 0, r, g, b); return; }
+    const int i = (int)floorf(level);
+    const float d = fsub(level, (float)i);
+    float r1, g1, b1;
+    tex_bilinear(tex_level(P, t, i), u, v, r, g, b);
+    tex_bilinear(tex_level(P, t, i + 1), u, v, r1, g1, b1);
+    const float e = fsub(1.0f, d);
+    r = fadd(fmul(e, r), fmul(d, r1)); g = fadd(fmul(e, g), fmul(d, g1)); b = fadd(fmul(e, b), fmul(d, b1));
+}
+
+// Shader.h:234-236: one Sample per pixel with the quad's two differentials
+__device__ __forceinline__ void tex_sample(const FrameParams& P, const TexDesc* t, float u, float v, float du0, float dv0, float du1, float dv1,
+                                           float& r, float& g, float& b)
+{
+    if (__ldg(&t->kind) == 0u) { r = __ldg(&t->r); g = __ldg(&t->g); b = __ldg(&t->b); return; }
+    const int filter = P.texFilter;
+    if (filter == 0) {                                                                     // shim 21
+        const TexLevelRef L0 = tex_level(P, t, 0);
+        tex_texel(L0, (int)floorf(tex_coord(u, L0.w, 0.0f)), (int)floorf(tex_coord(v, L0.h, 0.0f)), r, g, b);
+    } else if (filter == 1) {
+        tex_bilinear(tex_level(P, t, 0), u, v, r, g, b);
+    } else if (filter == 2) {
+        const float width = fmul(2.0f, fmaxf(fmaxf(fabsf(du0), fabsf(dv0)), fmaxf(fabsf(du1), fabsf(dv1))));
+        tex_trilinear(P, t, u, v, width, r, g, b);
+    } else {                                                                               // shim 24
+        const int N = filter == 3 ? 4 : (filter == 4 ? 8 : 16);
+        const float l0 = __fsqrt_rn(fadd(fmul(du0, du0), fmul(dv0, dv0))), l1 = __fsqrt_rn(fadd(fmul(du1, du1), fmul(dv1, dv1)));
+        const bool first = l0 >= l1;
+        const float lmaj = first ? l0 : l1, lmin = first ? l1 : l0;
+        const float mu = first ? du0 : du1, mv = first ? dv0 : dv1;
+        int n = 1;
+        if (lmaj > 0.0f) n = (fmul(lmin, (float)N) <= lmaj) ? N : min(N, max(1, (int)ceilf(fdiv(lmaj, lmin))));
+        if (!(lmaj < 3.0e38f)) n = 1;
+        const float width = fmul(2.0f, fdiv(lmaj, (float)n));
+        float ar = 0.0f, ag = 0.0f, ab = 0.0f;
+        for (int i = 0; i < n; i++) {
+            const float s = fsub(fdiv(fadd((float)i, 0.5f), (float)n), 0.5f);
+            float cr, cg, cb;
+            tex_trilinear(P, t, fadd(u, fmul(mu, s)), fadd(v, fmul(mv, s)), width, cr, cg, cb);
+            ar = fadd(ar, cr); ag = fadd(ag, cg); ab = fadd(ab, cb);
+        }
+        const float inv = fdiv(1.0f, (float)n);
+        r = fmul(ar, inv); g = fmul(ag, inv); b = fmul(ab, inv);
+    }
+}
+
+// one mip level from the previous one (shim 19): 2x2 box in float, re-quantised like Color4b::FromFloats
+__global__ void __launch_bounds__(256) mip_kernel(uchar4* __restrict__ pool, uint32_t srcOff, int sw, int sh, uint32_t dstOff, int dw, int dh)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dw * dh) return;
+    const int x = i % dw, y = i / dw;
+    const int x0 = min(2 * x, sw - 1), x1 = min(2 * x + 1, sw - 1), y0 = min(2 * y, sh - 1), y1 = min(2 * y + 1, sh - 1);
+    const uchar4 c00 = pool[srcOff + (size_t)y0 * sw + x0], c10 = pool[srcOff + (size_t)y0 * sw + x1];
+    const uchar4 c01 = pool[srcOff + (size_t)y1 * sw + x0], c11 = pool[srcOff + (size_t)y1 * sw + x1];
+    const float k = 1.0f / 255.0f;
+    auto box = [&](uint8_t a, uint8_t b, uint8_t c, uint8_t d) {
+        return to_u8(fmul(fadd(fadd(fadd(fmul((float)a, k), fmul((float)b, k)), fmul((float)c, k)), fmul((float)d, k)), 0.25f));
+    };
+    pool[dstOff + i] = make_uchar4(box(c00.x, c10.x, c01.x, c11.x), box(c00.y, c10.y, c01.y, c11.y), box(c00.z, c10.z, c01.z, c11.z),
+                                   box(c00.w, c10.w, c01.w, c11.w));
+}
+
+// Shader.h:228-241. The reference shades 2x2 quads (even-aligned, lane k = (x + (k & 1), y + (k >> 1)),
+// Rasterizer.h:23) and takes the texture differentials from lanes 1 and 2 against lane 0, whether or not those
+// pixels are covered: evaluate this triangle's texcoord there with the same arithmetic, then Sample once for
+// this pixel. Not inlined: its registers must not weigh on the untextured shaders.
+struct TexQuad { uint32_t B1, C1, B2, C2; int v2x, v2y; float invDet, iw0, iw1, iw2; float tu[3], tv[3]; };
+
+__device__ __noinline__ float3 albedo_textured(const FrameParams& P, const TexQuad& q, uint32_t tri, int px, int py, float b0, float b1, float b2)
+{
+    auto uv_at = [&](int x, int y, float& u, float& v) {
+        const uint32_t ex = (uint32_t)((x << 4) + 8 - q.v2x), ey = (uint32_t)((y << 4) + 8 - q.v2y);
+        float q0, q1;
+        barycentric((int)(q.B1 * ex + q.C1 * ey), (int)(q.B2 * ex + q.C2 * ey), q.invDet, q0, q1);
+        float q2 = fsub(fsub(1.0f, q0), q1);
+        q0 = fmul(q0, q.iw0); q1 = fmul(q1, q.iw1); q2 = fmul(q2, q.iw2);
+        const float iq = fdiv(1.0f, fadd(fadd(q0, q1), q2));
+        q0 = fmul(q0, iq); q1 = fmul(q1, iq);
+        q2 = fsub(fsub(1.0f, q0), q1);
+        u = blend3(q0, q1, q2, q.tu[0], q.tu[1], q.tu[2]);
+        v = blend3(q0, q1, q2, q.tv[0], q.tv[1], q.tv[2]);
+    };
+    const int qx = px & ~1, qy = py & ~1;
+    float u0, v0, u1, v1, u2, v2;
+    uv_at(qx, qy, u0, v0); uv_at(qx + 1, qy, u1, v1); uv_at(qx, qy + 1, u2, v2);
+    const float uu = blend3(b0, b1, b2, q.tu[0], q.tu[1], q.tu[2]), vv = blend3(b0, b1, b2, q.tv[0], q.tv[1], q.tv[2]);   // Shader.h:167-169
+    uint32_t slot = P.texIds ? __ldg(P.texIds + tri) : 0u;
+    if (slot >= P.nTex) slot = 0u;
+    float3 c;
+    tex_sample(P, P.tex + slot, uu, vv, fsub(u1, u0), fsub(v1, v0), fsub(u2, u0), fsub(v2, v0), c.x, c.y, c.z);
+    return c;
+}
+
 // Stages a15-a17 for one pixel: re-derive the owning triangle from its prim id (visibility-buffer
 // style: nothing per-triangle was stored for small triangles), interpolate perspective-correctly
 // (Shader.h:142-170), shade (Shader.h:185-282) and pack (Renderer.cpp:295-301).
-__device__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int py)
+template <bool TEX>
+__device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim, int px, int py)
 {
     const uint32_t t = prim >> 3, fan = prim & 7u;
     const uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
@@ -728,6 +876,8 @@ __device__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int p
     int v1x, v1y, v2x, v2y, v0y, v0x;
     float invDet, iw0, iw1, iw2;
     float A[3][6];                     // position.xyz, normal.xyz of the three (fan) vertices
+    float TU[3], TV[3];                // their texture coordinates (only the textured shader reads them)
+    const bool textured = TEX;
     if ((clip_code(c0) | clip_code(c1) | clip_code(c2)) == 0) {
         SetupTri s;
         setup_tri(P.raster, P.rasterAffineXY != 0, c0, c1, c2, s);
@@ -736,6 +886,7 @@ __device__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int p
         A[0][0] = p0.x; A[0][1] = p0.y; A[0][2] = p0.z; A[0][3] = n0.x; A[0][4] = n0.y; A[0][5] = n0.z;
         A[1][0] = p1.x; A[1][1] = p1.y; A[1][2] = p1.z; A[1][3] = n1.x; A[1][4] = n1.y; A[1][5] = n1.z;
         A[2][0] = p2.x; A[2][1] = p2.y; A[2][2] = p2.z; A[2][3] = n2.x; A[2][4] = n2.y; A[2][5] = n2.z;
+        TU[0] = n0.w; TU[1] = n1.w; TU[2] = n2.w; TV[0] = p0.w; TV[1] = p1.w; TV[2] = p2.w;
     } else {
         const ClipRec* rp = P.clipRecs + (__ldg(P.clipSlot + t) + fan);
         const int4 w0 = __ldg(reinterpret_cast<const int4*>(rp));
@@ -758,6 +909,11 @@ __device__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int p
                 // Clipper.h:141-146: weight.x*a + weight.y*b + weight.z*c for new vertices
                 float blended = blend3(wt[k][0], wt[k][1], wt[k][2], O[0][m], O[1][m], O[2][m]);
                 A[k][m] = sk == 0 ? O[0][m] : (sk == 1 ? O[1][m] : (sk == 2 ? O[2][m] : blended));
+            }
+            if (textured) {
+                const float bu = blend3(wt[k][0], wt[k][1], wt[k][2], n0.w, n1.w, n2.w), bv = blend3(wt[k][0], wt[k][1], wt[k][2], p0.w, p1.w, p2.w);
+                TU[k] = sk == 0 ? n0.w : (sk == 1 ? n1.w : (sk == 2 ? n2.w : bu));
+                TV[k] = sk == 0 ? p0.w : (sk == 1 ? p1.w : (sk == 2 ? p2.w : bv));
             }
         }
     }
@@ -796,13 +952,49 @@ __device__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int p
         const float spec = fmul(powf(dot3(nx, ny, nz, hx, hy, hz), 200.0f), 3.0f);
         cr = cg = cb = fadd(diffuse, spec);
     } else if (P.shader == SH_LAMBERT_ALBEDO) {
-        cr = fmul(diffuse, P.albedo[0]); cg = fmul(diffuse, P.albedo[1]); cb = fmul(diffuse, P.albedo[2]);
+        float ar = P.albedo[0], ag = P.albedo[1], ab = P.albedo[2];
+        if (textured) {
+            const TexQuad q = { B1, C1, B2, C2, v2x, v2y, invDet, iw0, iw1, iw2, { TU[0], TU[1], TU[2] }, { TV[0], TV[1], TV[2] } };
+            const float3 c = albedo_textured(P, q, t, px, py, b0, b1, b2);
+            ar = c.x; ag = c.y; ab = c.z;
+        }
+        cr = fmul(diffuse, ar); cg = fmul(diffuse, ag); cb = fmul(diffuse, ab);
     }
     return make_uchar4(to_u8(cr), to_u8(cg), to_u8(cb), 255);
 }
 
+// tile_kernel only ever shades untextured (inlined, as before): compiled next to the rasteriser, the textured
+// variant - even as a call - raised that kernel's register pressure and made C3 twice as slow. Textured frames
+// get their colour from textured_resolve_kernel (or msaa_resolve_kernel) instead.
+__device__ __forceinline__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int py) { return shade_impl<false>(P, prim, px, py); }
+
+__device__ __noinline__ uchar4 shade_pixel_textured(const FrameParams& P, uint32_t prim, int px, int py) { return shade_impl<true>(P, prim, px, py); }
+
+__device__ __forceinline__ uchar4 shade_pixel_any(const FrameParams& P, uint32_t prim, int px, int py)
+{
+    if (P.shader == SH_LAMBERT_ALBEDO && P.nTex != 0u) return shade_pixel_textured(P, prim, px, py);
+    return shade_impl<false>(P, prim, px, py);
+}
+
 // ---------------------------------------------------------------------------------------------
 // tile_kernel: stages a7-a11 for large triangles + a13 resolve + a15-a17 for every pixel
+// ---------------------------------------------------------------------------------------------
+// Colour pass of a textured single-sample frame (LambertianAlbedoPixelShader with image textures, Shader.h:209-244):
+// tile_kernel has written depth and the owning prim id of every pixel and left colour alone; one thread per pixel
+// shades its owner here. 8x8-pixel blocks per 64 threads so that a warp's texture footprints stay close.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) textured_resolve_kernel(const __grid_constant__ FrameParams P)
+{
+    cudaGridDependencySynchronize();
+    const uint32_t blocksX = (uint32_t)(P.width + 7) >> 3;
+    const uint32_t blk = blockIdx.x * 4u + (threadIdx.x >> 6), in = threadIdx.x & 63u;
+    const int px = (int)((blk % blocksX) * 8u + (in & 7u)), py = (int)((blk / blocksX) * 8u + (in >> 3));
+    if (px >= P.width || py >= P.height || !owns_pixel(px, py, P.binsX, P.part, P.parts)) return;
+    const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);
+    const uint32_t prim = P.ids[at];
+    P.color[at] = prim != 0xFFFFFFFFu ? shade_pixel_textured(P, prim, px, py) : make_uchar4(0, 0, 0, 0);
+}
+
 // ---------------------------------------------------------------------------------------------
 struct TileShared {
     unsigned long long keys[KEYS_PER_BIN];     // 32 KB: [tile 4x4][block 2x2][8x8]
@@ -841,9 +1033,10 @@ __device__ __forceinline__ uint32_t tile_key_max(const unsigned long long (&k)[8
 // triangle for the tile-level test (exact reject / full cover / hierarchical Z), then the whole warp per
 // surviving triangle. The Z bound tightens as the tile fills: it is the smaller of (a) the far side of
 // any triangle covering the whole tile and (b) the largest depth currently stored in the tile.
+template <bool MS>
 __device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShared& S, int ox, int oy, bool hiz, int offX, int offY)
 {
-    const bool ms = P.samples > 1;
+    const bool ms = MS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
     const int n = (int)S.survCount;
@@ -917,21 +1110,40 @@ __device__ __forceinline__ void frame_done(const FrameParams& P)
     __threadfence();
     if (atomicAdd(&P.counters->done, 1u) != gridDim.x * gridDim.y - 1u) return;
     volatile Counters* d = P.counters;
-    const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump;
+    const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs;
 #ifdef EDX_DEBUG_STATS
     for (int i = 0; i < 8; i++) { P.hostCounters->dbg[i] = P.counters->dbg[i]; P.counters->dbg[i] = 0; }
 #endif
-    d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->done = 0;
+    d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->done = 0; d->tilePairs = 0;
     if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap) d->overFrames = d->overFrames + 1u;
     d->maxBig = max(d->maxBig, nBig); d->maxClipQueue = max(d->maxClipQueue, nClipQueue); d->maxClipRecs = max(d->maxClipRecs, nClipRecs);
     volatile Counters* h = P.hostCounters;
-    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump;
+    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs;
     h->overFrames = d->overFrames; h->maxBig = d->maxBig; h->maxClipQueue = d->maxClipQueue; h->maxClipRecs = d->maxClipRecs;
     __threadfence_system();
 }
 
+#ifdef EDX_DEBUG_STATS
+__device__ uint32_t g_tileResident[512];       // [sm] live tile_kernel CTAs, [256 + sm] the most seen at once
+struct ResidentScope {
+    uint32_t sm;
+    __device__ ResidentScope() {
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        if (threadIdx.x == 0) atomicMax(&g_tileResident[256u + (sm & 255u)], atomicAdd(&g_tileResident[sm & 255u], 1u) + 1u);
+    }
+    __device__ ~ResidentScope() { if (threadIdx.x == 0) atomicSub(&g_tileResident[sm & 255u], 1u); }
+};
+#endif
+
+// MS = false is the single-sample instantiation: sample id and offsets are the constants 0, which keeps them out of
+// registers (the kernel is at its 64-register limit; spilled values made its speed depend on the context's
+// local-memory layout - C3 ran 0.8 or 1.65 ms depending on which other CUDA modules the process had used).
+template <bool MS>
 __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_constant__ FrameParams P)
 {
+#ifdef EDX_DEBUG_STATS
+    ResidentScope residentScope;
+#endif
     extern __shared__ __align__(16) unsigned char smemRaw[];
     TileShared& S = *reinterpret_cast<TileShared*>(smemRaw);
     const int tid = threadIdx.x;
@@ -939,9 +1151,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     const int bin = blockIdx.x;
     // MSAA: blockIdx.y is the sample; each (bin, sample) CTA works on that sample's key plane, evaluates
     // coverage and depth at centre + offset, and leaves the keys in place for msaa_resolve_kernel.
-    const bool ms = P.samples > 1;
-    const int sId = (int)blockIdx.y;
-    const int offX = c_sampleOffsets[P.msLevel][2 * sId], offY = c_sampleOffsets[P.msLevel][2 * sId + 1];
+    const bool ms = MS;
+    const int sId = MS ? (int)blockIdx.y : 0;
+    const int offX = MS ? c_sampleOffsets[P.msLevel][2 * sId] : 0, offY = MS ? c_sampleOffsets[P.msLevel][2 * sId + 1] : 0;
     const uint32_t bx = (uint32_t)(bin % P.binsX), by = (uint32_t)(bin / P.binsX);
     const int ox = (int)bx << BIN_LOG2, oy = (int)by << BIN_LOG2;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
@@ -972,14 +1184,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             // keys 2*lane and 2*lane + 1 of block b4 are two horizontally adjacent pixels
             const int px = tx0 + (b4 & 1) * BLOCK_PX + ((2 * lane) & 7), py = ty0 + (b4 >> 1) * BLOCK_PX + ((2 * lane) >> 3);
             if (py >= P.height || px >= P.width) continue;
+            const ulonglong2 kc = kk[b4];      // (dynamic index: kk[] has a local-memory copy; selecting from registers spills more)
             if (P.shader == SH_DEPTH_ONLY && !P.captureIds && px + 1 < P.width) {
                 const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);
-                const float d0 = kk[b4].x != KEY_EMPTY ? key_depth(kk[b4].x) : 1.0f, d1 = kk[b4].y != KEY_EMPTY ? key_depth(kk[b4].y) : 1.0f;
+                const float d0 = kc.x != KEY_EMPTY ? key_depth(kc.x) : 1.0f, d1 = kc.y != KEY_EMPTY ? key_depth(kc.y) : 1.0f;
                 if ((at & 1) == 0) *reinterpret_cast<float2*>(P.depth + at) = make_float2(d0, d1);
                 else { P.depth[at] = d0; P.depth[at + 1] = d1; }
             } else {
-                resolve_pixel(P, kk[b4].x, px, py);
-                if (px + 1 < P.width) resolve_pixel(P, kk[b4].y, px + 1, py);
+                resolve_pixel(P, kc.x, px, py);
+                if (px + 1 < P.width) resolve_pixel(P, kc.y, px + 1, py);
             }
         }
         frame_done(P);
@@ -1039,10 +1252,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             const uint32_t haveSurv = S.survCount;               // same rule: read, barrier, then decide
             __syncthreads();
             if (haveSurv > SURV_CAP - TILE_THREADS) {
+                if (tid == 0) atomicAdd(&P.counters->tilePairs, haveSurv);
 #ifdef EDX_DEBUG_STATS
                 long long tF = clock64(); nFlush++; nSurvTot += haveSurv;
 #endif
-                raster_survivors(P, S, ox, oy, hiz, offX, offY);
+                raster_survivors<MS>(P, S, ox, oy, hiz, offX, offY);
                 __syncthreads();
 #ifdef EDX_DEBUG_STATS
                 tFlush += clock64() - tF;
@@ -1091,7 +1305,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
 #ifdef EDX_DEBUG_STATS
     nSurvTot += S.survCount;
 #endif
-    raster_survivors(P, S, ox, oy, hizOn && S.survCount >= HIZ_MIN_CAND, offX, offY);
+    if (tid == 0) atomicAdd(&P.counters->tilePairs, S.survCount);      // load of the tile path, for the host's tuning
+    raster_survivors<MS>(P, S, ox, oy, hizOn && S.survCount >= HIZ_MIN_CAND, offX, offY);
 #ifdef EDX_DEBUG_STATS
     __syncthreads();
     if (tid == 0) {
@@ -1160,7 +1375,7 @@ __global__ void __launch_bounds__(256) msaa_resolve_kernel(const __grid_constant
             if (P.captureIds) P.ids[sId * plane + at] = hit ? key_prim(key) : 0xFFFFFFFFu;
             if (hit && P.shader != SH_DEPTH_ONLY) {
                 const uint32_t prim = key_prim(key);
-                if (prim != lastPrim) { lastColor = shade_pixel(P, prim, px, py); lastPrim = prim; }
+                if (prim != lastPrim) { lastColor = shade_pixel_any(P, prim, px, py); lastPrim = prim; }
                 acc[0] = fadd(acc[0], fmul((float)lastColor.x, 1.0f / 255.0f));
                 acc[1] = fadd(acc[1], fmul((float)lastColor.y, 1.0f / 255.0f));
                 acc[2] = fadd(acc[2], fmul((float)lastColor.z, 1.0f / 255.0f));
@@ -1174,5 +1389,28 @@ __global__ void __launch_bounds__(256) msaa_resolve_kernel(const __grid_constant
     }
     frame_done(P);
 }
+
+
+// Diagnostic: how many CTAs of tile_kernel's shape (512 threads, sizeof(TileShared) dynamic shared memory) does an SM
+// really hold at once? perSm[sm] = live CTAs, perSm[256 + sm] = the most seen.
+__global__ void __launch_bounds__(TILE_THREADS, 2) residency_kernel(uint32_t* perSm)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    if (threadIdx.x == 0) {
+        uint32_t sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        const uint32_t now = atomicAdd(&perSm[sm & 255u], 1u) + 1u;
+        atomicMax(&perSm[256u + (sm & 255u)], now);
+        unsigned long long g0, g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+        const long long t0 = clock64();
+        while (clock64() - t0 < 100000) { }
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        perSm[512] = (uint32_t)(g1 - g0);                   // ns that 100,000 SM cycles took
+        atomicSub(&perSm[sm & 255u], 1u);
+        smemRaw[0] = 1;
+    }
+}
+
 
 } // namespace edx

@@ -21,6 +21,8 @@ struct edx_mesh {
     float4* pos4 = nullptr;
     float4* nrm4 = nullptr;
     uint32_t* i0 = nullptr; uint32_t* i1 = nullptr; uint32_t* i2 = nullptr;
+    // Mesh::mTextures + per-triangle slot (Utils/Mesh.h:23,54-59); nTex == 0: the context's constant albedo
+    TexDesc* texDesc = nullptr; uchar4* texels = nullptr; uint32_t* texIds = nullptr; uint32_t nTex = 0;
     float4* clusterBox = nullptr;                          // 2 x float4 per 256-triangle cluster
     void* staging = nullptr; size_t stagingBytes = 0;     // device-side landing area for the AoS upload
     uint32_t nVerts = 0, nTris = 0, capVerts = 0, capTris = 0;
@@ -41,6 +43,7 @@ struct edx_context {
     int shader = EDX_SHADER_BLINN_PHONG;
     int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
     int smallMax = 32, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1, part = 0, parts = 1;
+    int clipCarveout = 0;                    // 0 auto (follow the tile path's load), 1 prefer L1, 2 prefer shared memory
     bool colorDirty = false;
 
     unsigned long long* keys = nullptr;
@@ -146,6 +149,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.rasterAffineXY = (Rm[2] == 0.0f && Rm[6] == 0.0f && Rm[12] == 0.0f && Rm[13] == 0.0f && Rm[14] == 0.0f && Rm[15] == 1.0f) ? 1 : 0;
     P.pos4 = m->pos4; P.nrm4 = m->nrm4; P.i0 = m->i0; P.i1 = m->i1; P.i2 = m->i2; P.clusterBox = m->clusterBox;
     P.nTris = m->nTris; P.nVerts = m->nVerts;
+    P.tex = m->texDesc; P.texels = m->texels; P.texIds = m->texIds; P.nTex = m->nTex; P.texFilter = c->texFilter;
     P.keys = c->keys;
     P.big = c->big; P.bigCap = c->bigCap; P.bigBox = c->bigBox;
     P.clipQueue = c->clipQueue; P.clipQueueCap = c->clipQueueCap;
@@ -194,16 +198,43 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[1], c->stream));
     if (m->nTris) EDX_CUDA(c, launch(clip_kernel, dim3(148 * 4), dim3(128), 0));
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[2], c->stream));
-    if (c->msaaLog2 == 0) {
-        EDX_CUDA(c, launch(tile_kernel, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
+    const bool textured = c->shader == EDX_SHADER_LAMBERT_ALBEDO && m->nTex != 0;
+    if (c->msaaLog2 == 0 && textured) {
+        // tile_kernel resolves depth + owner ids only; the colour pass is a kernel of its own (see its comment)
+        FrameParams T = P;
+        T.shader = EDX_SHADER_DEPTH_ONLY; T.captureIds = 1;
+        std::swap(P, T);
+        EDX_CUDA(c, launch(tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
+        std::swap(P, T);
+        const uint32_t blocks = ((c->width + 7) / 8) * ((c->height + 7) / 8);
+        EDX_CUDA(c, launch(textured_resolve_kernel, dim3((blocks + 3) / 4), dim3(256), 0));
+    } else if (c->msaaLog2 == 0) {
+        EDX_CUDA(c, launch(tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
     } else {
         // one CTA per (bin, sample), then the per-pixel resolve that also ends the frame
-        EDX_CUDA(c, launch(tile_kernel, dim3(c->binsX * c->binsY, 1u << c->msaaLog2), dim3(TILE_THREADS), sizeof(TileShared)));
+        EDX_CUDA(c, launch(tile_kernel<true>, dim3(c->binsX * c->binsY, 1u << c->msaaLog2), dim3(TILE_THREADS), sizeof(TileShared)));
         EDX_CUDA(c, launch(msaa_resolve_kernel, dim3((c->keyStride + 255) / 256), dim3(256), 0));
     }
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[3], c->stream));
     EDX_CUDA(c, cudaGetLastError());
     return EDX_OK;
+}
+
+// Which shared-memory carve-out clip_kernel asks for. Measured on B200 ("carve-out"): when the
+// clipper runs with the default (large L1) configuration, the tile kernel that follows it takes up to 2x longer on
+// frames dominated by the tile path (C3: 0.80 -> 1.65 ms in a process that uses no other CUDA module); when it asks
+// for the max-shared configuration the tile kernel always runs at full speed (0.70 ms) but the clipper itself, whose
+// polygons live in local memory, slows down (C2 +12 us, C4 +16 us per frame). The mechanism is not understood (CTA
+// residency, clocks and per-CTA cycle counts are identical in both states). So: follow the load of the tile path
+// seen in the last vetted frame. Purely a speed knob - results never depend on it.
+void tune_clip_carveout(edx_context* c, uint32_t tilePairs)
+{
+    static int current = -1;                                   // function attributes are per process
+    int want = c->clipCarveout == 0 ? (tilePairs > 100000u ? 2 : 1) : c->clipCarveout;
+    if (want == current) return;
+    cudaFuncSetAttribute(clip_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         want == 2 ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
+    current = want;
 }
 
 // Wait for the pending frame; if a queue overflowed, grow it and run the frame again. Frames submitted earlier
@@ -219,7 +250,18 @@ int finish_frame(edx_context* c)
         const Counters k = *c->hostCounters;
         const bool over = k.nBig > c->bigCap || k.nClipQueue > c->clipQueueCap || k.nClipRecs > c->clipRecCap;
         c->stats.binned_tris = k.nBig; c->stats.clipped_tris = k.nClipQueue; c->stats.clip_records = k.nClipRecs;
+        c->stats.tile_pairs = k.tilePairs;
 #ifdef EDX_DEBUG_STATS
+        if (getenv("EDX_DEBUG_PRINT")) {
+            uint32_t h[512];
+            if (cudaMemcpyFromSymbol(h, g_tileResident, sizeof(h)) == cudaSuccess) {
+                int hist[4] = { 0, 0, 0, 0 };
+                for (int i = 0; i < 256; i++) hist[std::min(3u, h[256 + i])]++;
+                fprintf(stderr, "[edx dbg] tile_kernel CTAs resident per SM (max seen): %d SMs x1, %d SMs x2, %d SMs x3+\n", hist[1], hist[2], hist[3]);
+                memset(h, 0, sizeof(h));
+                cudaMemcpyToSymbol(g_tileResident, h, sizeof(h));
+            }
+        }
         if (getenv("EDX_DEBUG_PRINT") && k.dbg[6])
             fprintf(stderr, "[edx dbg] bins=%llu  mean cycles/bin: cand=%llu sweep=%llu flush=%llu final=%llu resolve=%llu | flushes=%llu survivors=%llu\n",
                     k.dbg[6], k.dbg[0] / k.dbg[6], k.dbg[1] / k.dbg[6], k.dbg[2] / k.dbg[6], k.dbg[3] / k.dbg[6], k.dbg[7] / k.dbg[6], k.dbg[4], k.dbg[5]);
@@ -233,6 +275,7 @@ int finish_frame(edx_context* c)
                 cudaEventElapsedTime(&ms, c->evStage[0], c->evStage[3]); c->stats.stage_ms[3] = ms;
             }
             c->framePending = false;
+            tune_clip_carveout(c, k.tilePairs);
             const uint32_t lost = k.overFrames - c->seenOverFrames - repaired;
             c->seenOverFrames = k.overFrames;
             if (lost) {
@@ -312,7 +355,13 @@ int edx_create(int device, edx_context** out)
               cudaHostAlloc(&c->hostCounters, sizeof(Counters), cudaHostAllocMapped) == cudaSuccess &&
               cudaHostGetDevicePointer((void**)&c->hostCountersDev, c->hostCounters, 0) == cudaSuccess &&
               cudaMemset(c->counters, 0, sizeof(Counters)) == cudaSuccess &&
-              cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess;
+              cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
+              cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
+              // Two 97 KB CTAs per SM need the 196 KB shared-memory carve-out. Left to the driver's default heuristic a
+              // fresh process got a smaller one (one CTA per SM: C3 took 1.65 ms instead of 0.80 ms) until some other
+              // module's kernel had run; ask for it explicitly.
+              cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+              cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
     for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&c->evTimer[i]) == cudaSuccess;
     for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&c->evStage[i]) == cudaSuccess;
     if (!ok) { edx_destroy(c); return EDX_ERR_CUDA; }
@@ -430,13 +479,13 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }
+    if (!strcmp(name, "clip_carveout")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "clip_carveout: 0 auto, 1 L1, 2 shared"); c->clipCarveout = value; tune_clip_carveout(c, c->stats.tile_pairs); return EDX_OK; }
     return fail(c, EDX_ERR_INVALID, std::string("unknown option ") + name);
 }
 
 int edx_mesh_create(edx_context* c, const void* vertices, uint32_t nv, const uint32_t* indices, uint32_t nt,
                     const uint32_t* tex_ids, edx_mesh** out)
 {
-    (void)tex_ids;      // texture slots feed only the textured shader
     if (!c || !out || (nv && !vertices) || (nt && !indices)) return fail(c, EDX_ERR_INVALID, "null buffer");
     if (nt > (1u << 29) - 1) return fail(c, EDX_ERR_UNSUPPORTED, "more than 2^29-1 triangles per mesh (prim id = tri*8 + fan)");
     if (int r = bind(c)) return r;
@@ -451,6 +500,13 @@ int edx_mesh_create(edx_context* c, const void* vertices, uint32_t nv, const uin
     if (e == cudaSuccess) e = cudaMalloc(&m->clusterBox, (size_t)((m->capTris + 255) / 256) * 32);
     if (e != cudaSuccess) { edx_mesh_destroy(c, m); return fail(c, EDX_ERR_OOM, cudaGetErrorString(e)); }
     if (int r = upload_mesh(c, m, vertices, nv, indices, nt)) { edx_mesh_destroy(c, m); return r; }
+    if (tex_ids && nt) {                 // Mesh::GetTextureIds (Mesh.h:58): kept until edx_mesh_set_textures passes its own
+        if (cudaMalloc(&m->texIds, (size_t)nt * 4) != cudaSuccess ||
+            cudaMemcpyAsync(m->texIds, tex_ids, (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+            edx_mesh_destroy(c, m);
+            return fail(c, EDX_ERR_OOM, "texture id upload failed");
+        }
+    }
     // copy semantics of CreateVertexBuffer / CreateIndexBuffer: the caller's arrays are free on return
     if (cudaStreamSynchronize(c->stream) != cudaSuccess) { edx_mesh_destroy(c, m); return fail(c, EDX_ERR_CUDA, "mesh upload failed"); }
     // Is the triangle order spatially coherent? Cluster culling (geom_kernel prologue) only pays when a
@@ -492,13 +548,93 @@ int edx_mesh_update(edx_context* c, edx_mesh* m, const void* vertices, uint32_t 
     return upload_mesh(c, m, vertices, nv, indices, nt);
 }
 
+int edx_mesh_set_textures(edx_context* c, edx_mesh* m, const edx_texture_desc* textures, uint32_t count, const uint32_t* tri_tex_ids)
+{
+    if (!c || !m || (count && !textures)) return fail(c, EDX_ERR_INVALID, "null argument");
+    if (count > 4096) return fail(c, EDX_ERR_UNSUPPORTED, "more than 4096 texture slots");
+    if (int r = bind(c)) return r;
+    std::vector<TexDesc> descs(count);
+    size_t total = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        const edx_texture_desc& t = textures[i];
+        TexDesc& d = descs[i];
+        memset(&d, 0, sizeof(d));
+        if (t.kind == EDX_TEXTURE_CONSTANT) {
+            d.kind = 0; d.r = t.color[0]; d.g = t.color[1]; d.b = t.color[2];
+        } else if (t.kind == EDX_TEXTURE_IMAGE) {
+            if (!t.rgba8 || t.width == 0 || t.height == 0 || t.width > 32768 || t.height > 32768)
+                return fail(c, EDX_ERR_INVALID, "image texture needs pixels and 1..32768 texels per side");
+            d.kind = 1; d.w = t.width; d.h = t.height;
+            uint32_t w = t.width, h = t.height;
+            for (;;) {                                              // shim 19: halve (floor, min 1) down to 1x1
+                if (total + (size_t)w * h > 0xFFFFFFF0ull) return fail(c, EDX_ERR_UNSUPPORTED, "texel pool would exceed 2^32 texels");
+                d.off[d.levels++] = (uint32_t)total;
+                total += (size_t)w * h;
+                if (w == 1 && h == 1) break;
+                w = std::max(1u, w >> 1); h = std::max(1u, h >> 1);
+            }
+        } else {
+            return fail(c, EDX_ERR_INVALID, "unknown texture kind");
+        }
+    }
+    if (tri_tex_ids)
+        for (uint32_t i = 0; i < m->nTris; i++)
+            if (tri_tex_ids[i] >= std::max(count, 1u)) return fail(c, EDX_ERR_INVALID, "texture id out of range");
+    // the mesh may be rendering (shared, frames in flight): wait for the device before replacing its tables
+    EDX_CUDA(c, cudaDeviceSynchronize());
+    dev_free(m->texDesc); dev_free(m->texels);
+    if (tri_tex_ids) dev_free(m->texIds);
+    m->nTex = 0;
+    if (count == 0) return EDX_OK;
+    EDX_CUDA(c, cudaMalloc(&m->texDesc, count * sizeof(TexDesc)));
+    EDX_CUDA(c, cudaMalloc(&m->texels, std::max<size_t>(total, 1) * sizeof(uchar4)));
+    EDX_CUDA(c, cudaMemcpyAsync(m->texDesc, descs.data(), count * sizeof(TexDesc), cudaMemcpyHostToDevice, c->stream));
+    for (uint32_t i = 0; i < count; i++) {
+        const TexDesc& d = descs[i];
+        if (d.kind != 1) continue;
+        EDX_CUDA(c, cudaMemcpyAsync(m->texels + d.off[0], textures[i].rgba8, (size_t)d.w * d.h * 4, cudaMemcpyHostToDevice, c->stream));
+        uint32_t w = d.w, h = d.h;
+        for (uint32_t l = 1; l < d.levels; l++) {
+            const uint32_t dw = std::max(1u, w >> 1), dh = std::max(1u, h >> 1);
+            mip_kernel<<<(dw * dh + 255) / 256, 256, 0, c->stream>>>(m->texels, d.off[l - 1], (int)w, (int)h, d.off[l], (int)dw, (int)dh);
+            w = dw; h = dh;
+        }
+    }
+    if (tri_tex_ids && m->nTris) {
+        EDX_CUDA(c, cudaMalloc(&m->texIds, (size_t)m->nTris * 4));
+        EDX_CUDA(c, cudaMemcpyAsync(m->texIds, tri_tex_ids, (size_t)m->nTris * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    EDX_CUDA(c, cudaGetLastError());
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));        // copy semantics: the caller's arrays are free on return
+    m->nTex = count;
+    return EDX_OK;
+}
+
+int edx_mesh_read_texture_level(edx_context* c, const edx_mesh* m, uint32_t slot, uint32_t level, uint8_t* out_rgba8, uint32_t* out_w, uint32_t* out_h)
+{
+    if (!c || !m || slot >= m->nTex) return fail(c, EDX_ERR_INVALID, "no such texture slot");
+    if (int r = bind(c)) return r;
+    TexDesc d;
+    EDX_CUDA(c, cudaMemcpy(&d, m->texDesc + slot, sizeof(d), cudaMemcpyDeviceToHost));
+    if (d.kind != 1 || level >= d.levels) return fail(c, EDX_ERR_INVALID, "no such mip level");
+    const uint32_t w = std::max(1u, d.w >> level), h = std::max(1u, d.h >> level);
+    if (out_w) *out_w = w;
+    if (out_h) *out_h = h;
+    if (out_rgba8) EDX_CUDA(c, cudaMemcpy(out_rgba8, m->texels + d.off[level], (size_t)w * h * 4, cudaMemcpyDeviceToHost));
+    return EDX_OK;
+}
+
 int edx_mesh_destroy(edx_context* c, edx_mesh* m)
 {
     if (!m) return EDX_OK;
-    // ctx may be NULL (the mesh outlived its context, or the caller cannot tell): fall back to a device-wide wait
-    if (c) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); if (c->lastMesh == m) { c->lastMesh = nullptr; c->framePending = false; } }
-    else { cudaSetDevice(m->device); cudaDeviceSynchronize(); }
+    // A mesh may be shared by several contexts of its device (frames in flight), and ctx may be NULL (the mesh
+    // outlived its context): wait for the whole device. Contexts other than ctx that rendered it last must be
+    // synchronised by the caller first (their overflow re-run would need the mesh).
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    if (c && c->lastMesh == m) { c->lastMesh = nullptr; c->framePending = false; }
     dev_free(m->pos4); dev_free(m->nrm4); dev_free(m->i0); dev_free(m->i1); dev_free(m->i2); dev_free(m->clusterBox);
+    dev_free(m->texDesc); dev_free(m->texels); dev_free(m->texIds);
     if (m->staging) cudaFree(m->staging);
     delete m;
     return EDX_OK;
@@ -708,6 +844,28 @@ int edx_get_stats(edx_context* c, edx_stats* out)
 }
 
 int edx_last_launch_count(const edx_context* c) { return c ? c->launches : 0; }
+
+int edx_debug_tile_residency(edx_context* c, int* ctas_per_sm)
+{
+    if (!c || !ctas_per_sm) return EDX_ERR_INVALID;
+    if (int r = bind(c)) return r;
+    uint32_t* d = nullptr;
+    EDX_CUDA(c, cudaMalloc(&d, 1024 * 4));
+    EDX_CUDA(c, cudaMemsetAsync(d, 0, 1024 * 4, c->stream));
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(residency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)); attr = true; }
+    residency_kernel<<<2048, TILE_THREADS, sizeof(TileShared), c->stream>>>(d);
+    uint32_t h[1024];
+    cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(c, EDX_ERR_CUDA, cudaGetErrorString(e));
+    int m = 0, sms = 0;
+    for (int i = 0; i < 256; i++) { m = std::max(m, (int)h[256 + i]); sms += h[256 + i] ? 1 : 0; }
+    *ctas_per_sm = m;
+    if (getenv("EDX_DEBUG_PRINT")) fprintf(stderr, "[edx dbg] residency: %d CTAs/SM on %d SMs; 100000 SM cycles took %u ns (%.0f MHz)\n", m, sms, h[512], h[512] ? 1e8 / h[512] : 0.0);
+    return EDX_OK;
+}
 
 int edx_write_frame_to_file(edx_context* c, const char* path)
 {

@@ -46,6 +46,36 @@ class Mesh:
         self._r._check(self._r._lib.edx_mesh_update(self._r._h, self._h, vertices_ptr, num_verts, indices_ptr, num_tris))
         self.num_verts, self.num_tris = num_verts, num_tris
 
+    def SetTextures(self, textures, tex_ids=None):
+        """Mesh::mTextures + GetTextureIds (Utils/Mesh.h:23,54-59). `textures`: list of ('constant', (r, g, b)) or
+        ('image', uint8 array H x W x 4, row 0 at v = 0); `tex_ids`: one slot per triangle (None = all 0)."""
+        descs = (_lib.TextureDesc * max(1, len(textures)))()
+        keep = []
+        for d, (kind, val) in zip(descs, textures):
+            if kind == "constant":
+                d.kind = 0
+                d.color[0], d.color[1], d.color[2] = float(val[0]), float(val[1]), float(val[2])
+            else:
+                img = np.ascontiguousarray(val, dtype=np.uint8)
+                if img.ndim != 3 or img.shape[2] != 4:
+                    raise ValueError("image textures are H x W x 4 uint8")
+                keep.append(img)
+                d.kind, d.rgba8, d.width, d.height = 1, img.ctypes.data, img.shape[1], img.shape[0]
+        ids = None
+        if tex_ids is not None:
+            ids = np.ascontiguousarray(tex_ids, dtype=np.uint32)
+            if ids.shape[0] != self.num_tris:
+                raise ValueError("one texture id per triangle")
+        self._r._check(self._r._lib.edx_mesh_set_textures(self._r._h, self._h, descs, len(textures), None if ids is None else ids.ctypes.data))
+
+    def TextureLevel(self, slot, level):
+        """one mip level of an image texture, read back from the device (diagnostics)"""
+        w, h = C.c_uint32(), C.c_uint32()
+        self._r._check(self._r._lib.edx_mesh_read_texture_level(self._r._h, self._h, slot, level, None, C.byref(w), C.byref(h)))
+        out = np.zeros((h.value, w.value, 4), np.uint8)
+        self._r._check(self._r._lib.edx_mesh_read_texture_level(self._r._h, self._h, slot, level, out.ctypes.data, None, None))
+        return out
+
     def Release(self):
         if self._h:
             self._r._lib.edx_mesh_destroy(self._r._h, self._h)
@@ -207,11 +237,16 @@ class Renderer:
         s = _lib.Stats()
         self._check(self._lib.edx_get_stats(self._h, C.byref(s)))
         return {"submitted_tris": s.submitted_tris, "clipped_tris": s.clipped_tris, "binned_tris": s.binned_tris,
-                "clip_records": s.clip_records, "regrow_count": s.regrow_count,
+                "clip_records": s.clip_records, "regrow_count": s.regrow_count, "tile_pairs": s.tile_pairs,
                 "stage_ms": {"geom": s.stage_ms[0], "clip": s.stage_ms[1], "tile": s.stage_ms[2], "total": s.stage_ms[3]}}
 
     def SetOption(self, name, value):
         self._check(self._lib.edx_set_option(self._h, name.encode(), int(value)))
+
+    def TileResidency(self):
+        n = C.c_int(0)
+        self._check(self._lib.edx_debug_tile_residency(self._h, C.byref(n)))
+        return n.value
 
     def LastLaunchCount(self):
         return int(self._lib.edx_last_launch_count(self._h))

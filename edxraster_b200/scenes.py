@@ -208,3 +208,51 @@ def by_name(name, scale=1.0):
         s = math.sqrt(scale)
         return config4(quads_x=max(2, int(2500 * s)), quads_z=max(2, int(2000 * s)))
     raise ValueError(name)
+
+
+# ---------------------------------------------------------------------------------------------
+# Textured cases (LambertianAlbedoPixelShader + filter modes). Not BASELINE configs.
+# ---------------------------------------------------------------------------------------------
+def noise_texture(width, height, seed=7, cell=4):
+    """RGBA8 image with structure at several scales: coloured checker cells + per-texel noise (H x W x 4)."""
+    rng = np.random.default_rng(seed)
+    ys, xs = np.mgrid[0:height, 0:width]
+    cells = rng.integers(40, 256, ((height + cell - 1) // cell + 1, (width + cell - 1) // cell + 1, 3))
+    img = cells[ys // cell, xs // cell].astype(np.int32) + rng.integers(-30, 31, (height, width, 3))
+    out = np.empty((height, width, 4), np.uint8)
+    out[..., :3] = np.clip(img, 0, 255)
+    out[..., 3] = 255
+    return out
+
+
+def textured_plane(width=640, height=360, quads=24, uv_scale=6.0, tex=(128, 64), tex_filter=2, seed=11):
+    """A ground plane seen at a grazing angle: minification grows towards the horizon (every mip level is used,
+    footprints are strongly anisotropic) and the near edge crosses the near plane (texcoords of clipped vertices)."""
+    n = quads + 1
+    g = np.linspace(-12.0, 12.0, n)
+    xx, zz = np.meshgrid(g, g)
+    pos = np.stack([xx.ravel(), np.zeros(n * n), zz.ravel()], axis=1)
+    nrm = np.tile(np.array([0.0, 1.0, 0.0]), (n * n, 1))
+    uv = np.stack([xx.ravel(), zz.ravel()], axis=1) * (uv_scale / 24.0)
+    idx = []
+    for j in range(quads):
+        for i in range(quads):
+            a = j * n + i
+            idx += [[a, a + n, a + 1], [a + 1, a + n, a + n + 1]]
+    c = cam.Camera((0.3, 0.7, -11.0), (0.0, 0.0, 4.0), (0.0, 1.0, 0.0), width, height, 60.0, 0.5, 100.0)
+    return Scene(name="textured_plane", width=width, height=height, vertices=_pack(pos, nrm, uv),
+                 indices=np.array(idx, np.uint32), mv=c.view, proj=c.proj, raster=c.raster, shader=SHADER_LAMBERT_ALBEDO,
+                 textures=[("image", noise_texture(tex[0], tex[1], seed))], tex_ids=None, tex_filter=tex_filter)
+
+
+def textured_sphere(width=640, height=360, slices=48, stacks=48, tex_filter=2):
+    """C1's sphere with three slots - a constant colour, an odd-sized image and a tiny image - assigned per triangle."""
+    sc = config1(width=width, height=height, slices=slices, stacks=stacks)
+    sc["shader"] = SHADER_LAMBERT_ALBEDO
+    sc["textures"] = [("constant", (0.9, 0.5, 0.2)), ("image", noise_texture(37, 21, 3, cell=3)), ("image", noise_texture(2, 2, 5, cell=1))]
+    sc["tex_ids"] = (np.arange(sc.num_tris, dtype=np.uint32) // 7) % 3
+    sc["tex_filter"] = tex_filter
+    v = sc.vertices.copy()
+    v[:, 6:8] *= np.array([3.0, 2.0], np.float32)           # repeat addressing
+    sc["vertices"] = v
+    return sc

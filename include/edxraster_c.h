@@ -56,7 +56,7 @@ typedef struct edx_stats {
     uint64_t binned_tris;      /* post-setup triangles routed to the tile (large-triangle) path */
     uint64_t clip_records;     /* fan triangles emitted by the clipper */
     uint32_t regrow_count;     /* times an internal queue was grown and the frame re-run */
-    uint32_t reserved;
+    uint32_t tile_pairs;       /* (triangle, 64x64 bin) pairs that survived the bin-level culls: load of the tile path */
     float    stage_ms[8];      /* valid with profiling on: geom, clip, tile, total; rest 0 */
 } edx_stats;
 
@@ -79,7 +79,8 @@ int edx_set_transform(edx_context* ctx, const float model_view[16], const float 
  * of Core/FrameBuffer.cpp:107-191). Re-creates the frame buffer; a no-op when the level is unchanged.
  * With MSAA the back buffer is the box-filtered resolve (FrameBuffer.cpp:70-87). */
 int edx_set_msaa_mode(edx_context* ctx, int sample_count_log2);
-/* Renderer::SetTextureFilter (Core/Renderer.h:48). Stored; no textured shader this round. */
+/* Renderer::SetTextureFilter (Core/Renderer.h:48): 0 nearest, 1 linear, 2 trilinear (default, RenderStates.h:60),
+ * 3 / 4 / 5 anisotropic 4x / 8x / 16x. Read by EDX_SHADER_LAMBERT_ALBEDO on meshes that own image textures. */
 int edx_set_texture_filter(edx_context* ctx, int filter);
 /* Renderer::SetHierarchicalRasterize (Core/Renderer.h:49). Off = per-pixel tests only; same image. */
 int edx_set_hierarchical_rasterize(edx_context* ctx, int enabled);
@@ -101,6 +102,25 @@ int edx_mesh_create(edx_context* ctx, const void* vertices_pnt32, uint32_t verte
  * stream: contexts other than ctx that share the mesh must not render it until edx_synchronize(ctx). */
 int edx_mesh_update(edx_context* ctx, edx_mesh* mesh, const void* vertices_pnt32, uint32_t vertex_count,
                     const uint32_t* indices, uint32_t triangle_count);
+/* Mesh::mTextures and GetTextureIds (Utils/Mesh.h:23,54-59; Mesh.cpp:26-29,47,66): the textures a mesh owns and
+ * one slot index per triangle (NULL = keep the ids given to edx_mesh_create, or slot 0 everywhere), read by EDX_SHADER_LAMBERT_ALBEDO
+ * (LambertianAlbedoPixelShader, Core/Shader.h:209-244) under the filter of edx_set_texture_filter. A constant
+ * texture is ConstantTexture2D<Color>; an image texture is ImageTexture<Color, Color4b>(path, gamma 1) given as
+ * decoded RGBA8 texels, row 0 at v = 0, repeat addressing; its mip chain is built on the device. A mesh with no
+ * textures is shaded with the context's constant albedo (edx_set_albedo). Replaces any previous set; count = 0
+ * removes them. Synchronous. The sampler is our definition (EDXUtil's Texture2D is absent): DESIGN.md shims 19-24. */
+typedef enum edx_texture_kind { EDX_TEXTURE_CONSTANT = 0, EDX_TEXTURE_IMAGE = 1 } edx_texture_kind;
+typedef struct edx_texture_desc {
+    int kind;               /* edx_texture_kind */
+    float color[3];         /* constant textures */
+    const uint8_t* rgba8;   /* image textures: width * height * 4 bytes */
+    uint32_t width, height;
+} edx_texture_desc;
+int edx_mesh_set_textures(edx_context* ctx, edx_mesh* mesh, const edx_texture_desc* textures, uint32_t count,
+                          const uint32_t* triangle_texture_ids);
+/* diagnostics: one mip level of an image texture back to the host (out_rgba8 may be NULL to query the size) */
+int edx_mesh_read_texture_level(edx_context* ctx, const edx_mesh* mesh, uint32_t slot, uint32_t level,
+                                uint8_t* out_rgba8, uint32_t* out_width, uint32_t* out_height);
 /* Mesh::Release (Utils/Mesh.cpp:72-78) */
 int edx_mesh_destroy(edx_context* ctx, edx_mesh* mesh);
 
@@ -162,6 +182,8 @@ int edx_get_stats(edx_context* ctx, edx_stats* out);
  * "pdl" (programmatic dependent launch, default 1). None of them changes a pixel. */
 int edx_set_option(edx_context* ctx, const char* name, int value);
 /* number of kernel launches issued by the last RenderMesh (for bench.py's gpu_launches) */
+/* diagnostics: CTAs of the tile kernel's shape (512 threads, 97 KB shared memory) an SM holds at once (expected 2) */
+int edx_debug_tile_residency(edx_context* ctx, int* ctas_per_sm);
 int edx_last_launch_count(const edx_context* ctx);
 
 #ifdef __cplusplus

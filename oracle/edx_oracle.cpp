@@ -251,6 +251,116 @@ struct Stats {
     double ms[6];            // vertex, clip+setup, bin, raster, shade, fbupdate
 };
 
+// ------------------------------------------------------------------------------------------
+// Texture2D<Color> (EDXUtil Graphics/Texture.h, absent): DESIGN.md shims 19-24. ImageTexture<Color, Color4b>
+// keeps 8-bit texels and returns float colours (Mesh.cpp:27); ConstantTexture2D returns its colour (:29,47,66).
+// ------------------------------------------------------------------------------------------
+struct TexLevel { int w = 0, h = 0; std::vector<uint8_t> px; };      // RGBA8, row-major, row 0 = v 0
+struct Texture {
+    int kind = 0;                      // 0 constant, 1 image
+    float color[3] = { 0, 0, 0 };
+    std::vector<TexLevel> levels;      // shim 19: 2x2 box-filtered chain down to 1x1
+};
+
+static const float kInv255 = 1.0f / 255.0f;        // shim 18: Color(Color4b) = byte * (1/255)
+
+static void build_mips(Texture& t)                 // shim 19
+{
+    while (t.levels.back().w > 1 || t.levels.back().h > 1) {
+        const TexLevel& s = t.levels.back();
+        TexLevel d;
+        d.w = std::max(1, s.w >> 1); d.h = std::max(1, s.h >> 1);
+        d.px.resize((size_t)d.w * d.h * 4);
+        for (int y = 0; y < d.h; y++)
+            for (int x = 0; x < d.w; x++) {
+                const int x0 = std::min(2 * x, s.w - 1), x1 = std::min(2 * x + 1, s.w - 1);
+                const int y0 = std::min(2 * y, s.h - 1), y1 = std::min(2 * y + 1, s.h - 1);
+                for (int c = 0; c < 4; c++) {
+                    const float c00 = s.px[4 * ((size_t)y0 * s.w + x0) + c] * kInv255, c10 = s.px[4 * ((size_t)y0 * s.w + x1) + c] * kInv255;
+                    const float c01 = s.px[4 * ((size_t)y1 * s.w + x0) + c] * kInv255, c11 = s.px[4 * ((size_t)y1 * s.w + x1) + c] * kInv255;
+                    d.px[4 * ((size_t)y * d.w + x) + c] = to_u8((((c00 + c10) + c01) + c11) * 0.25f);
+                }
+            }
+        t.levels.push_back(std::move(d));
+    }
+}
+
+static inline int tex_wrap(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }       // shim 20: repeat
+
+static inline void tex_texel(const TexLevel& L, int x, int y, float out[3])
+{
+    const uint8_t* p = &L.px[4 * ((size_t)tex_wrap(y, L.h) * L.w + tex_wrap(x, L.w))];
+    out[0] = p[0] * kInv255; out[1] = p[1] * kInv255; out[2] = p[2] * kInv255;
+}
+
+// texel-space coordinate of a uv component; anything a float -> int conversion cannot hold becomes 0
+static inline float tex_coord(float u, int n, float bias)
+{
+    const float x = u * (float)n - bias;
+    return fabsf(x) < 1.0e9f ? x : 0.0f;
+}
+
+static void tex_bilinear(const TexLevel& L, float u, float v, float out[3])                  // shim 22
+{
+    const float x = tex_coord(u, L.w, 0.5f), y = tex_coord(v, L.h, 0.5f);
+    const float x0 = floorf(x), y0 = floorf(y);
+    const float fx = x - x0, fy = y - y0;
+    const int ix = (int)x0, iy = (int)y0;
+    float c00[3], c10[3], c01[3], c11[3];
+    tex_texel(L, ix, iy, c00); tex_texel(L, ix + 1, iy, c10); tex_texel(L, ix, iy + 1, c01); tex_texel(L, ix + 1, iy + 1, c11);
+    const float gx = 1.0f - fx, gy = 1.0f - fy;
+    const float w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
+    for (int c = 0; c < 3; c++) out[c] = ((w00 * c00[c] + w10 * c10[c]) + w01 * c01[c]) + w11 * c11[c];
+}
+
+static void tex_trilinear(const Texture& t, float u, float v, float width, float out[3])    // shim 23
+{
+    const int L = (int)t.levels.size();
+    const float level = (float)(L - 1) + log2f(std::max(width, 1.0e-8f));
+    if (!(level >= 0.0f)) { tex_bilinear(t.levels[0], u, v, out); return; }
+    if (level >= (float)(L - 1)) { tex_texel(t.levels[L - 1], 0, 0, out); return; }
+    const int i = (int)floorf(level);
+    const float d = level - (float)i;
+    float a[3], b[3];
+    tex_bilinear(t.levels[i], u, v, a);
+    tex_bilinear(t.levels[i + 1], u, v, b);
+    for (int c = 0; c < 3; c++) out[c] = (1.0f - d) * a[c] + d * b[c];
+}
+
+// Texture2D::Sample(uv, differentials) under RenderStates' filter (Shader.h:234-236; Renderer.h:48)
+static void tex_sample(const Texture& t, int filter, float u, float v, float du0, float dv0, float du1, float dv1, float out[3])
+{
+    if (t.kind == 0) { out[0] = t.color[0]; out[1] = t.color[1]; out[2] = t.color[2]; return; }
+    const TexLevel& L0 = t.levels[0];
+    if (filter == 0) {                                                                          // shim 21: nearest
+        tex_texel(L0, (int)floorf(tex_coord(u, L0.w, 0.0f)), (int)floorf(tex_coord(v, L0.h, 0.0f)), out);
+    } else if (filter == 1) {
+        tex_bilinear(L0, u, v, out);
+    } else if (filter == 2) {
+        const float width = 2.0f * std::max(std::max(fabsf(du0), fabsf(dv0)), std::max(fabsf(du1), fabsf(dv1)));
+        tex_trilinear(t, u, v, width, out);
+    } else {                                                                                    // shim 24: N taps along the major axis
+        const int N = filter == 3 ? 4 : (filter == 4 ? 8 : 16);
+        const float l0 = sqrtf(du0 * du0 + dv0 * dv0), l1 = sqrtf(du1 * du1 + dv1 * dv1);
+        const bool first = l0 >= l1;
+        const float lmaj = first ? l0 : l1, lmin = first ? l1 : l0;
+        const float mu = first ? du0 : du1, mv = first ? dv0 : dv1;
+        int n = 1;
+        if (lmaj > 0.0f) n = (lmin * (float)N <= lmaj) ? N : std::min(N, std::max(1, (int)ceilf(lmaj / lmin)));
+        if (!(lmaj < 3.0e38f)) n = 1;                                   // inf / NaN footprints: one tap
+        const float width = 2.0f * (lmaj / (float)n);
+        float acc[3] = { 0.0f, 0.0f, 0.0f };
+        for (int i = 0; i < n; i++) {
+            const float s = ((float)i + 0.5f) / (float)n - 0.5f;
+            float c[3];
+            tex_trilinear(t, u + mu * s, v + mv * s, width, c);
+            acc[0] += c[0]; acc[1] += c[1]; acc[2] += c[2];
+        }
+        const float inv = 1.0f / (float)n;
+        out[0] = acc[0] * inv; out[1] = acc[1] * inv; out[2] = acc[2] * inv;
+    }
+}
+
 static const int TILE = 32, TILE_LOG2 = 5;
 
 struct Oracle {
@@ -259,6 +369,9 @@ struct Oracle {
     int msLevel = 0, samples = 1;   // FrameBuffer.cpp:14-15
     bool hierarchical = true;
     float albedo[3] = { 0.9f, 0.9f, 0.9f };
+    int texFilter = 2;              // RenderStates.h:60: TextureFilter::TriLinear
+    std::vector<struct Texture> textures;        // Mesh::mTextures (Mesh.h:23); empty = the constant `albedo`
+    std::vector<uint32_t> texIds;                // Mesh::GetTextureIds (Mesh.h:58): one slot index per submitted triangle
     Mat4 MV, MVinv, P, MVP, R;
     std::vector<Tile> tiles;
     std::vector<__m128> depth;      // per tile 16x16 quads, FrameBuffer.cpp:25-27
@@ -876,7 +989,8 @@ static void fragment_processing(Oracle& o)
         __m128 nx = lerp3(b0, b1, b2, v0.normal.x, v1.normal.x, v2.normal.x);
         __m128 ny = lerp3(b0, b1, b2, v0.normal.y, v1.normal.y, v2.normal.y);
         __m128 nz = lerp3(b0, b1, b2, v0.normal.z, v1.normal.z, v2.normal.z);
-        // (texcoord interpolation, Shader.h:167-169, feeds only the textured shader: not on this path)
+        const __m128 tu = lerp3(b0, b1, b2, v0.uv.x, v1.uv.x, v2.uv.x);      // Shader.h:167-169
+        const __m128 tv = lerp3(b0, b1, b2, v0.uv.y, v1.uv.y, v2.uv.y);
 
         // Shader.h:256-264 (shared by the Lambertian and Blinn-Phong shaders)
         __m128 w = rsqrt4(dot3(nx, ny, nz, nx, ny, nz));
@@ -899,11 +1013,27 @@ static void fragment_processing(Oracle& o)
             for (int k = 0; k < 4; k++) sp[k] = powf(sp[k], 200.0f);      // shim 10: Math::Pow = powf
             __m128 spec = _mm_mul_ps(_mm_load_ps(sp), _mm_set1_ps(3.0f));
             r = g = b = _mm_add_ps(diffuse, spec);
-        } else if (o.shader == 3) {
+        } else if (o.shader == 3 && o.textures.empty()) {
             // Shader.h:209-244 with the constant-colour texture Mesh.cpp:48,67 installs
             r = _mm_mul_ps(diffuse, _mm_set1_ps(o.albedo[0]));
             g = _mm_mul_ps(diffuse, _mm_set1_ps(o.albedo[1]));
             b = _mm_mul_ps(diffuse, _mm_set1_ps(o.albedo[2]));
+        } else if (o.shader == 3) {
+            // Shader.h:228-241: differentials from quad lanes 1 and 2 against lane 0, one Sample per lane
+            alignas(16) float uu[4], vv[4], ar[4], ag[4], ab[4];
+            _mm_store_ps(uu, tu); _mm_store_ps(vv, tv);
+            const uint32_t tri = f.primId >> 3;
+            const uint32_t slot = tri < o.texIds.size() ? o.texIds[tri] : 0u;
+            const Texture& tex = o.textures[slot < o.textures.size() ? slot : 0u];
+            const float du0 = uu[1] - uu[0], dv0 = vv[1] - vv[0], du1 = uu[2] - uu[0], dv1 = vv[2] - vv[0];
+            for (int k = 0; k < 4; k++) {
+                float c[3];
+                tex_sample(tex, o.texFilter, uu[k], vv[k], du0, dv0, du1, dv1, c);
+                ar[k] = c[0]; ag[k] = c[1]; ab[k] = c[2];
+            }
+            r = _mm_mul_ps(diffuse, _mm_load_ps(ar));
+            g = _mm_mul_ps(diffuse, _mm_load_ps(ag));
+            b = _mm_mul_ps(diffuse, _mm_load_ps(ab));
         }
         alignas(16) float rr[4], gg[4], bb[4];
         _mm_store_ps(rr, r); _mm_store_ps(gg, g); _mm_store_ps(bb, b);
@@ -1046,6 +1176,33 @@ void orc_get_derived(void* h, float* mvp16, float* eye3, float* light3)
 }
 void orc_set_shader(void* h, int mode) { ((Oracle*)h)->shader = mode; }
 void orc_set_albedo(void* h, float r, float g, float b) { Oracle& o = *(Oracle*)h; o.albedo[0] = r; o.albedo[1] = g; o.albedo[2] = b; }
+void orc_set_texture_filter(void* h, int filter) { ((Oracle*)h)->texFilter = filter; }
+void orc_clear_textures(void* h) { Oracle& o = *(Oracle*)h; o.textures.clear(); o.texIds.clear(); }
+void orc_add_constant_texture(void* h, float r, float g, float b)
+{
+    Texture t; t.kind = 0; t.color[0] = r; t.color[1] = g; t.color[2] = b;
+    ((Oracle*)h)->textures.push_back(std::move(t));
+}
+void orc_add_image_texture(void* h, const uint8_t* rgba8, int w, int ht)
+{
+    Texture t; t.kind = 1;
+    TexLevel l; l.w = w; l.h = ht; l.px.assign(rgba8, rgba8 + (size_t)w * ht * 4);
+    t.levels.push_back(std::move(l));
+    build_mips(t);
+    ((Oracle*)h)->textures.push_back(std::move(t));
+}
+void orc_set_texture_ids(void* h, const uint32_t* ids, uint32_t n) { ((Oracle*)h)->texIds.assign(ids, ids + n); }
+// sampler alone, for known-answer tests: texture `slot`, filter, uv and the two differentials
+void orc_tex_sample(void* h, uint32_t slot, int filter, float u, float v, float du0, float dv0, float du1, float dv1, float* out3)
+{
+    tex_sample(((Oracle*)h)->textures[slot], filter, u, v, du0, dv0, du1, dv1, out3);
+}
+int orc_tex_levels(void* h, uint32_t slot) { return (int)((Oracle*)h)->textures[slot].levels.size(); }
+void orc_tex_level(void* h, uint32_t slot, int level, uint8_t* out)
+{
+    const TexLevel& l = ((Oracle*)h)->textures[slot].levels[level];
+    memcpy(out, l.px.data(), l.px.size());
+}
 void orc_set_hierarchical(void* h, int on) { ((Oracle*)h)->hierarchical = on != 0; }
 
 // Renderer.cpp:100-118. vtx: nv x 32-byte (pos3, normal3, uv2); idx: nt x 3 uint32.

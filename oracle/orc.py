@@ -44,6 +44,15 @@ def _load(timing):
     lib.orc_set_shader.argtypes = [vp, C.c_int]
     lib.orc_set_albedo.argtypes = [vp, C.c_float, C.c_float, C.c_float]
     lib.orc_set_hierarchical.argtypes = [vp, C.c_int]
+    u8p = C.POINTER(C.c_uint8)
+    lib.orc_set_texture_filter.argtypes = [vp, C.c_int]
+    lib.orc_clear_textures.argtypes = [vp]
+    lib.orc_add_constant_texture.argtypes = [vp, C.c_float, C.c_float, C.c_float]
+    lib.orc_add_image_texture.argtypes = [vp, u8p, C.c_int, C.c_int]
+    lib.orc_set_texture_ids.argtypes = [vp, u32p, C.c_uint32]
+    lib.orc_tex_sample.argtypes = [vp, C.c_uint32, C.c_int] + [C.c_float] * 6 + [f32p]
+    lib.orc_tex_levels.argtypes = [vp, C.c_uint32]
+    lib.orc_tex_level.argtypes = [vp, C.c_uint32, C.c_int, u8p]
     lib.orc_set_msaa.argtypes = [vp, C.c_int]
     lib.orc_samples.argtypes = [vp]
     lib.orc_get_winner_sample.argtypes = [vp, C.c_int, u32p]
@@ -120,6 +129,43 @@ class Oracle:
 
     def set_albedo(self, r, g, b):
         self.lib.orc_set_albedo(self.h_, r, g, b)
+
+    def set_texture_filter(self, f):
+        """Renderer::SetTextureFilter (Core/Renderer.h:48): 0 nearest, 1 linear, 2 trilinear, 3/4/5 anisotropic 4x/8x/16x."""
+        self.lib.orc_set_texture_filter(self.h_, int(f))
+
+    def set_textures(self, textures, tex_ids=None):
+        """Mesh::mTextures + GetTextureIds (Utils/Mesh.h:23,54-59). `textures`: list of ('constant', (r, g, b)) or
+        ('image', uint8 array H x W x 4); `tex_ids`: one slot per submitted triangle (None = all 0)."""
+        self.lib.orc_clear_textures(self.h_)
+        self._tex_dims = []
+        for kind, val in textures:
+            if kind == "constant":
+                self.lib.orc_add_constant_texture(self.h_, float(val[0]), float(val[1]), float(val[2]))
+                self._tex_dims.append(None)
+            else:
+                img = np.ascontiguousarray(val, dtype=np.uint8)
+                assert img.ndim == 3 and img.shape[2] == 4
+                self.lib.orc_add_image_texture(self.h_, img.ctypes.data_as(C.POINTER(C.c_uint8)), img.shape[1], img.shape[0])
+                self._tex_dims.append((img.shape[1], img.shape[0]))
+        if tex_ids is not None:
+            ids = np.ascontiguousarray(tex_ids, dtype=np.uint32)
+            self.lib.orc_set_texture_ids(self.h_, ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.shape[0])
+
+    def tex_sample(self, slot, filt, u, v, d0=(0.0, 0.0), d1=(0.0, 0.0)):
+        out = np.zeros(3, np.float32)
+        self.lib.orc_tex_sample(self.h_, slot, filt, u, v, d0[0], d0[1], d1[0], d1[1], _f32(out))
+        return out
+
+    def tex_mips(self, slot):
+        w, h = self._tex_dims[slot]
+        out = []
+        for l in range(self.lib.orc_tex_levels(self.h_, slot)):
+            lw, lh = max(1, w >> l), max(1, h >> l)
+            a = np.zeros((lh, lw, 4), np.uint8)
+            self.lib.orc_tex_level(self.h_, slot, l, a.ctypes.data_as(C.POINTER(C.c_uint8)))
+            out.append(a)
+        return out
 
     def set_msaa(self, log2):
         """Renderer::SetMSAAMode (Core/Renderer.cpp:94-98): 2^log2 samples per pixel."""

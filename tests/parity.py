@@ -12,6 +12,9 @@ def render_oracle(scene, threads=0, shader=None, hierarchical=True, msaa=0):
     o.set_transform(scene.mv, scene.proj, scene.raster)
     o.set_shader(scene.shader if shader is None else shader)
     o.set_hierarchical(hierarchical)
+    if scene.get("textures"):
+        o.set_textures(scene["textures"], scene.get("tex_ids"))
+        o.set_texture_filter(scene.get("tex_filter", 2))
     o.render(scene.vertices, scene.indices)
     out = {"color": o.color(), "depth": o.depth(), "winner": o.winner(), "clip": o.clip_verts(),
            "tris": o.raster_tris(), "stats": o.stats(), "derived": o.derived()}
@@ -32,6 +35,9 @@ def render_gpu(scene, shader=None, options=None, hierarchical=True, stages=True,
     for k, v in (options or {}).items():
         r.SetOption(k, v)
     m = r.CreateMesh(scene.vertices, scene.indices)
+    if scene.get("textures"):
+        m.SetTextures(scene["textures"], scene.get("tex_ids"))
+    r.SetTextureFilter(scene.get("tex_filter", 2))
     r.RenderMesh(m)
     out = {"color": r.GetBackBuffer().copy(), "depth": r.GetDepthBuffer(), "winner": r.GetWinnerIds(),
            "stats": r.GetStats(), "derived": r.DerivedState()}

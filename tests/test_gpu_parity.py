@@ -302,7 +302,8 @@ def test_frame_ring_frames_in_flight_match_the_oracle():
     got = {}
     tickets = []
     for i, v in enumerate(views):
-        tickets.append(ring.Submit(mesh, *v))
+        # both spellings of the transform: three matrices, or marshalled once (PackedTransform)
+        tickets.append(ring.Submit(mesh, R.PackedTransform(*v)) if i % 2 else ring.Submit(mesh, *v))
         if i >= 2:
             t = tickets[i - 2]
             lane = ring.lanes[t % 3]
@@ -350,4 +351,82 @@ def test_overflow_in_an_unsynchronised_earlier_frame_is_reported():
     assert r.GetStats()["regrow_count"] == 1
     ref = parity.render_oracle(big)
     assert (ref["depth"].view(np.uint32) != got.view(np.uint32)).sum() == 0
+    r.close()
+
+
+# ---- textured LambertianAlbedoPixelShader + filter modes (Core/Shader.h:209-244) ----
+
+@pytest.mark.parametrize("filt", [0, 1, 2, 3, 4, 5])
+def test_textured_plane_every_filter(filt):
+    # grazing-angle plane: every mip level, strongly anisotropic footprints, near-plane clipping of the front row
+    sc = scenes.textured_plane(tex_filter=filt)
+    _, got, rep = assert_parity(sc)
+    assert got["stats"]["clipped_tris"] > 0
+    assert len(np.unique(got["color"].reshape(-1, 4), axis=0)) > 5000
+
+
+@pytest.mark.parametrize("filt", [0, 2, 4])
+def test_textured_sphere_slots_and_odd_sizes(filt):
+    # constant + 37x21 + 2x2 textures assigned per triangle, texcoords beyond [0, 1) (repeat)
+    assert_parity(scenes.textured_sphere(tex_filter=filt), stages=False)
+
+
+def test_textured_terrain_with_clipping_and_msaa():
+    sc = scenes.config4(width=640, height=360, quads_x=200, quads_z=160)
+    sc["shader"] = scenes.SHADER_LAMBERT_ALBEDO
+    sc["textures"] = [("image", scenes.noise_texture(64, 64, 9)), ("constant", (0.2, 0.8, 0.4)), ("image", scenes.noise_texture(16, 128, 10))]
+    sc["tex_ids"] = (np.arange(sc.num_tris, dtype=np.uint32) // 3) % 3
+    v = sc.vertices.copy()
+    v[:, 6:8] = v[:, [0, 2]] * 0.7                     # world-space planar mapping
+    sc["vertices"] = v
+    for filt, msaa in ((2, 0), (3, 0), (2, 2)):
+        sc["tex_filter"] = filt
+        assert_parity(sc, stages=False, msaa=msaa)
+
+
+def test_device_mip_chain_equals_the_oracle_chain():
+    from edxraster_b200 import renderer as R
+    from oracle import orc
+    imgs = [scenes.noise_texture(128, 64, 1), scenes.noise_texture(37, 21, 2, cell=3), scenes.noise_texture(1, 5, 3, cell=1)]
+    o = orc.Oracle(16, 16, 1)
+    o.set_textures([("image", i) for i in imgs])
+    r = R.Renderer(0)
+    r.Initialize(16, 16)
+    sc = scenes.config1(width=16, height=16, slices=4, stacks=4)
+    m = r.CreateMesh(sc.vertices, sc.indices)
+    m.SetTextures([("image", i) for i in imgs])
+    for slot in range(3):
+        ref = o.tex_mips(slot)
+        for level, want in enumerate(ref):
+            np.testing.assert_array_equal(m.TextureLevel(slot, level), want)
+    m.Release()
+    r.close()
+
+
+def test_texture_api_errors_and_replacement():
+    from edxraster_b200 import renderer as R
+    from edxraster_b200._lib import EdxError, EDX_ERR_INVALID
+    sc = scenes.textured_sphere()
+    r = R.Renderer(0)
+    r.Initialize(sc.width, sc.height)
+    m = r.CreateMesh(sc.vertices, sc.indices)
+    with pytest.raises(EdxError) as e:
+        m.SetTextures([("constant", (1, 1, 1))], np.full(sc.num_tris, 1, np.uint32))     # slot 1 does not exist
+    assert e.value.code == EDX_ERR_INVALID
+    with pytest.raises(ValueError):
+        m.SetTextures([("image", np.zeros((4, 4, 3), np.uint8))])
+    with pytest.raises(EdxError):
+        m.TextureLevel(0, 0)
+    # replacing and removing textures: the last state wins, none = the context's constant albedo
+    m.SetTextures(sc["textures"], sc["tex_ids"])
+    m.SetTextures([])
+    r.SetTransform(sc.mv, sc.proj, sc.raster)
+    r.SetPixelShader(scenes.SHADER_LAMBERT_ALBEDO)
+    r.RenderMesh(m)
+    got = r.GetBackBuffer().copy()
+    plain = dict(sc)
+    plain.pop("textures"); plain.pop("tex_ids")
+    ref = parity.render_oracle(scenes.Scene(plain))
+    assert np.abs(got.astype(np.int32) - ref["color"].astype(np.int32)).max() <= 1
+    m.Release()
     r.close()
