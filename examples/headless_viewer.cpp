@@ -1,6 +1,6 @@
 // headless_viewer.cpp — the reference's RealtimeViewer (RealtimeViewer/Main.cpp) without the window:
 // same calls in the same order (OnInit :32-62, OnRender :65-75), frames go to a BMP instead of
-// glDrawPixels. Usage: headless_viewer [frames] [out.bmp] [dump.bin] [mesh.obj] [msaa_log2] [frames_in_flight]
+// glDrawPixels. Usage: headless_viewer [frames] [out.bmp] [dump.bin] [mesh.obj] [msaa_log2] [frames_in_flight] [texture_filter]
 // With frames_in_flight > 1 the loop keeps that many frames on the GPU (FrameRing) and reads each back in order.
 #include <chrono>
 #include <cstdio>
@@ -34,6 +34,22 @@ int main(int argc, char** argv)
     }
     if (argc > 5) renderer.SetMSAAMode(std::atoi(argv[5]));                                 // Main.cpp:97
     renderer.SetPixelShader(PixelShaderKind::BlinnPhong);
+    if (argc > 7) {
+        // the reference's default shader (LambertianAlbedoPixelShader, Renderer.cpp:41) on an image texture; the
+        // texels are a formula so that a test can rebuild them: 64 x 32 RGBA8
+        std::vector<_byte> tex(64 * 32 * 4);
+        for (int y = 0; y < 32; y++)
+            for (int x = 0; x < 64; x++) {
+                _byte* p = &tex[4 * (y * 64 + x)];
+                p[0] = (_byte)((x * 37 + y * 11) & 255); p[1] = (_byte)(((x / 4 + y / 4) & 1) ? 230 : 40); p[2] = (_byte)((x * y * 3) & 255); p[3] = 255;
+            }
+        mesh.AddImageTexture(tex.data(), 64, 32);
+        std::vector<uint> ids(mesh.GetIndexBuffer()->GetTriangleCount());
+        for (size_t i = 0; i < ids.size(); i++) ids[i] = (i / 5) % 2 ? (uint)(mesh.GetTextureCount() - 1) : 0u;      // image / the mesh's first slot
+        mesh.SetTextureIds(ids);
+        renderer.SetPixelShader(PixelShaderKind::LambertianAlbedo);
+        renderer.SetTextureFilter(TextureFilter(std::atoi(argv[7])));                       // Main.cpp:108
+    }
 
     const int inFlight = argc > 6 ? std::atoi(argv[6]) : 1;
     std::vector<_byte> ringFrame;                                  // last frame that came out of the ring

@@ -195,6 +195,7 @@ public:
                 idx.insert(idx.end(), { a, b, c, b, d, c });
             }
         SetBuffers(v.data(), v.size(), idx.data(), idx.size() / 3);
+        AddConstantTexture(0.9f, 0.9f, 0.9f);          // Mesh.cpp:47
     }
     void LoadPlane(const Vector3& pos, const Vector3& scl, const Vector3& rot, float length)
     {
@@ -209,6 +210,7 @@ public:
         }
         const uint idx[6] = { 0, 2, 1, 1, 2, 3 };
         SetBuffers(v, 4, idx, 2);
+        AddConstantTexture(0.9f, 0.9f, 0.9f);          // Mesh.cpp:66
     }
     // Mesh::LoadMesh (Utils/Mesh.cpp:11-34): Wavefront OBJ. The reference delegates to EDXUtil's ObjMesh (absent);
     // this reader handles v / vt / vn / f (polygons fanned, negative indices, v, v/vt, v//vn, v/vt/vn), builds one
@@ -292,15 +294,36 @@ public:
     const IVertexBuffer* GetVertexBuffer() const { return mpVertexBuf.get(); }
     IndexBuffer* GetIndexBuffer() const { return mpIndexBuf.get(); }
     const std::vector<uint>& GetTextureIds() const { return mTexIdx; }
+    // Mesh::mTextures (Mesh.h:23): ConstantTexture2D<Color>(colour) or ImageTexture<Color, Color4b> (Mesh.cpp:27,29).
+    // The reference decodes image files through EDXUtil; here the caller hands over decoded RGBA8 texels (row 0 at
+    // v = 0). Returns the slot index that SetTextureIds refers to.
+    uint AddConstantTexture(float r, float g, float b)
+    {
+        Texture t; t.kind = EDX_TEXTURE_CONSTANT; t.color[0] = r; t.color[1] = g; t.color[2] = b;
+        mTextures.push_back(t); mTexDirty = true;
+        return (uint)mTextures.size() - 1;
+    }
+    uint AddImageTexture(const _byte* rgba8, uint width, uint height)
+    {
+        Texture t; t.kind = EDX_TEXTURE_IMAGE; t.width = width; t.height = height;
+        t.texels.assign(rgba8, rgba8 + (size_t)width * height * 4);
+        mTextures.push_back(t); mTexDirty = true;
+        return (uint)mTextures.size() - 1;
+    }
+    void SetTextureIds(const std::vector<uint>& perTriangle) { mTexIdx = perTriangle; mTexDirty = true; }
+    size_t GetTextureCount() const { return mTextures.size(); }
     void Release()
     {
         if (mDevice) ReleaseDevice();
         mDevice = nullptr; mOwner = nullptr;
-        mpVertexBuf.reset(); mpIndexBuf.reset(); mTexIdx.clear();
+        mpVertexBuf.reset(); mpIndexBuf.reset(); mTexIdx.clear(); mTextures.clear(); mTexDirty = false;
     }
 private:
     friend class Renderer;
     inline void ReleaseDevice() const;           // defined after Renderer (needs its registry of live contexts)
+    struct Texture { int kind = 0; float color[3] = { 0, 0, 0 }; uint width = 0, height = 0; std::vector<_byte> texels; };
+    std::vector<Texture> mTextures;
+    mutable bool mTexDirty = false;
     std::unique_ptr<IVertexBuffer> mpVertexBuf;
     std::unique_ptr<IndexBuffer> mpIndexBuf;
     std::vector<uint> mTexIdx;
@@ -343,6 +366,19 @@ public:
             Call(edx_mesh_create(mCtx, vb->GetBuffer(), vb->GetVertexCount(), ib->GetBuffer(), ib->GetTriangleCount(),
                                  mesh.GetTextureIds().data(), &mesh.mDevice));
             mesh.mOwner = mCtx;
+            if (mStatus != EDX_OK) return;
+            mesh.mTexDirty = !mesh.mTextures.empty();
+        }
+        if (mesh.mTexDirty) {                    // Renderer.cpp:106: RenderStates::TextureSlots = &mesh.GetTextures()
+            std::vector<edx_texture_desc> descs(mesh.mTextures.size());
+            for (size_t i = 0; i < descs.size(); i++) {
+                const Mesh::Texture& t = mesh.mTextures[i];
+                descs[i].kind = t.kind; descs[i].rgba8 = t.texels.data(); descs[i].width = t.width; descs[i].height = t.height;
+                for (int k = 0; k < 3; k++) descs[i].color[k] = t.color[k];
+            }
+            const bool ids = mesh.mTexIdx.size() == mesh.GetIndexBuffer()->GetTriangleCount();
+            Call(edx_mesh_set_textures(mCtx, mesh.mDevice, descs.data(), (uint32_t)descs.size(), ids ? mesh.mTexIdx.data() : nullptr));
+            mesh.mTexDirty = false;
             if (mStatus != EDX_OK) return;
         }
         Call(edx_render_mesh(mCtx, mesh.mDevice));

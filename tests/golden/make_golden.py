@@ -29,6 +29,10 @@ def cases():
         "C2_small": scenes.config2(width=480, height=270, num_tris=20000),
         "C3_small": scenes.config3(width=384, height=216, num_tris=64),
         "C4_small": scenes.config4(width=480, height=270, quads_x=120, quads_z=96),
+        # textured LambertianAlbedo shader: trilinear, anisotropic 16x, nearest + slots
+        "TEX_plane_trilinear": scenes.textured_plane(width=320, height=180, tex_filter=2),
+        "TEX_plane_aniso16": scenes.textured_plane(width=320, height=180, tex_filter=5),
+        "TEX_sphere_nearest": scenes.textured_sphere(width=320, height=180, slices=32, stacks=32, tex_filter=0),
     }
 
 
@@ -59,6 +63,8 @@ def main():
             frames["C1_small_depth"] = ref["depth"]
             frames["C1_small_winner"] = ref["winner"]
             frames["C1_small_color"] = ref["color"]
+        if name.startswith("TEX_"):
+            frames[name + "_color"] = ref["color"]
     for name, (sc, level) in msaa_cases().items():
         ref = parity.render_oracle(sc, threads=2, msaa=level)
         out[name] = {

@@ -73,6 +73,9 @@ def test_cuda_matches_msaa_golden(name):
 def test_cuda_matches_golden(name):
     out = parity.render_gpu(CASES[name])
     check(name, out, color_exact=False)
+    if name.startswith("TEX_"):
+        d = np.abs(out["color"].astype(np.int32) - FRAMES[name + "_color"].astype(np.int32))
+        assert d.max() <= 1
     if name == "C1_small":
         # colour tolerance stated by north_star: +-1 of 8 bits per channel
         d = np.abs(out["color"].astype(np.int32) - FRAMES["C1_small_color"].astype(np.int32))

@@ -107,3 +107,28 @@ def test_frame_ring_through_the_cpp_api(tmp_path):
     assert "3 frames in flight" in out.stdout
     assert "ring frames identical to the single-frame path: yes" in out.stdout
     compare_with_oracle(bmp, dump)
+
+
+def test_textured_default_shader_through_the_cpp_api(tmp_path):
+    # LoadSphere installs the constant 0.9 texture (Mesh.cpp:47); the viewer adds a 64x32 image and alternates the two
+    # slots every five triangles; LambertianAlbedo + anisotropic 4x (Main.cpp:108)
+    out, bmp, dump = run_viewer(tmp_path, ["", "0", "1", "3"])
+    raw = open(dump, "rb").read()
+    w, h, nv, nt = struct.unpack("4I", raw[:16])
+    mats = np.frombuffer(raw, np.float32, 48, 16).reshape(3, 4, 4)
+    verts = np.frombuffer(raw, np.float32, nv * 8, 16 + 192).reshape(nv, 8)
+    idx = np.frombuffer(raw, np.uint32, nt * 3, 16 + 192 + nv * 32).reshape(nt, 3)
+    ys, xs = np.mgrid[0:32, 0:64]
+    tex = np.stack([(xs * 37 + ys * 11) & 255, np.where((xs // 4 + ys // 4) & 1, 230, 40), (xs * ys * 3) & 255, np.full_like(xs, 255)], axis=-1).astype(np.uint8)
+    o = orc.Oracle(w, h, 0)
+    o.set_transform(mats[0], mats[1], mats[2])
+    o.set_shader(scenes.SHADER_LAMBERT_ALBEDO)
+    o.set_textures([("constant", (0.9, 0.9, 0.9)), ("image", tex)], ((np.arange(nt) // 5) % 2).astype(np.uint32))
+    o.set_texture_filter(3)
+    o.render(verts, idx)
+    ref = o.color()
+    data = open(bmp, "rb").read()
+    off = struct.unpack("<I", data[10:14])[0]
+    pix = np.frombuffer(data, np.uint8, w * h * 3, off).reshape(h, w, 3)[..., ::-1]
+    assert np.abs(pix.astype(np.int32) - ref[..., :3].astype(np.int32)).max() <= 1
+    assert len(np.unique(pix.reshape(-1, 3), axis=0)) > 2000         # the image really is on the sphere
