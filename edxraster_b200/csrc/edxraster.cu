@@ -356,12 +356,7 @@ int edx_create(int device, edx_context** out)
               cudaHostGetDevicePointer((void**)&c->hostCountersDev, c->hostCounters, 0) == cudaSuccess &&
               cudaMemset(c->counters, 0, sizeof(Counters)) == cudaSuccess &&
               cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
-              cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
-              // Two 97 KB CTAs per SM need the 196 KB shared-memory carve-out. Left to the driver's default heuristic a
-              // fresh process got a smaller one (one CTA per SM: C3 took 1.65 ms instead of 0.80 ms) until some other
-              // module's kernel had run; ask for it explicitly.
-              cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
-              cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
+              cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess;
     for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&c->evTimer[i]) == cudaSuccess;
     for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&c->evStage[i]) == cudaSuccess;
     if (!ok) { edx_destroy(c); return EDX_ERR_CUDA; }
