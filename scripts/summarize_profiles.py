@@ -1,5 +1,12 @@
 """Turn gpurun_out/*.csv / *.ncu-rep into the tracked summaries under profiles/ (round-tagged)."""
-import csv, glob, io, json, os, subprocess, sys
+import csv, glob, io, json, os, re, subprocess, sys
+
+
+def kname(n):
+    """"void tile_kernel<0>(FrameParams)" -> "tile_kernel"; the <1> instantiation (MSAA) keeps its suffix"""
+    n = re.sub(r"^void\s+", "", n).split("(")[0]
+    return n.replace("<0>", "").replace("<(bool)0>", "").replace("<1>", "_msaa").replace("<(bool)1>", "_msaa")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 out = os.path.join(ROOT, "profiles")
@@ -17,7 +24,7 @@ for w in ("C1", "C2", "C3", "C4"):
     ki, vi = h.index("Kernel Name"), h.index("Metric Value")
     per = {}
     for r in rows[1:]:
-        per.setdefault(r[ki].split("(")[0], []).append(float(r[vi].replace(",", "")))
+        per.setdefault(kname(r[ki]), []).append(float(r[vi].replace(",", "")))
     frame = {k: sum(v[-3:]) / len(v[-3:]) for k, v in per.items() if k in ("geom_kernel", "clip_kernel", "tile_kernel")}
     tot = sum(frame.values()) or 1
     lines += ["## %s launch list (ns per launch, mean of last 3 frames)" % w, "", "| kernel | ns | share of frame |", "|---|---|---|"]
@@ -39,9 +46,9 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "full_*.ncu-rep")))
     units = rows[1]
     lines += ["## full capture %s" % name, "", "| " + " | ".join(c for c, _ in idx) + " |", "|" + "---|" * len(idx)]
     for r in rows[2:]:
-        lines.append("| " + " | ".join((r[i].split("(")[0] if c == "Kernel Name" else r[i] + " " + units[i]) for c, i in idx) + " |")
+        lines.append("| " + " | ".join((kname(r[i]) if c == "Kernel Name" else r[i] + " " + units[i]) for c, i in idx) + " |")
         try:
-            kn = r[h.index("Kernel Name")].split("(")[0]
+            kn = kname(r[h.index("Kernel Name")])
             rd, wr = float(r[h.index("dram__bytes_read.sum")]), float(r[h.index("dram__bytes_write.sum")])
             ur, uw = units[h.index("dram__bytes_read.sum")], units[h.index("dram__bytes_write.sum")]
             mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
@@ -68,7 +75,7 @@ if os.path.exists(bl):
           "| # | stream | kernel | ns |", "|---|---|---|---|"]
     tot = {}
     for n, r in enumerate(rows[1:]):
-        k = r[ki].split("(")[0]
+        k = kname(r[ki])
         v = float(r[vi].replace(",", ""))
         md.append("| %d | %s | %s | %.0f |" % (n, r[si], k, v))
         tot.setdefault(k, []).append(v)
