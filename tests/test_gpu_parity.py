@@ -266,9 +266,21 @@ def _fuzz_scene(seed):
     eye = (rng.random(3) - 0.5) * np.array([2.0, 2.0, 2.0]) + np.array([0.0, 0.0, -2.0])
     c = cam.Camera(eye, (0.0, 0.0, 3.0), (0.0, 1.0, 0.0), w, h, float(rng.choice([40.0, 65.0, 100.0])),
                    float(rng.choice([0.05, 0.5, 2.0])), float(rng.choice([6.0, 50.0])))
-    return scenes.Scene(name="fuzz%d" % seed, width=w, height=h, vertices=v,
-                        indices=np.arange(n * 3, dtype=np.uint32).reshape(-1, 3), mv=c.view, proj=c.proj, raster=c.raster,
-                        shader=int(rng.choice([0, 1, 2, 3]))), int(rng.choice([0, 0, 1, 2, 3]))
+    sc = scenes.Scene(name="fuzz%d" % seed, width=w, height=h, vertices=v,
+                      indices=np.arange(n * 3, dtype=np.uint32).reshape(-1, 3), mv=c.view, proj=c.proj, raster=c.raster,
+                      shader=int(rng.choice([0, 1, 2, 3])))
+    msaa = int(rng.choice([0, 0, 1, 2, 3]))
+    if sc.shader == 3 and rng.random() < 0.8:            # textured: random slots, sizes, filter, texcoord range
+        v[:, 6:8] = (v[:, 6:8] - 0.5) * float(rng.choice([1.0, 4.0, 40.0]))
+        tex = []
+        for k in range(int(rng.integers(1, 4))):
+            if rng.random() < 0.25:
+                tex.append(("constant", tuple(rng.random(3))))
+            else:
+                tex.append(("image", scenes.noise_texture(int(rng.choice([1, 2, 5, 16, 33, 128])), int(rng.choice([1, 3, 8, 64])), seed + k, cell=2)))
+        sc["textures"], sc["tex_ids"] = tex, rng.integers(0, len(tex), n).astype(np.uint32)
+        sc["tex_filter"] = int(rng.integers(0, 6))
+    return sc, msaa
 
 
 @pytest.mark.parametrize("seed", list(range(100, 116)))
