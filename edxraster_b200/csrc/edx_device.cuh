@@ -97,6 +97,7 @@ struct FrameParams {
     int fuseClip;            // clip single-plane straddlers inside geom_kernel instead of queueing them
     int msLevel, samples;    // Renderer::SetMSAAMode (Renderer.cpp:94-98): samples = 1 << msLevel
     uint32_t keyStride;      // keys per sample plane
+    int leanResolve;         // lean_resolve_kernel runs before tile_kernel this frame
     int rasterAffineXY;      // raster matrix has no z column and w' == 1: skip the unused z/w and w' arithmetic
     // mesh (SoA streams built at upload)
     const float4* pos4;      // x, y, z, texcoord.v

@@ -190,18 +190,21 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                 // instructions instead of the warp iterating max(height) x max(width) times.
                 const uint32_t colMask = (1u << (wm1 + 1)) - 1u;
                 const int hgt = y1 - y0 + 1;
-                uint32_t m = 0;                                         // bit 5*dy + dx
+                // Walk the fixed 5x5 block backwards: funnel-shifting each coverage bit (sign of the OR clear) in from
+                // the right then leaves pixel (dx, dy) at bit 5*dy + dx - two instructions per pixel besides the adds.
+                uint32_t q0 = r0 + 4u * sB0 + 4u * sC0, q1 = r1 + 4u * sB1 + 4u * sC1, q2 = r2 + 4u * sB2 + 4u * sC2;
+                uint32_t m = 0;
                 #pragma unroll
-                for (int dy = 0; dy < 5; dy++) {
-                    uint32_t a0 = r0, a1 = r1, a2 = r2, row = 0;
+                for (int dy = 4; dy >= 0; dy--) {
+                    uint32_t a0 = q0, a1 = q1, a2 = q2;
                     #pragma unroll
-                    for (int dx = 0; dx < 5; dx++) {
-                        row |= (~(a0 | a1 | a2) >> 31) << dx;           // bit dx = pixel x0 + dx covered
-                        a0 += sB0; a1 += sB1; a2 += sB2;
+                    for (int dx = 4; dx >= 0; dx--) {
+                        m = __funnelshift_l(~(a0 | a1 | a2), m, 1);
+                        a0 -= sB0; a1 -= sB1; a2 -= sB2;
                     }
-                    m |= (dy < hgt ? (row & colMask) : 0u) << (5 * dy);
-                    r0 += sC0; r1 += sC1; r2 += sC2;
+                    q0 -= sC0; q1 -= sC1; q2 -= sC2;
                 }
+                m &= (colMask * 0x00108421u) & ((1u << (5 * hgt)) - 1u);    // the real box: wm1 + 1 columns of hgt rows
                 while (m) {
                     const uint32_t b = (uint32_t)__ffs(m) - 1u;
                     m &= m - 1u;
@@ -1123,6 +1126,64 @@ __device__ __forceinline__ void frame_done(const FrameParams& P)
     __threadfence_system();
 }
 
+// A 16x16 tile whose pixels were all decided by the direct (small-triangle) path: turn its keys, already in
+// registers, into depth / ids / colour and leave the key buffer clean for the next frame. One warp per tile.
+template <bool DEPTH_ONLY>             // true: the caller guarantees a depth-only frame without id capture (no shading code at all)
+__device__ __forceinline__ void resolve_tile_direct(const FrameParams& P, ulonglong2* gk2, const ulonglong2 (&kk)[4], int tx0, int ty0, int lane)
+{
+    if (tx0 >= P.width || ty0 >= P.height) return;
+    const ulonglong2 empty2 = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+    #pragma unroll
+    for (int b4 = 0; b4 < 4; b4++)
+        if (kk[b4].x != KEY_EMPTY || kk[b4].y != KEY_EMPTY) gk2[b4 * 32 + lane] = empty2;
+    #pragma unroll 1
+    for (int b4 = 0; b4 < 4; b4++) {
+        // keys 2*lane and 2*lane + 1 of block b4 are two horizontally adjacent pixels
+        const int px = tx0 + (b4 & 1) * BLOCK_PX + ((2 * lane) & 7), py = ty0 + (b4 >> 1) * BLOCK_PX + ((2 * lane) >> 3);
+        if (py >= P.height || px >= P.width) continue;
+        const ulonglong2 kc = kk[b4];      // (dynamic index: kk[] has a local-memory copy; selecting from registers spills more)
+        if ((DEPTH_ONLY || (P.shader == SH_DEPTH_ONLY && !P.captureIds)) && px + 1 < P.width) {
+            const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);
+            const float d0 = kc.x != KEY_EMPTY ? key_depth(kc.x) : 1.0f, d1 = kc.y != KEY_EMPTY ? key_depth(kc.y) : 1.0f;
+            if ((at & 1) == 0) *reinterpret_cast<float2*>(P.depth + at) = make_float2(d0, d1);
+            else { P.depth[at] = d0; P.depth[at + 1] = d1; }
+        } else if (DEPTH_ONLY) {
+            const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);      // last column of an odd width
+            P.depth[at] = kc.x != KEY_EMPTY ? key_depth(kc.x) : 1.0f;
+        } else {
+            resolve_pixel(P, kc.x, px, py);
+            if (px + 1 < P.width) resolve_pixel(P, kc.y, px + 1, py);
+        }
+    }
+}
+
+// The same resolve as a kernel of its own, launched before tile_kernel when the previous frame had nothing on the
+// tile path (dense meshes of small triangles: C1, C2, most of C4). It does the work only if this frame has nothing
+// there either; tile_kernel then finds leanResolve set and just ends the frame. Why: tile_kernel's CTAs own half an
+// SM each (512 threads x 64 registers, 97 KB of shared memory) even when all they do is this latency-bound pass, so
+// nothing else - in particular the geometry kernel of another frame in flight - can share the SM with them. This
+// kernel has no shared memory and small CTAs. MEASURED (C2, B200): one frame at a time 59.5 -> 59.5 us, C1 46 -> 43.8 us,
+// but with three frames in flight 45.0 -> 49.0 us - the extra launch and tile_kernel's 510 empty CTAs cost more
+// than the co-residency wins. Off by default (`edx_set_option("lean_resolve", 1 | 2)`).
+template <bool DEPTH_ONLY>
+__global__ void __launch_bounds__(256) lean_resolve_kernel(const __grid_constant__ FrameParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t tileG = blockIdx.x * 8u + (threadIdx.x >> 5);
+    const uint32_t bin = tileG >> 4, warp = tileG & 15u;
+    cudaGridDependencySynchronize();
+    if (bin >= (uint32_t)(P.binsX * P.binsY)) return;
+    if (P.parts > 1 && bin % (uint32_t)P.parts != (uint32_t)P.part) return;
+    const uint32_t bx = bin % (uint32_t)P.binsX, by = bin / (uint32_t)P.binsX;
+    const int tx0 = ((int)bx << BIN_LOG2) + (int)(warp & 3u) * TILE_PX, ty0 = ((int)by << BIN_LOG2) + (int)(warp >> 2) * TILE_PX;
+    ulonglong2* gk2 = reinterpret_cast<ulonglong2*>(P.keys + (size_t)bin * KEYS_PER_BIN + warp * 256u);
+    ulonglong2 kk[4];
+    #pragma unroll
+    for (int b4 = 0; b4 < 4; b4++) kk[b4] = gk2[b4 * 32 + lane];
+    if (min(P.counters->nBig, P.bigCap) != 0) return;           // the tile path has work: tile_kernel does everything
+    resolve_tile_direct<DEPTH_ONLY>(P, gk2, kk, tx0, ty0, lane);
+}
+
 #ifdef EDX_DEBUG_STATS
 __device__ uint32_t g_tileResident[512];       // [sm] live tile_kernel CTAs, [256 + sm] the most seen at once
 struct ResidentScope {
@@ -1164,6 +1225,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     }
     unsigned long long* gkeys = P.keys + (size_t)sId * P.keyStride + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
     if (ms && min(P.counters->nBig, P.bigCap) == 0) return;      // nothing on the tile path: the keys are already final
+    if (!MS && P.leanResolve && min(P.counters->nBig, P.bigCap) == 0) { frame_done(P); return; }   // lean_resolve_kernel has resolved the frame
     // the tile's keys are wanted on every path: issue the loads (16 bytes per lane, linear key order) before
     // the (dependent) counter read
     ulonglong2* gk2 = reinterpret_cast<ulonglong2*>(gkeys);
@@ -1174,27 +1236,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     const ulonglong2 empty2 = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
 
     if (nBig == 0) {
-        // Nothing on the tile path: resolve straight from the L2-resident keys, no staging.
-        if (tx0 >= P.width || ty0 >= P.height) { frame_done(P); return; }
-        #pragma unroll
-        for (int b4 = 0; b4 < 4; b4++)
-            if (kk[b4].x != KEY_EMPTY || kk[b4].y != KEY_EMPTY) gk2[b4 * 32 + lane] = empty2;   // leave the buffer clean for the next frame
-        #pragma unroll 1
-        for (int b4 = 0; b4 < 4; b4++) {
-            // keys 2*lane and 2*lane + 1 of block b4 are two horizontally adjacent pixels
-            const int px = tx0 + (b4 & 1) * BLOCK_PX + ((2 * lane) & 7), py = ty0 + (b4 >> 1) * BLOCK_PX + ((2 * lane) >> 3);
-            if (py >= P.height || px >= P.width) continue;
-            const ulonglong2 kc = kk[b4];      // (dynamic index: kk[] has a local-memory copy; selecting from registers spills more)
-            if (P.shader == SH_DEPTH_ONLY && !P.captureIds && px + 1 < P.width) {
-                const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);
-                const float d0 = kc.x != KEY_EMPTY ? key_depth(kc.x) : 1.0f, d1 = kc.y != KEY_EMPTY ? key_depth(kc.y) : 1.0f;
-                if ((at & 1) == 0) *reinterpret_cast<float2*>(P.depth + at) = make_float2(d0, d1);
-                else { P.depth[at] = d0; P.depth[at + 1] = d1; }
-            } else {
-                resolve_pixel(P, kc.x, px, py);
-                if (px + 1 < P.width) resolve_pixel(P, kc.y, px + 1, py);
-            }
-        }
+        // Nothing on the tile path: resolve straight from the L2-resident keys, no staging (unless
+        // lean_resolve_kernel has already done exactly that for this frame).
+        if (!P.leanResolve) resolve_tile_direct<false>(P, gk2, kk, tx0, ty0, lane);
         frame_done(P);
         return;
     }

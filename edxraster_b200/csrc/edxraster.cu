@@ -43,6 +43,7 @@ struct edx_context {
     int shader = EDX_SHADER_BLINN_PHONG;
     int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
     int smallMax = 32, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1, part = 0, parts = 1;
+    int leanResolve = 0;                     // 0 never (default: measured slower with frames in flight), 1 when the last vetted frame had an empty tile path, 2 always
     int clipCarveout = 0;                    // 0 auto (follow the tile path's load), 1 prefer L1, 2 prefer shared memory
     bool colorDirty = false;
 
@@ -199,16 +200,22 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     if (m->nTris) EDX_CUDA(c, launch(clip_kernel, dim3(148 * 4), dim3(128), 0));
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[2], c->stream));
     const bool textured = c->shader == EDX_SHADER_LAMBERT_ALBEDO && m->nTex != 0;
+    const bool lean = c->msaaLog2 == 0 && (c->leanResolve == 2 || (c->leanResolve == 1 && c->stats.binned_tris == 0));
+    P.leanResolve = lean ? 1 : 0;
+    const dim3 leanGrid((c->binsX * c->binsY * 16 + 7) / 8);
     if (c->msaaLog2 == 0 && textured) {
         // tile_kernel resolves depth + owner ids only; the colour pass is a kernel of its own (see its comment)
         FrameParams T = P;
         T.shader = EDX_SHADER_DEPTH_ONLY; T.captureIds = 1;
         std::swap(P, T);
+        if (lean) EDX_CUDA(c, launch(lean_resolve_kernel<false>, leanGrid, dim3(256), 0));      // (ids are captured: not the depth-only variant)
         EDX_CUDA(c, launch(tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
         std::swap(P, T);
         const uint32_t blocks = ((c->width + 7) / 8) * ((c->height + 7) / 8);
         EDX_CUDA(c, launch(textured_resolve_kernel, dim3((blocks + 3) / 4), dim3(256), 0));
     } else if (c->msaaLog2 == 0) {
+        if (lean && c->shader == EDX_SHADER_DEPTH_ONLY && !c->captureIds) EDX_CUDA(c, launch(lean_resolve_kernel<true>, leanGrid, dim3(256), 0));
+        else if (lean) EDX_CUDA(c, launch(lean_resolve_kernel<false>, leanGrid, dim3(256), 0));
         EDX_CUDA(c, launch(tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
     } else {
         // one CTA per (bin, sample), then the per-pixel resolve that also ends the frame
@@ -474,6 +481,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }
+    if (!strcmp(name, "lean_resolve")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "lean_resolve: 0 never, 1 auto, 2 always"); c->leanResolve = value; return EDX_OK; }
     if (!strcmp(name, "clip_carveout")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "clip_carveout: 0 auto, 1 L1, 2 shared"); c->clipCarveout = value; tune_clip_carveout(c, c->stats.tile_pairs); return EDX_OK; }
     return fail(c, EDX_ERR_INVALID, std::string("unknown option ") + name);
 }

@@ -38,7 +38,8 @@ def test_reduced_configs_bit_exact(name):
 @pytest.mark.parametrize("name", ["C1", "C3", "C4"])
 @pytest.mark.parametrize("options,hier", [({"hiz": 0}, True), ({}, False), ({"small_max": 0}, True),
                                           ({"small_max": 2}, True), ({"small_max": 40}, True),
-                                          ({"cluster_cull": 2, "pdl": 0}, True), ({"cluster_cull": 0, "small_max_clip": 0}, True)])
+                                          ({"cluster_cull": 2, "pdl": 0}, True), ({"cluster_cull": 0, "small_max_clip": 0}, True),
+                                          ({"lean_resolve": 0, "clip_carveout": 2}, True), ({"lean_resolve": 2, "clip_carveout": 1}, True)])
 def test_tuning_knobs_never_change_the_image(name, options, hier):
     # routing (direct vs tile path), hierarchical Z and the 8x8 block tests are pure optimisations
     assert_parity(REDUCED[name](), options=options, hierarchical=hier, stages=False)
