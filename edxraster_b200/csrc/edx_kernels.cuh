@@ -1103,15 +1103,14 @@ __device__ __forceinline__ void resolve_pixel(const FrameParams& P, unsigned lon
         P.color[at] = hit ? shade_pixel(P, key_prim(key), px, py) : make_uchar4(0, 0, 0, 0);
 }
 
-// End-of-frame hand-off, called once per CTA when it is done: the last CTA publishes the frame's counters
-// to pinned host memory (the host checks them for queue overflow) and zeroes them for the next frame, so a
-// frame needs no memset before and no copy after it. Every CTA has read nBig before it takes its ticket.
-__device__ __forceinline__ void frame_done(const FrameParams& P)
+// End of frame: a one-thread kernel behind the frame's last kernel publishes the counters to pinned host memory
+// (the host checks them for queue overflow) and zeroes them for the next frame, so a frame needs no memset before
+// and no copy after it. (It used to be a ticket taken by every tile_kernel CTA - fence, atomic, last one publishes;
+// that kept each CTA, i.e. half an SM, alive 2-3 us longer than its work.)
+__global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
 {
-    __syncthreads();
+    cudaGridDependencySynchronize();
     if (threadIdx.x != 0) return;
-    __threadfence();
-    if (atomicAdd(&P.counters->done, 1u) != gridDim.x * gridDim.y - 1u) return;
     volatile Counters* d = P.counters;
     const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs;
 #ifdef EDX_DEBUG_STATS
@@ -1220,12 +1219,11 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
     cudaGridDependencySynchronize();
     if (P.parts > 1 && (uint32_t)bin % (uint32_t)P.parts != (uint32_t)P.part) {   // sort-first: not this context's bin
-        if (!ms) frame_done(P);
         return;
     }
     unsigned long long* gkeys = P.keys + (size_t)sId * P.keyStride + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
     if (ms && min(P.counters->nBig, P.bigCap) == 0) return;      // nothing on the tile path: the keys are already final
-    if (!MS && P.leanResolve && min(P.counters->nBig, P.bigCap) == 0) { frame_done(P); return; }   // lean_resolve_kernel has resolved the frame
+    if (!MS && P.leanResolve && min(P.counters->nBig, P.bigCap) == 0) return;   // lean_resolve_kernel has resolved the frame
     // the tile's keys are wanted on every path: issue the loads (16 bytes per lane, linear key order) before
     // the (dependent) counter read
     ulonglong2* gk2 = reinterpret_cast<ulonglong2*>(gkeys);
@@ -1239,7 +1237,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         // Nothing on the tile path: resolve straight from the L2-resident keys, no staging (unless
         // lean_resolve_kernel has already done exactly that for this frame).
         if (!P.leanResolve) resolve_tile_direct<false>(P, gk2, kk, tx0, ty0, lane);
-        frame_done(P);
         return;
     }
 
@@ -1385,7 +1382,6 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     __syncthreads();
     if (tid == 0) atomicAdd(&P.counters->dbg[7], (unsigned long long)(clock64() - tMark));
 #endif
-    frame_done(P);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1431,7 +1427,6 @@ __global__ void __launch_bounds__(256) msaa_resolve_kernel(const __grid_constant
             P.color[at] = make_uchar4(to_u8(fmul(acc[0], inv)), to_u8(fmul(acc[1], inv)), to_u8(fmul(acc[2], inv)), to_u8(fmul(acc[3], inv)));
         }
     }
-    frame_done(P);
 }
 
 

@@ -222,6 +222,7 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
         EDX_CUDA(c, launch(tile_kernel<true>, dim3(c->binsX * c->binsY, 1u << c->msaaLog2), dim3(TILE_THREADS), sizeof(TileShared)));
         EDX_CUDA(c, launch(msaa_resolve_kernel, dim3((c->keyStride + 255) / 256), dim3(256), 0));
     }
+    EDX_CUDA(c, launch(frame_end_kernel, dim3(1), dim3(32), 0));       // counters -> pinned host memory, reset for the next frame
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[3], c->stream));
     EDX_CUDA(c, cudaGetLastError());
     return EDX_OK;
