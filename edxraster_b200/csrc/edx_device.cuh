@@ -64,7 +64,7 @@ struct Counters {
     uint32_t nClipQueue;     // straddling triangles queued for the clipper
     uint32_t nClipRecs;      // fan-triangle records written by the clipper
     uint32_t nDump;
-    uint32_t done;           // tile_kernel CTAs that have finished (ticket for the end-of-frame hand-off)
+    uint32_t done;           // (unused since frame_end_kernel replaced the per-CTA ticket)
     // Never reset on the device: frames whose queues overflowed, and the largest demand seen. A caller may
     // submit several frames before the next synchronising call; that call learns from these whether any of
     // them (not just the last) was incomplete.
@@ -116,7 +116,7 @@ struct FrameParams {
     ClipRec* clipRecs; uint32_t clipRecCap;
     uint32_t* clipSlot;                  // per submitted triangle: first ClipRec of its polygon
     Counters* counters;
-    Counters* hostCounters;              // pinned, device-mapped: the frame's last CTA publishes the counters here
+    Counters* hostCounters;              // pinned, device-mapped: frame_end_kernel publishes the counters here
     uchar4* color; float* depth; uint32_t* ids;
     DumpRec* dumpBuf; uint32_t dumpCap;
 };
