@@ -1111,18 +1111,21 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
 {
     cudaGridDependencySynchronize();
     if (threadIdx.x != 0) return;
+    // every load first (nine independent L2 reads in flight), then the stores from registers; no fence: the host
+    // reads the pinned copy only after the stream has completed this kernel
     volatile Counters* d = P.counters;
     const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs;
+    uint32_t overFrames = d->overFrames;
+    const uint32_t maxBig = max(d->maxBig, nBig), maxClipQueue = max(d->maxClipQueue, nClipQueue), maxClipRecs = max(d->maxClipRecs, nClipRecs);
 #ifdef EDX_DEBUG_STATS
     for (int i = 0; i < 8; i++) { P.hostCounters->dbg[i] = P.counters->dbg[i]; P.counters->dbg[i] = 0; }
 #endif
+    if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap) overFrames++;
     d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->done = 0; d->tilePairs = 0;
-    if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap) d->overFrames = d->overFrames + 1u;
-    d->maxBig = max(d->maxBig, nBig); d->maxClipQueue = max(d->maxClipQueue, nClipQueue); d->maxClipRecs = max(d->maxClipRecs, nClipRecs);
+    d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs;
     volatile Counters* h = P.hostCounters;
     h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs;
-    h->overFrames = d->overFrames; h->maxBig = d->maxBig; h->maxClipQueue = d->maxClipQueue; h->maxClipRecs = d->maxClipRecs;
-    __threadfence_system();
+    h->overFrames = overFrames; h->maxBig = maxBig; h->maxClipQueue = maxClipQueue; h->maxClipRecs = maxClipRecs;
 }
 
 // A 16x16 tile whose pixels were all decided by the direct (small-triangle) path: turn its keys, already in

@@ -25,7 +25,7 @@ for w in ("C1", "C2", "C3", "C4"):
     per = {}
     for r in rows[1:]:
         per.setdefault(kname(r[ki]), []).append(float(r[vi].replace(",", "")))
-    frame = {k: sum(v[-3:]) / len(v[-3:]) for k, v in per.items() if k in ("geom_kernel", "clip_kernel", "tile_kernel")}
+    frame = {k: sum(v[-3:]) / len(v[-3:]) for k, v in per.items() if k in ("geom_kernel", "clip_kernel", "tile_kernel", "frame_end_kernel")}
     tot = sum(frame.values()) or 1
     lines += ["## %s launch list (ns per launch, mean of last 3 frames)" % w, "", "| kernel | ns | share of frame |", "|---|---|---|"]
     for k, v in frame.items():
@@ -67,8 +67,8 @@ if os.path.exists(bl):
     h = rows[0]
     ki, vi, si = h.index("Kernel Name"), h.index("Metric Value"), h.index("Stream")
     md = ["# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-extra` (%s)" % tag, "",
-          "`ncu --metrics gpu__time_duration.sum --clock-control none -s 3030 -c 60 --csv python bench.py --steps 2 --warmup 1 --no-extra`",
-          "(-s 3030 skips the mesh uploads and most of the 1008 warm-up frames; the window covers the end of the warm-up, the two",
+          "`ncu --metrics gpu__time_duration.sum --clock-control none -s 4040 -c 80 --csv python bench.py --steps 2 --warmup 1 --no-extra`",
+          "(-s 4040 skips the mesh uploads and most of the 1008 warm-up frames; the window covers the end of the warm-up, the two",
           "timed frames with 3 frames in flight - three lanes = three streams - then the warm-up and the two timed frames of the",
           "one-frame-in-flight pass and the first end-to-end steps with their mesh re-upload kernels). Times are cold-cache and",
           "serialised by ncu: compare shares, not absolutes. Every kernel is ours; no library kernel runs in a step.", "",
@@ -80,8 +80,8 @@ if os.path.exists(bl):
         md.append("| %d | %s | %s | %.0f |" % (n, r[si], k, v))
         tot.setdefault(k, []).append(v)
     md += ["", "| kernel | launches | mean ns | share of the frame kernels |", "|---|---|---|---|"]
-    fsum = sum(sum(v) / len(v) for k, v in tot.items() if k in ("geom_kernel", "clip_kernel", "tile_kernel")) or 1
+    fsum = sum(sum(v) / len(v) for k, v in tot.items() if k in ("geom_kernel", "clip_kernel", "tile_kernel", "frame_end_kernel")) or 1
     for k, v in tot.items():
-        share = "%.1f %%" % (100 * (sum(v) / len(v)) / fsum) if k in ("geom_kernel", "clip_kernel", "tile_kernel") else ""
+        share = "%.1f %%" % (100 * (sum(v) / len(v)) / fsum) if k in ("geom_kernel", "clip_kernel", "tile_kernel", "frame_end_kernel") else ""
         md.append("| %s | %d | %.0f | %s |" % (k, len(v), sum(v) / len(v), share))
     open(os.path.join(out, "%s_bench_launches.md" % tag), "w").write("\n".join(md) + "\n")
