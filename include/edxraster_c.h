@@ -179,11 +179,15 @@ int edx_get_stats(edx_context* ctx, edx_stats* out);
  * geometry / clip kernels, defaults 32 / 8),
  * "hiz" (hierarchical-Z culling of the tile path, default 1), "cluster_cull" (frustum-cull 256-triangle
  * clusters: 0 off, 1 = only for meshes whose triangle order is spatially coherent (default), 2 always),
- * "pdl" (programmatic dependent launch, default 1). None of them changes a pixel. */
+ * "pdl" (programmatic dependent launch, default 1), "fuse_clip" (clip single-plane straddlers inside the geometry
+ * kernel, default 0), "clip_carveout" (shared-memory carve-out the clipper asks for: 0 = follow the tile path's load
+ * (default), 1 = prefer L1, 2 = prefer shared memory), "lean_resolve" (shared-memory-free resolve
+ * kernel ahead of the tile kernel: 0 never (default), 1 when the last vetted frame had an empty tile path, 2 always).
+ * None of them changes a pixel. */
 int edx_set_option(edx_context* ctx, const char* name, int value);
-/* number of kernel launches issued by the last RenderMesh (for bench.py's gpu_launches) */
 /* diagnostics: CTAs of the tile kernel's shape (512 threads, 97 KB shared memory) an SM holds at once (expected 2) */
 int edx_debug_tile_residency(edx_context* ctx, int* ctas_per_sm);
+/* number of kernel launches issued by the last RenderMesh (for bench.py's gpu_launches) */
 int edx_last_launch_count(const edx_context* ctx);
 
 #ifdef __cplusplus
