@@ -443,3 +443,36 @@ def test_texture_api_errors_and_replacement():
     assert np.abs(got.astype(np.int32) - ref["color"].astype(np.int32)).max() <= 1
     m.Release()
     r.close()
+
+
+def test_farm_render_views_through_a_frame_ring_into_torch_tensors():
+    # the frame farm's per-rank loop (farm.render_views) with three views in flight, rendering straight into the
+    # torch tensors a gather would send
+    import copy
+    import torch
+    from edxraster_b200 import farm, renderer as R
+    base = scenes.by_name("C4", 0.01)
+    views = scenes.config5_views(base, 5)
+    ring = R.FrameRing(0, depth=3)
+    ring.Initialize(base.width, base.height)
+    ring.SetPixelShader(base.shader)
+    mesh = ring.CreateMesh(base.vertices, base.indices)
+    dev = torch.device("cuda", 0)
+    out = torch.zeros((len(views), base.height, base.width, 4), dtype=torch.uint8, device=dev)
+    farm.render_views(ring, mesh, [R.PackedTransform(*v) for v in views], out, shaded=True)
+    got = out.cpu().numpy()
+    single = R.Renderer(0)
+    single.Initialize(base.width, base.height)
+    single.SetPixelShader(base.shader)
+    out1 = torch.zeros_like(out)
+    farm.render_views(single, mesh, views, out1, shaded=True)          # the shared mesh, one frame at a time, plain matrices
+    np.testing.assert_array_equal(got, out1.cpu().numpy())
+    for k, v in enumerate(views):
+        sc = copy.copy(base)
+        sc.mv, sc.proj, sc.raster = v
+        ref = parity.render_oracle(sc)
+        assert np.abs(got[k].astype(np.int32) - ref["color"].astype(np.int32)).max() <= 1, k
+    assert len({g.tobytes() for g in got}) == len(views)
+    mesh.Release()
+    single.close()
+    ring.close()
