@@ -505,7 +505,7 @@ int edx_mesh_create(edx_context* c, const void* vertices, uint32_t nv, const uin
     if (e != cudaSuccess) { edx_mesh_destroy(c, m); return fail(c, EDX_ERR_OOM, cudaGetErrorString(e)); }
     if (int r = upload_mesh(c, m, vertices, nv, indices, nt)) { edx_mesh_destroy(c, m); return r; }
     if (tex_ids && nt) {                 // Mesh::GetTextureIds (Mesh.h:58): kept until edx_mesh_set_textures passes its own
-        if (cudaMalloc(&m->texIds, (size_t)nt * 4) != cudaSuccess ||
+        if (cudaMalloc(&m->texIds, (size_t)m->capTris * 4) != cudaSuccess ||
             cudaMemcpyAsync(m->texIds, tex_ids, (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
             edx_mesh_destroy(c, m);
             return fail(c, EDX_ERR_OOM, "texture id upload failed");
@@ -605,7 +605,9 @@ int edx_mesh_set_textures(edx_context* c, edx_mesh* m, const edx_texture_desc* t
         }
     }
     if (tri_tex_ids && m->nTris) {
-        EDX_CUDA(c, cudaMalloc(&m->texIds, (size_t)m->nTris * 4));
+        // sized for the mesh's capacity (edx_mesh_update may raise the triangle count later); the rest reads slot 0
+        EDX_CUDA(c, cudaMalloc(&m->texIds, (size_t)m->capTris * 4));
+        EDX_CUDA(c, cudaMemsetAsync(m->texIds, 0, (size_t)m->capTris * 4, c->stream));
         EDX_CUDA(c, cudaMemcpyAsync(m->texIds, tri_tex_ids, (size_t)m->nTris * 4, cudaMemcpyHostToDevice, c->stream));
     }
     EDX_CUDA(c, cudaGetLastError());
