@@ -1,6 +1,6 @@
 // headless_viewer.cpp — the reference's RealtimeViewer (RealtimeViewer/Main.cpp) without the window:
 // same calls in the same order (OnInit :32-62, OnRender :65-75), frames go to a BMP instead of
-// glDrawPixels. Usage: headless_viewer [frames] [out.bmp] [dump.bin] [mesh.obj] [msaa_log2] [frames_in_flight] [texture_filter]
+// glDrawPixels. Usage: headless_viewer [frames] [out.bmp] [dump.bin] [mesh.obj] [msaa_log2] [frames_in_flight] [texture_filter] [mtl]
 // With frames_in_flight > 1 the loop keeps that many frames on the GPU (FrameRing) and reads each back in order.
 #include <chrono>
 #include <cstdio>
@@ -43,10 +43,12 @@ int main(int argc, char** argv)
                 _byte* p = &tex[4 * (y * 64 + x)];
                 p[0] = (_byte)((x * 37 + y * 11) & 255); p[1] = (_byte)(((x / 4 + y / 4) & 1) ? 230 : 40); p[2] = (_byte)((x * y * 3) & 255); p[3] = 255;
             }
-        mesh.AddImageTexture(tex.data(), 64, 32);
-        std::vector<uint> ids(mesh.GetIndexBuffer()->GetTriangleCount());
-        for (size_t i = 0; i < ids.size(); i++) ids[i] = (i / 5) % 2 ? (uint)(mesh.GetTextureCount() - 1) : 0u;      // image / the mesh's first slot
-        mesh.SetTextureIds(ids);
+        if (argc <= 8) {                           // argv[8] ("mtl"): keep the textures and slots the OBJ's materials gave the mesh
+            mesh.AddImageTexture(tex.data(), 64, 32);
+            std::vector<uint> ids(mesh.GetIndexBuffer()->GetTriangleCount());
+            for (size_t i = 0; i < ids.size(); i++) ids[i] = (i / 5) % 2 ? (uint)(mesh.GetTextureCount() - 1) : 0u;      // image / the mesh's first slot
+            mesh.SetTextureIds(ids);
+        }
         renderer.SetPixelShader(PixelShaderKind::LambertianAlbedo);
         renderer.SetTextureFilter(TextureFilter(std::atoi(argv[7])));                       // Main.cpp:108
     }
@@ -99,6 +101,18 @@ int main(int argc, char** argv)
         std::fwrite(camera.GetRasterMatrix().Data(), 4, 16, f);
         std::fwrite(mesh.GetVertexBuffer()->GetBuffer(), 32, hdr[2], f);
         std::fwrite(mesh.GetIndexBuffer()->GetBuffer(), 12, hdr[3], f);
+        // trailer: the mesh's texture table and per-triangle slots (count; per slot kind, colour, size, texels; ids)
+        const uint32_t nTex = (uint32_t)mesh.GetTextureCount();
+        std::fwrite(&nTex, 4, 1, f);
+        for (uint32_t k = 0; k < nTex; k++) {
+            int kind; float color[3]; uint w, h; const _byte* px;
+            mesh.GetTexture(k, kind, color, w, h, px);
+            std::fwrite(&kind, 4, 1, f); std::fwrite(color, 4, 3, f); std::fwrite(&w, 4, 1, f); std::fwrite(&h, 4, 1, f);
+            if (kind == EDX_TEXTURE_IMAGE) std::fwrite(px, 4, (size_t)w * h, f);
+        }
+        const uint32_t nIds = (uint32_t)mesh.GetTextureIds().size();
+        std::fwrite(&nIds, 4, 1, f);
+        std::fwrite(mesh.GetTextureIds().data(), 4, nIds, f);
         std::fclose(f);
     }
     return 0;

@@ -215,7 +215,11 @@ public:
     // Mesh::LoadMesh (Utils/Mesh.cpp:11-34): Wavefront OBJ. The reference delegates to EDXUtil's ObjMesh (absent);
     // this reader handles v / vt / vn / f (polygons fanned, negative indices, v, v/vt, v//vn, v/vt/vn), builds one
     // vertex per distinct index triple, computes area-weighted normals when the file has none, and applies
-    // scale, then rotation (degrees, about x then y then z), then translation. Materials map to texture id 0.
+    // scale, then rotation (degrees, about x then y then z), then translation. Materials (Mesh.cpp:22-31): `mtllib` files
+    // are read for `newmtl` / `Kd` / `map_Kd`; every material becomes one texture slot in file order - an
+    // ImageTexture when map_Kd names a readable uncompressed 24/32-bit BMP (the only decoder here; EDXUtil's image
+    // loaders are absent), else a ConstantTexture2D of Kd - and every face carries the slot of the `usemtl` in force
+    // (Mesh::GetTextureIds). A file without materials gets one constant 0.9 white slot like LoadSphere.
     bool LoadMesh(const Vector3& pos, const Vector3& scl, const Vector3& rot, const char* path)
     {
         FILE* f = std::fopen(path, "r");
@@ -225,9 +229,31 @@ public:
         std::vector<Vertex_PositionNormalTex> verts;
         std::vector<uint> idx;
         std::map<std::tuple<int, int, int>, uint> seen;
+        struct Material { std::string name; float kd[3] = { 0.9f, 0.9f, 0.9f }; std::string map; };
+        std::vector<Material> mats;
+        std::vector<uint> faceSlot;                        // per triangle
+        uint curSlot = 0;
+        const std::string dir = DirOf(path);
         char line[1024];
         while (std::fgets(line, sizeof(line), f)) {
-            if (line[0] == 'v' && line[1] == ' ') { Vector3 v; if (std::sscanf(line + 2, "%f %f %f", &v.x, &v.y, &v.z) == 3) P.push_back(v); }
+            if (!std::strncmp(line, "mtllib ", 7)) {
+                FILE* mf = std::fopen((dir + Trim(line + 7)).c_str(), "r");
+                if (mf) {
+                    char ml[1024];
+                    while (std::fgets(ml, sizeof(ml), mf)) {
+                        char* q = ml; while (*q == ' ' || *q == '\t') q++;
+                        if (!std::strncmp(q, "newmtl ", 7)) { mats.emplace_back(); mats.back().name = Trim(q + 7); }
+                        else if (!mats.empty() && !std::strncmp(q, "Kd ", 3)) std::sscanf(q + 3, "%f %f %f", &mats.back().kd[0], &mats.back().kd[1], &mats.back().kd[2]);
+                        else if (!mats.empty() && !std::strncmp(q, "map_Kd ", 7)) mats.back().map = Trim(q + 7);
+                    }
+                    std::fclose(mf);
+                }
+            }
+            else if (!std::strncmp(line, "usemtl ", 7)) {
+                const std::string name = Trim(line + 7);
+                for (size_t k = 0; k < mats.size(); k++) if (mats[k].name == name) curSlot = (uint)k;
+            }
+            else if (line[0] == 'v' && line[1] == ' ') { Vector3 v; if (std::sscanf(line + 2, "%f %f %f", &v.x, &v.y, &v.z) == 3) P.push_back(v); }
             else if (line[0] == 'v' && line[1] == 'n') { Vector3 v; if (std::sscanf(line + 3, "%f %f %f", &v.x, &v.y, &v.z) == 3) N.push_back(v); }
             else if (line[0] == 'v' && line[1] == 't') { Vector2 v; if (std::sscanf(line + 3, "%f %f", &v.x, &v.y) >= 1) T.push_back(v); }
             else if (line[0] == 'f' && line[1] == ' ') {
@@ -255,7 +281,7 @@ public:
                     }
                     poly.push_back(it->second);
                 }
-                for (size_t k = 2; k < poly.size(); k++) { idx.push_back(poly[0]); idx.push_back(poly[k - 1]); idx.push_back(poly[k]); }
+                for (size_t k = 2; k < poly.size(); k++) { idx.push_back(poly[0]); idx.push_back(poly[k - 1]); idx.push_back(poly[k]); faceSlot.push_back(curSlot); }
             }
         }
         std::fclose(f);
@@ -281,7 +307,59 @@ public:
             v.Normal = rotate(v.Normal);
         }
         SetBuffers(verts.data(), verts.size(), idx.data(), idx.size() / 3);
+        if (mats.empty()) AddConstantTexture(0.9f, 0.9f, 0.9f);
+        for (const Material& m : mats) {
+            std::vector<_byte> texels; uint tw = 0, th = 0;
+            if (!m.map.empty() && LoadBmp((dir + m.map).c_str(), texels, tw, th)) AddImageTexture(texels.data(), tw, th);
+            else AddConstantTexture(m.kd[0], m.kd[1], m.kd[2]);
+        }
+        SetTextureIds(faceSlot);
         return true;
+    }
+    // Uncompressed 24- or 32-bit BMP -> RGBA8, first row = top of the picture (v = 0 at the top, the D3D convention
+    // the reference's raster space uses). Stands in for EDXUtil's bitmap loader behind ImageTexture (Mesh.cpp:27).
+    static bool LoadBmp(const char* path, std::vector<_byte>& rgba, uint& w, uint& h)
+    {
+        FILE* f = std::fopen(path, "rb");
+        if (!f) return false;
+        unsigned char hd[54];
+        bool ok = std::fread(hd, 1, 54, f) == 54 && hd[0] == 'B' && hd[1] == 'M';
+        auto u32 = [&](int o) { return (uint32_t)hd[o] | ((uint32_t)hd[o + 1] << 8) | ((uint32_t)hd[o + 2] << 16) | ((uint32_t)hd[o + 3] << 24); };
+        const uint32_t off = ok ? u32(10) : 0;
+        const int32_t bw = ok ? (int32_t)u32(18) : 0, bh = ok ? (int32_t)u32(22) : 0;
+        const int bpp = ok ? (hd[28] | (hd[29] << 8)) : 0;
+        ok = ok && u32(30) == 0 && (bpp == 24 || bpp == 32) && bw > 0 && bh != 0 && bw <= 32768 && std::abs(bh) <= 32768;
+        if (ok) {
+            w = (uint)bw; h = (uint)std::abs(bh);
+            const size_t stride = ((size_t)w * (bpp / 8) + 3) & ~(size_t)3;
+            std::vector<unsigned char> row(stride);
+            rgba.assign((size_t)w * h * 4, 255);
+            ok = std::fseek(f, (long)off, SEEK_SET) == 0;
+            for (uint y = 0; ok && y < h; y++) {
+                ok = std::fread(row.data(), 1, stride, f) == stride;
+                const uint dy = bh > 0 ? h - 1 - y : y;                   // positive height = bottom-up file
+                for (uint x = 0; ok && x < w; x++) {
+                    const unsigned char* p = &row[(size_t)x * (bpp / 8)];
+                    _byte* o = &rgba[4 * ((size_t)dy * w + x)];
+                    o[0] = p[2]; o[1] = p[1]; o[2] = p[0]; o[3] = bpp == 32 ? p[3] : 255;
+                }
+            }
+        }
+        std::fclose(f);
+        return ok;
+    }
+    static std::string Trim(const char* s)
+    {
+        std::string t(s);
+        while (!t.empty() && (t.back() == '\n' || t.back() == '\r' || t.back() == ' ' || t.back() == '\t')) t.pop_back();
+        size_t b = 0; while (b < t.size() && (t[b] == ' ' || t[b] == '\t')) b++;
+        return t.substr(b);
+    }
+    static std::string DirOf(const char* path)
+    {
+        const std::string p(path);
+        const size_t k = p.find_last_of("/\\");
+        return k == std::string::npos ? std::string() : p.substr(0, k + 1);
     }
     // raw submission in the reference's wire format (CreateVertexBuffer / CreateIndexBuffer)
     void SetBuffers(const void* vertices, size_t vertexCount, const uint* indices, size_t triCount)
@@ -312,6 +390,12 @@ public:
     }
     void SetTextureIds(const std::vector<uint>& perTriangle) { mTexIdx = perTriangle; mTexDirty = true; }
     size_t GetTextureCount() const { return mTextures.size(); }
+    void GetTexture(size_t slot, int& kind, float color[3], uint& width, uint& height, const _byte*& texels) const
+    {
+        const Texture& t = mTextures[slot];
+        kind = t.kind; color[0] = t.color[0]; color[1] = t.color[1]; color[2] = t.color[2];
+        width = t.width; height = t.height; texels = t.texels.data();
+    }
     void Release()
     {
         if (mDevice) ReleaseDevice();

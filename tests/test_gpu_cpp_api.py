@@ -132,3 +132,71 @@ def test_textured_default_shader_through_the_cpp_api(tmp_path):
     pix = np.frombuffer(data, np.uint8, w * h * 3, off).reshape(h, w, 3)[..., ::-1]
     assert np.abs(pix.astype(np.int32) - ref[..., :3].astype(np.int32)).max() <= 1
     assert len(np.unique(pix.reshape(-1, 3), axis=0)) > 2000         # the image really is on the sphere
+
+
+def _write_bmp24(path, img):
+    """img: H x W x 3 uint8 RGB, row 0 = top. Classic bottom-up 24-bit BMP."""
+    h, w = img.shape[:2]
+    stride = (w * 3 + 3) & ~3
+    rows = b"".join(img[y, :, ::-1].tobytes() + b"\0" * (stride - w * 3) for y in range(h - 1, -1, -1))
+    hdr = b"BM" + struct.pack("<IHHI", 54 + len(rows), 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, w, h, 1, 24, 0, len(rows), 2835, 2835, 0, 0)
+    open(path, "wb").write(hdr + rows)
+
+
+def read_dump(dump):
+    raw = open(dump, "rb").read()
+    w, h, nv, nt = struct.unpack("4I", raw[:16])
+    mats = np.frombuffer(raw, np.float32, 48, 16).reshape(3, 4, 4)
+    verts = np.frombuffer(raw, np.float32, nv * 8, 16 + 192).reshape(nv, 8)
+    off = 16 + 192 + nv * 32
+    idx = np.frombuffer(raw, np.uint32, nt * 3, off).reshape(nt, 3)
+    off += nt * 12
+    ntex = struct.unpack_from("I", raw, off)[0]; off += 4
+    tex = []
+    for _ in range(ntex):
+        kind, r, g, b, tw, th = struct.unpack_from("i3f2I", raw, off); off += 24
+        if kind == 1:
+            tex.append(("image", np.frombuffer(raw, np.uint8, tw * th * 4, off).reshape(th, tw, 4))); off += tw * th * 4
+        else:
+            tex.append(("constant", (r, g, b)))
+    nids = struct.unpack_from("I", raw, off)[0]; off += 4
+    ids = np.frombuffer(raw, np.uint32, nids, off)
+    return w, h, mats, verts, idx, tex, ids
+
+
+def test_obj_materials_become_texture_slots(tmp_path):
+    # Mesh::LoadMesh (Utils/Mesh.cpp:22-31): one slot per material - ImageTexture for map_Kd, ConstantTexture2D(Kd)
+    # otherwise - and one slot id per face
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (8, 16, 3), dtype=np.uint8)
+    _write_bmp24(str(tmp_path / "tex.bmp"), img)
+    (tmp_path / "cube.mtl").write_text("newmtl red\nKd 0.8 0.2 0.1\nnewmtl img\nKd 1 1 1\nmap_Kd tex.bmp\n")
+    verts = "".join("v %d %d %d\n" % p for p in [(1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, -1, -1), (-1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1)])
+    vts = "vt 0 0\nvt 3 0\nvt 3 2\nvt 0 2\n"
+    faces = ["1 4 3 2", "5 6 7 8", "1 2 7 6", "2 3 8 7", "3 4 5 8", "4 1 6 5"]
+    body = "mtllib cube.mtl\n" + verts + vts
+    for k, fc in enumerate(faces):
+        body += "usemtl %s\n" % ("img" if k % 2 == 0 else "red")
+        body += "f " + " ".join("%s/%d" % (v, t + 1) for t, v in enumerate(fc.split())) + "\n"
+    obj = tmp_path / "cube.obj"
+    obj.write_text(body)
+    out, bmp, dump = run_viewer(tmp_path, [str(obj), "0", "1", "2", "mtl"])
+    assert "Triangle Count: 12" in out.stdout
+    w, h, mats, v, idx, tex, ids = read_dump(dump)
+    assert [t[0] for t in tex] == ["constant", "image"]
+    np.testing.assert_allclose(tex[0][1], (0.8, 0.2, 0.1), rtol=1e-6)
+    np.testing.assert_array_equal(tex[1][1][..., :3], img)                 # row 0 = top of the picture
+    assert (tex[1][1][..., 3] == 255).all()
+    np.testing.assert_array_equal(ids, np.repeat([1, 0, 1, 0, 1, 0], 2))   # two triangles per quad, slot of its usemtl
+    o = orc.Oracle(w, h, 0)
+    o.set_transform(mats[0], mats[1], mats[2])
+    o.set_shader(scenes.SHADER_LAMBERT_ALBEDO)
+    o.set_textures(tex, ids)
+    o.set_texture_filter(2)
+    o.render(v, idx)
+    ref = o.color()
+    data = open(bmp, "rb").read()
+    off = struct.unpack("<I", data[10:14])[0]
+    pix = np.frombuffer(data, np.uint8, w * h * 3, off).reshape(h, w, 3)[..., ::-1]
+    assert np.abs(pix.astype(np.int32) - ref[..., :3].astype(np.int32)).max() <= 1
+    assert len(np.unique(pix.reshape(-1, 3), axis=0)) > 500
