@@ -10,6 +10,7 @@
 // GetDepthBuffer, a device ordinal in the constructor, and status codes through LastStatus()/LastError()
 // (the reference has void returns and no error reporting).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -166,6 +167,9 @@ inline IndexBuffer* CreateIndexBuffer(const void* pData, size_t triCount)       
     std::memcpy(ib->GetBuffer(), pData, ib->GetBufferSize() * sizeof(uint));
     return ib;
 }
+
+// EDXUtil's BoundingBox as far as Mesh::GetBounds needs it (Utils/Mesh.h:26,63-66)
+struct BoundingBox { Vector3 mMin, mMax; };
 
 // ---- Utils/Mesh.h ----------------------------------------------------------------------------
 class Mesh {
@@ -371,6 +375,20 @@ public:
     }
     const IVertexBuffer* GetVertexBuffer() const { return mpVertexBuf.get(); }
     IndexBuffer* GetIndexBuffer() const { return mpIndexBuf.get(); }
+    // Mesh::GetBounds (Mesh.h:63-66): object-space bounds of the submitted vertices
+    BoundingBox GetBounds() const
+    {
+        BoundingBox b;
+        if (!mpVertexBuf || !mpVertexBuf->GetVertexCount()) return b;
+        const float* v = (const float*)mpVertexBuf->GetBuffer();
+        b.mMin = b.mMax = Vector3(v[0], v[1], v[2]);
+        for (uint i = 1; i < mpVertexBuf->GetVertexCount(); i++) {
+            const float* p = v + 8 * (size_t)i;
+            b.mMin = Vector3(std::min(b.mMin.x, p[0]), std::min(b.mMin.y, p[1]), std::min(b.mMin.z, p[2]));
+            b.mMax = Vector3(std::max(b.mMax.x, p[0]), std::max(b.mMax.y, p[1]), std::max(b.mMax.z, p[2]));
+        }
+        return b;
+    }
     const std::vector<uint>& GetTextureIds() const { return mTexIdx; }
     // Mesh::mTextures (Mesh.h:23): ConstantTexture2D<Color>(colour) or ImageTexture<Color, Color4b> (Mesh.cpp:27,29).
     // The reference decodes image files through EDXUtil; here the caller hands over decoded RGBA8 texels (row 0 at
@@ -413,6 +431,15 @@ private:
     std::vector<uint> mTexIdx;
     mutable edx_mesh* mDevice = nullptr;        // device copy, made on first RenderMesh
     mutable edx_context* mOwner = nullptr;
+};
+
+// ---- Core/Scene.h: an array of meshes the Renderer constructs and never reads (Renderer.cpp:35-38); kept API-shaped
+class Scene {
+public:
+    void AddMesh(Mesh* pMesh) { mMeshes.emplace_back(pMesh); }
+    size_t GetMeshCount() const { return mMeshes.size(); }
+private:
+    std::vector<std::unique_ptr<Mesh>> mMeshes;
 };
 
 enum class TextureFilter { Nearest = 0, Linear = 1, TriLinear = 2, Anisotropic4x = 3, Anisotropic8x = 4, Anisotropic16x = 5 };

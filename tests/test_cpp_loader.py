@@ -25,6 +25,9 @@ int main(int argc, char** argv) {
     }
     const float* v = (const float*)m.GetVertexBuffer()->GetBuffer();
     std::printf("\nv0 %.3f %.3f %.3f uv %.3f %.3f\n", v[0], v[1], v[2], v[6], v[7]);
+    const BoundingBox b = m.GetBounds();
+    std::printf("bounds %.3f %.3f %.3f .. %.3f %.3f %.3f\n", b.mMin.x, b.mMin.y, b.mMin.z, b.mMax.x, b.mMax.y, b.mMax.z);
+    Scene scene; scene.AddMesh(new Mesh); std::printf("scene %zu\n", scene.GetMeshCount());
     return 0;
 }
 '''
@@ -71,6 +74,8 @@ def test_obj_with_materials_and_bmp_textures(tmp_path):
     got = np.array(lines[5].split("texels")[1].split(), np.uint8).reshape(2, 2, 4)
     np.testing.assert_array_equal(got[..., :3], b)
     assert lines[6] == "v0 1.000 2.000 3.000 uv 0.250 0.500"             # scale, then translation
+    assert lines[7] == "bounds 1.000 2.000 3.000 .. 3.000 4.000 3.000"   # Mesh::GetBounds (Mesh.h:63-66)
+    assert lines[8] == "scene 1"
 
 
 def test_obj_without_materials_gets_the_constant_white_slot(tmp_path):
