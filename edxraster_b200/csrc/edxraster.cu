@@ -40,7 +40,7 @@ struct edx_context {
     // Renderer::SetTransform state (RenderStates.h:15-19)
     edx_host::Mat4 mv, mvInv, proj, mvp, raster;
     float eye[3], light[3], albedo[3];
-    int shader = EDX_SHADER_BLINN_PHONG;
+    int shader = EDX_SHADER_LAMBERT_ALBEDO;   // the reference installs LambertianAlbedoPixelShader (Renderer.cpp:41)
     int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
     int smallMax = 32, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1, part = 0, parts = 1;
     int leanResolve = 0;                     // 0 never (default: measured slower with frames in flight), 1 when the last vetted frame had an empty tile path, 2 always

@@ -86,7 +86,8 @@ int edx_set_texture_filter(edx_context* ctx, int filter);
 int edx_set_hierarchical_rasterize(edx_context* ctx, int enabled);
 /* Renderer::SetWriteFrames / WriteFrameToFile (Core/Renderer.h:50, Renderer.cpp:352-358): 24-bit BMP. */
 int edx_write_frame_to_file(edx_context* ctx, const char* path);
-/* extension */
+/* extension: the reference hard-codes LambertianAlbedoPixelShader (Core/Renderer.cpp:41), which is
+ * also the default here; its other shaders (Core/Shader.h:185-282) and a depth-only mode are selectable. */
 int edx_set_pixel_shader(edx_context* ctx, int shader);
 int edx_set_albedo(edx_context* ctx, float r, float g, float b);
 

@@ -476,3 +476,21 @@ def test_farm_render_views_through_a_frame_ring_into_torch_tensors():
     mesh.Release()
     single.close()
     ring.close()
+
+
+def test_default_state_is_the_reference_default():
+    # Renderer::Initialize installs LambertianAlbedoPixelShader (Renderer.cpp:41) and TriLinear (RenderStates.h:60);
+    # a mesh without textures is shaded with the constant 0.9 white of LoadSphere / LoadPlane (Mesh.cpp:47,66)
+    from edxraster_b200 import renderer as R
+    sc = scenes.config1(width=320, height=180, slices=24, stacks=24)
+    r = R.Renderer(0)
+    r.Initialize(sc.width, sc.height)
+    r.SetTransform(sc.mv, sc.proj, sc.raster)
+    m = r.CreateMesh(sc.vertices, sc.indices)
+    r.RenderMesh(m)
+    got = r.GetBackBuffer().copy()
+    ref = parity.render_oracle(sc, shader=scenes.SHADER_LAMBERT_ALBEDO)
+    assert np.abs(got.astype(np.int32) - ref["color"].astype(np.int32)).max() <= 1
+    assert (got[..., 3] == 255).sum() > 3000
+    m.Release()
+    r.close()
