@@ -53,3 +53,44 @@ def test_product_never_imports_the_oracle():
         p = os.path.join(ROOT, "include", fn)
         if os.path.isfile(p):
             assert "oracle" not in open(p).read()
+
+
+def test_null_handles_are_rejected_not_dereferenced():
+    """Every entry point given NULL handles returns an error status (or NULL) instead of crashing - 'never abort'
+    (errors). Runs without a GPU: nothing here reaches CUDA."""
+    lib = _lib.load()
+    f16 = (C.c_float * 16)()
+    buf = (C.c_float * 64)()
+    u = C.c_uint32(0)
+    n64 = C.c_uint64(0)
+    ms = C.c_float(0)
+    st = _lib.Stats()
+    tex = (_lib.TextureDesc * 1)()
+    out = C.c_void_p()
+    calls = {
+        "edx_initialize": (None, 64, 64), "edx_resize": (None, 64, 64), "edx_set_transform": (None, f16, f16, f16),
+        "edx_set_msaa_mode": (None, 1), "edx_set_texture_filter": (None, 1), "edx_set_hierarchical_rasterize": (None, 1),
+        "edx_write_frame_to_file": (None, b"/tmp/x.bmp"), "edx_set_pixel_shader": (None, 1), "edx_set_albedo": (None, 0.5, 0.5, 0.5),
+        "edx_mesh_create": (None, None, 0, None, 0, None, C.byref(out)), "edx_mesh_update": (None, None, None, 0, None, 0),
+        "edx_mesh_set_textures": (None, None, tex, 1, None), "edx_mesh_read_texture_level": (None, None, 0, 0, None, C.byref(u), C.byref(u)),
+        "edx_render_mesh": (None, None), "edx_synchronize": (None,), "edx_read_depth": (None, buf),
+        "edx_set_capture_ids": (None, 1), "edx_read_winner_ids": (None, C.cast(buf, C.POINTER(C.c_uint32))),
+        "edx_read_sample": (None, 0, buf, C.cast(buf, C.POINTER(C.c_uint32))), "edx_debug_clip_vertices": (None, None, buf),
+        "edx_debug_raster_triangles": (None, None, 0, C.cast(buf, C.POINTER(C.c_int32)), buf, C.byref(n64)),
+        "edx_get_derived_state": (None, f16, buf, buf), "edx_set_render_target": (None, None, None),
+        "edx_set_screen_partition": (None, 0, 1), "edx_set_stream": (None, None), "edx_timer_begin": (None,),
+        "edx_timer_end": (None, C.byref(ms)), "edx_set_profiling": (None, 1), "edx_get_stats": (None, C.byref(st)),
+        "edx_set_option": (None, b"hiz", 1), "edx_debug_tile_residency": (None, C.cast(C.byref(u), C.POINTER(C.c_int))),
+    }
+    for name, args in calls.items():
+        rc = getattr(lib, name)(*args)
+        assert rc < 0, (name, rc)
+    assert not lib.edx_get_back_buffer(None)
+    assert not lib.edx_device_color(None) and not lib.edx_device_depth(None)
+    assert lib.edx_last_launch_count(None) == 0
+    assert lib.edx_mesh_destroy(None, None) == 0          # destroying nothing is not an error
+    lib.edx_destroy(None)
+    lib.edx_last_error(None)
+    untested = set(_lib.SYMBOLS) - set(calls) - {"edx_get_back_buffer", "edx_device_color", "edx_device_depth", "edx_last_launch_count",
+                                                 "edx_mesh_destroy", "edx_destroy", "edx_last_error", "edx_version", "edx_create"}
+    assert not untested, untested
