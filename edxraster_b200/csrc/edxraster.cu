@@ -237,12 +237,13 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
 // seen in the last vetted frame. Purely a speed knob - results never depend on it.
 void tune_clip_carveout(edx_context* c, uint32_t tilePairs)
 {
-    static int current = -1;                                   // function attributes are per process
+    static int current[64];                                    // function attributes are per device (0 = not set yet)
     int want = c->clipCarveout == 0 ? (tilePairs > 100000u ? 2 : 1) : c->clipCarveout;
-    if (want == current) return;
+    int& cur = current[c->device & 63];
+    if (want == cur) return;
     cudaFuncSetAttribute(clip_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                          want == 2 ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
-    current = want;
+    cur = want;
 }
 
 // Wait for the pending frame; if a queue overflowed, grow it and run the frame again. Frames submitted earlier
