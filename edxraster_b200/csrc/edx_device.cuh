@@ -305,8 +305,10 @@ __device__ __forceinline__ uint32_t key_index(int x, int y, int binsX)
     return ((bin * 16u + tile) * 4u + block) * 64u + (uint32_t)((y & 7) * 8 + (x & 7));
 }
 
-// Sample positions of FrameBuffer::MultiSampleOffsets (FrameBuffer.cpp:107-191): (x, y) pairs in 1/16 pixel
-// relative to the pixel centre, one row per SetMSAAMode level. DESIGN.md shim 17 on how the pairs are read.
+// FrameBuffer::MultiSampleOffsets (FrameBuffer.cpp:107-191) as written: pairs in 1/16 pixel relative to the pixel
+// centre, one row per SetMSAAMode level. The reference reads ONE int per sample, [2 * sampleId], into a Vector2i
+// (Rasterizer.h:247,382), so sample s sits at (table[2s], table[2s]) and the second column is unused — DESIGN.md
+// shim 17, established by compiling the reference itself.
 __constant__ int c_sampleOffsets[6][64] = {
     { 0, 0 },
     { 4, 4, -4, -4 },

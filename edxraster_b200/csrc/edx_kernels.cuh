@@ -164,7 +164,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                     const uint32_t ki = key_index(x, y, P.binsX);
                     const bool owned = owns_pixel(x, y, P.binsX, P.part, P.parts);
                     for (int sId = 0; sId < P.samples; sId++) {
-                        const uint32_t ox = (uint32_t)off[2 * sId], oy = (uint32_t)off[2 * sId + 1];
+                        const uint32_t ox = (uint32_t)off[2 * sId], oy = ox;      // DESIGN.md shim 17: Vector2i(int) sets both components
                         const uint32_t f0 = a0 + ox * e.B0 + oy * e.C0, f1 = a1 + ox * e.B1 + oy * e.C1, f2 = a2 + ox * e.B2 + oy * e.C2;
                         if ((int)(f0 | f1 | f2) >= 0) {
                             float l0, l1;
@@ -1216,7 +1216,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     // coverage and depth at centre + offset, and leaves the keys in place for msaa_resolve_kernel.
     const bool ms = MS;
     const int sId = MS ? (int)blockIdx.y : 0;
-    const int offX = MS ? c_sampleOffsets[P.msLevel][2 * sId] : 0, offY = MS ? c_sampleOffsets[P.msLevel][2 * sId + 1] : 0;
+    const int offX = MS ? c_sampleOffsets[P.msLevel][2 * sId] : 0, offY = offX;      // DESIGN.md shim 17: Vector2i(int) sets both components
     const uint32_t bx = (uint32_t)(bin % P.binsX), by = (uint32_t)(bin / P.binsX);
     const int ox = (int)bx << BIN_LOG2, oy = (int)by << BIN_LOG2;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;

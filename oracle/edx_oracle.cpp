@@ -635,8 +635,10 @@ static inline __m128 ztest_quad(Oracle& o, __m128 d, int x, int y, int sId, __m1
 }
 
 // FrameBuffer.cpp:107-191. Offsets in 1/16 pixel relative to the pixel centre, (x, y) pairs.
-// shim 17: the reference binds `const Vector2i&` to element [2*sampleId] of this int table
-// (Rasterizer.h:247,382); we read that as the pair (table[2s], table[2s+1]) the table is written as.
+// shim 17: the reference binds `const Vector2i&` to ONE element, [2*sampleId], of this int table
+// (Rasterizer.h:247,382). That only compiles through a converting constructor Vector2i(int), which sets
+// both components to the value, so sample s sits at (table[2s], table[2s]) — the table's second column is
+// never read. Established by compiling the reference itself (oracle/_ref); round 1 read the written pairs.
 static const int kSampleOffsets[6][64] = {
     { 0, 0 },
     { 4, 4, -4, -4 },
@@ -756,7 +758,7 @@ static void fine_rasterize_ms(Oracle& o, Tile& tile, V2i bmin, V2i bmax, const R
             uint32_t mask[4] = { 0, 0, 0, 0 };
             bool gen = false;
             for (int sId = 0; sId < o.samples; sId++) {
-                const int ox = table[2 * sId], oy = table[2 * sId + 1];
+                const int ox = table[2 * sId], oy = table[2 * sId];      // shim 17
                 const __m128i vx = _mm_set1_epi32(ox), vy = _mm_set1_epi32(oy);
                 // e = edgeVal + off.x * B + off.y * C   (Rasterizer.h:248-250)
                 __m128i f0 = _mm_add_epi32(_mm_add_epi32(e0, _mm_mullo_epi32(vx, s.B0)), _mm_mullo_epi32(vy, s.C0));
@@ -803,7 +805,7 @@ static void trivial_accept_ms(Oracle& o, Tile& tile, V2i bmin, V2i bmax, const R
             uint32_t mask[4] = { 0, 0, 0, 0 };
             bool gen = false;
             for (int sId = 0; sId < o.samples; sId++) {
-                s.bary(_mm_add_epi32(cx, _mm_set1_epi32(table[2 * sId])), _mm_add_epi32(cy, _mm_set1_epi32(table[2 * sId + 1])));
+                s.bary(_mm_add_epi32(cx, _mm_set1_epi32(table[2 * sId])), _mm_add_epi32(cy, _mm_set1_epi32(table[2 * sId])));      // shim 17
                 covered += 4;
                 int vis = _mm_movemask_ps(ztest_quad(o, s.depth(z0, z1, z2), x, y, sId, all));
                 if (vis) { mask_set(mask, vis, sId); gen = true; }

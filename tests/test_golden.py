@@ -1,5 +1,6 @@
-"""Golden fixtures (tests/golden/): the oracle must keep reproducing them (CPU); the CUDA path must
-produce the same bits (GPU). See tests/golden/make_golden.py for how they were made."""
+"""Golden fixtures (tests/golden/), produced by the reference's own compiled sources (oracle/_ref): the restatement
+must reproduce them (CPU), the CUDA path must produce the same bits (GPU), and where the reference build is present
+it must still reproduce them itself. See tests/golden/make_golden.py for how they were made."""
 import hashlib
 import json
 import os
@@ -27,16 +28,21 @@ def digest(a):
 
 
 def check(name, out, color_exact):
+    """`out` from render_oracle / render_gpu (owner = prim id, set-up dump with a leading prim column)."""
     g = GOLDEN[name]
-    assert digest(out["depth"]) == g["depth_sha256"]
-    assert digest(out["winner"]) == g["winner_sha256"]
-    assert digest(out["clip"]) == g["clip_sha256"]
     ints, flts = out["tris"]
     assert ints.shape[0] == g["raster_tris"]
-    assert digest(ints) == g["raster_tri_ints_sha256"]
+    assert digest(out["depth"]) == g["depth_sha256"]
+    assert digest(parity.to_ordinal(out["winner"], ints)) == g["winner_ordinal_sha256"]
+    assert digest(out["clip"]) == g["clip_sha256"]
+    assert digest(ints[:, 1:]) == g["raster_tri_ints_sha256"]
     assert digest(flts) == g["raster_tri_floats_sha256"]
-    if color_exact:
+    if color_exact and g["color_sha256"]:
         assert digest(out["color"]) == g["color_sha256"]
+
+
+def test_fixtures_come_from_the_reference_build():
+    assert all("oracle/_ref" in v["source"] for v in ALL_GOLDEN.values())
 
 
 @pytest.mark.parametrize("name", sorted(GOLDEN))
@@ -44,13 +50,13 @@ def check(name, out, color_exact):
 def test_oracle_reproduces_golden(name, threads):
     out = parity.render_oracle(CASES[name], threads=threads)
     check(name, out, color_exact=True)
-    assert out["stats"]["covered_samples"] == GOLDEN[name]["covered_samples"]
+    assert out["stats"]["fragments"] == GOLDEN[name]["fragments"]
 
 
-def check_ms(name, out, color_exact):
+def check_ms(name, out, tri_ints, color_exact):
     g = GOLDEN_MS[name]
     assert digest(np.stack([d for d, _ in out["samples"]])) == g["sample_depth_sha256"]
-    assert digest(np.stack([w for _, w in out["samples"]])) == g["sample_winner_sha256"]
+    assert digest(np.stack([parity.to_ordinal(w, tri_ints) for _, w in out["samples"]])) == g["sample_winner_ordinal_sha256"]
     if color_exact:
         assert digest(out["color"]) == g["color_sha256"]
 
@@ -58,14 +64,32 @@ def check_ms(name, out, color_exact):
 @pytest.mark.parametrize("name", sorted(GOLDEN_MS))
 def test_oracle_reproduces_msaa_golden(name):
     sc, level = MS_CASES[name]
-    check_ms(name, parity.render_oracle(sc, threads=3, msaa=level), color_exact=True)
+    out = parity.render_oracle(sc, threads=3, msaa=level)
+    check_ms(name, out, out["tris"][0], color_exact=True)
+
+
+@pytest.mark.skipif(not parity.reference_available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("name", sorted(ALL_GOLDEN))
+def test_reference_build_reproduces_golden(name):
+    g = ALL_GOLDEN[name]
+    if "msaa_level" in g:
+        sc, level = MS_CASES[name]
+        ref = parity.render_reference(sc, threads=3, msaa=level)
+        assert digest(ref["color"]) == g["color_sha256"]
+        assert digest(np.stack([d for d, _ in ref["samples"]])) == g["sample_depth_sha256"]
+        assert digest(np.stack([w for _, w in ref["samples"]])) == g["sample_winner_ordinal_sha256"]
+    else:
+        ref = parity.render_reference(CASES[name], threads=3)
+        assert digest(ref["depth"]) == g["depth_sha256"] and digest(ref["winner_ord"]) == g["winner_ordinal_sha256"]
+        assert digest(ref["tris"][0]) == g["raster_tri_ints_sha256"] and digest(ref["tris"][1]) == g["raster_tri_floats_sha256"]
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(GOLDEN_MS))
 def test_cuda_matches_msaa_golden(name):
     sc, level = MS_CASES[name]
-    check_ms(name, parity.render_gpu(sc, msaa=level, stages=False), color_exact=False)
+    out = parity.render_gpu(sc, msaa=level, stages=True)
+    check_ms(name, out, out["tris"][0], color_exact=False)
 
 
 @pytest.mark.gpu
@@ -81,4 +105,4 @@ def test_cuda_matches_golden(name):
         d = np.abs(out["color"].astype(np.int32) - FRAMES["C1_small_color"].astype(np.int32))
         assert d.max() <= 1
         np.testing.assert_array_equal(out["depth"].view(np.uint32), FRAMES["C1_small_depth"].view(np.uint32))
-        np.testing.assert_array_equal(out["winner"], FRAMES["C1_small_winner"])
+        np.testing.assert_array_equal(parity.to_ordinal(out["winner"], out["tris"][0]), FRAMES["C1_small_winner_ord"])
