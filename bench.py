@@ -2,7 +2,7 @@
 """bench.py — headline benchmark of the B200-native EDXRaster raster hot path.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, one process per GPU)
-    python bench.py --impl reference --gpus N --steps K ...   # CPU reference arm (oracle on host cores)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU reference arm: the reference's own sources (oracle/_ref) on host cores
 
 Workload (BASELINE.json configs[1], "C2"): 1,000,000 random <=4-px triangles at 1920x1080, depth test
 only, fixed submission order. One step = one frame of the hot path (Renderer::RenderMesh,
@@ -14,8 +14,12 @@ keeps --in-flight (3) independent frames in flight: lanes = edx contexts on thei
 meshes; the events sit on a control stream that every lane waits on at the start and that waits on every
 lane at the end. The same loop with one frame in flight is reported next to it (`one_frame_in_flight`). Inputs are made larger than L2 by rotating over 4 device copies of the mesh
 (4 x 108 MB of SoA streams > 126 MB L2), so every frame reads its geometry from HBM. At N > 1 the
-frames are independent (weak scaling: one frame per rank per step) and the finished depth buffers
-are gathered to rank 0 over NCCL in batches of 8 frames, overlapped with the next batch's rendering.
+frames are independent (weak scaling: one frame per rank per step) and every finished depth buffer is pushed
+into rank 0's memory over NVLink as soon as it is rendered (copy engine, one notification per 4 frames).
+
+Every default run also measures BASELINE.json configs[4] (C5: 256 views of the 10M-triangle mesh, view i on GPU
+i mod N, every colour buffer gathered to rank 0 inside the timed region) -> `other_configs.C5`; at N = 1 the other
+configs ride along too, each with a same-run CPU baseline.
 
 Rank 0 prints ONE JSON line on stdout; everything else goes to stderr.
 """
@@ -145,26 +149,101 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm: the CPU restatement of the reference's SSE path on all host cores
+# the `config` block: built the same way by both arms, so the two lines describe the same workload key for key
 # ------------------------------------------------------------------------------------------------
-def cpu_frames(scene, threads, frames, warm, timing=True, tri_limit=None):
-    from oracle import orc
-    orc.build()
-    o = orc.Oracle(scene.width, scene.height, threads, timing=timing)
-    o.set_transform(scene.mv, scene.proj, scene.raster)
-    o.set_shader(scene.shader)
-    idx = scene.indices if tri_limit is None else scene.indices[:tri_limit]
-    for _ in range(warm):
-        o.render(scene.vertices, idx)
-    times = []
-    for _ in range(frames):
+def mesh_copies(nv, nt):
+    """GPU arm: inputs are kept larger than L2 by rotating over this many device copies of the mesh."""
+    return 4 if nv * 32 + nt * 12 < 200e6 else 1          # C4/C5: one 440 MB mesh already exceeds L2
+
+
+def config_block(name, nv, nt, w, h):
+    copies = mesh_copies(nv, nt)
+    return {"workload": WORKLOADS[name], "triangles": nt, "vertices": nv, "resolution": [w, h], "frames_per_step_per_gpu": 1,
+            "l2": "GPU arm: inputs larger than L2 - round-robin over %d device cop%s of the mesh (%d MB of SoA streams), nothing is "
+                  "flushed; CPU arm: host memory" % (copies, "ies" if copies > 1 else "y", copies * (nv * 32 + nt * 12) // 1000000)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own sources compiled against the EDXUtil stand-in (oracle/_ref, kind "reference");
+# the restatement (oracle/edx_oracle.cpp, kind "port") only where that library is absent
+# ------------------------------------------------------------------------------------------------
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+class CpuRenderer:
+    """One scene on the host cores. Timing builds: rsqrtps + one Newton step, as EDXUtil's Embree-style SSE::Rsqrt."""
+
+    def __init__(self, scene, threads):
+        from oracle import ref
+        self.scene = scene
+        self.kind = "reference" if ref.available() else "port"
+        if self.kind == "reference":
+            self.r = ref.Reference(scene.width, scene.height, threads, timing=True)
+            self.r.set_transform(scene.mv, scene.proj, scene.raster)
+            # the reference has Blinn-Phong and the textured Lambert shader only (Shader.h); a depth-only workload
+            # runs its default shader - more CPU work per fragment than the GPU arm does, noted in `note`
+            self.r.set_shader(scene.shader if scene.shader in (1, 3) else 3)
+            self.threads = max(self.r.threads, min(threads, host_threads()))      # OpenMP threads parallel_for really uses
+            self.note = ("oracle/_ref: the reference's own Core/*.cpp, Core/*.h, Utils/* compiled unmodified with g++ -O2 -msse4.1 "
+                         "-fopenmp against the EDXUtil stand-in (oracle/_ref_shim; SSE::Rsqrt = rsqrtps + Newton step); parallel_for on "
+                         "%d OpenMP threads, per-core lists capped at 12 (Tile.h:34)" % host_threads())
+            if scene.shader not in (1, 3):
+                self.note += "; the reference has no depth-only mode: its default LambertianAlbedo shader runs on every fragment"
+        else:
+            from oracle import orc
+            orc.build()
+            self.r = orc.Oracle(scene.width, scene.height, threads, timing=True)
+            self.r.set_transform(scene.mv, scene.proj, scene.raster)
+            self.r.set_shader(scene.shader)
+            self.threads = self.r.threads
+            self.note = "oracle/ timing build (CPU restatement of the reference SSE path); oracle/_ref is not present on this box"
+        self._tris = None
+
+    def set_view(self, view):
+        self.r.set_transform(*view)
+
+    def frame(self, tri_limit=None):
+        sc = self.scene
+        n = sc.num_tris if tri_limit is None else min(tri_limit, sc.num_tris)
         t = time.perf_counter()
-        o.render(scene.vertices, idx)
-        times.append(time.perf_counter() - t)
-    th = o.threads
-    st = o.stats()
-    o.close()
-    return times, th, int(idx.shape[0]), st
+        if self.kind == "reference":
+            if self._tris != n:
+                self.r.set_mesh(sc.vertices, sc.indices[:n])      # Mesh::LoadMesh copies, outside the timed call
+                self._tris = n
+                t = time.perf_counter()
+            self.r.render()
+        else:
+            self.r.render(sc.vertices, sc.indices[:n])
+        return time.perf_counter() - t, n
+
+    def close(self):
+        self.r.close()
+
+
+def cpu_baseline(scene, cpu_seconds=20.0, max_frames=40, views=None):
+    """Bounded sample of `scene` on the host cores: about `cpu_seconds` of CPU work (wall x threads)."""
+    c = CpuRenderer(scene, host_threads())
+    try:
+        c.frame()                                  # cold: page faults, mesh copy
+        probe, used = c.frame()
+        work = probe * c.threads
+        nfr = int(min(max_frames, max(1 if work > cpu_seconds else 3, round(cpu_seconds / max(work, 1e-6)))))
+        times = []
+        for k in range(nfr):
+            if views is not None:
+                c.set_view(views[(k * 37) % len(views)])
+            times.append(c.frame()[0])
+        while sum(times) < 0.5 and len(times) < 2000:       # tiny frames: at least half a second of wall time
+            times.append(c.frame()[0])
+        v = used * len(times) / sum(times) / 1e6
+        what = "full frames" if views is None else "views (every 37th of the 256, extrapolated to all)"
+        return {"value": v, "unit": "Mtris/s", "cores": c.threads, "kind": c.kind,
+                "sample": "%d %s of the same workload after 1 warm-up (%.3f s each, ~%.0f s of CPU work on %d threads)"
+                          % (len(times), what, sum(times) / len(times), sum(times) * c.threads, c.threads),
+                "frames_per_s": len(times) / sum(times), "note": c.note}
+    finally:
+        c.close()
 
 
 def reference_arm(args):
@@ -173,14 +252,22 @@ def reference_arm(args):
         return 0
     scene = make_scene(args.workload, args.scale)
     nt = scene.num_tris
+    views = scene.get("views")
+    c = CpuRenderer(scene, host_threads())     # explicit thread count: torchrun exports OMP_NUM_THREADS=1
     # calibrate: one full frame, then bound the per-step sample so K+W steps end within ~2 minutes
-    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    t_probe, threads, _, _ = cpu_frames(scene, ncpu, 1, 1)   # explicit count: torchrun exports OMP_NUM_THREADS=1
+    probe, _ = c.frame()
     budget = 120.0 / max(1, args.steps + args.warmup)
     limit = None
-    if t_probe[0] > budget:
-        limit = max(1000, int(nt * budget / t_probe[0]))
-    times, threads, used, st = cpu_frames(scene, ncpu, args.steps, min(args.warmup, 3), tri_limit=limit)
+    if probe > budget:
+        limit = max(1000, int(nt * budget / probe))
+    for _ in range(min(args.warmup, 3)):
+        c.frame(limit)
+    times, used = [], nt
+    for k in range(args.steps):
+        if views is not None:
+            c.set_view(views[k % len(views)])
+        dt, used = c.frame(limit)
+        times.append(dt)
     total = sum(times)
     value = used * len(times) / total / 1e6
     sample = ("full frames (%d triangles each)" % used) if limit is None else \
@@ -190,14 +277,13 @@ def reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 depth / i32 28.4 fixed-point coverage",
         "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "triangles": nt, "resolution": [scene.width, scene.height]},
+        "config": config_block(args.workload, scene.num_verts, nt, scene.width, scene.height),
         "frames_per_s": len(times) / total, "gpix_per_s": scene.width * scene.height * len(times) / total / 1e9,
-        "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "CPU restatement of the reference SSE path (oracle/, timing build: rsqrtps+NR, OpenMP); "
-                                 "the reference itself cannot be built offline (SURVEY.md F1/F2)"},
+        "cpu_baseline": {"value": value, "unit": "Mtris/s", "cores": c.threads, "kind": c.kind, "sample": sample, "note": c.note},
         "e2e": {"value": value, "unit": "Mtris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    c.close()
     print(json.dumps(line), flush=True)
     return 0
 
@@ -205,6 +291,9 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+NVLINK_INGRESS_GBS = 733.0      # one B200's NVLink receive rate as measured in round 1 (7 senders, copy engine); nominal 900
+
+
 def time_frames(r, meshes, frames, warm):
     """Device time of `frames` back-to-back frames (CUDA events on the context's stream)."""
     for i in range(warm):
@@ -216,17 +305,226 @@ def time_frames(r, meshes, frames, warm):
     return r.TimerEnd()
 
 
-def secondary_config(name, device, peak):
-    """Quick device-resident measurement of another BASELINE config (rank 0, N=1 only)."""
-    from edxraster_b200 import renderer as R
+class Farm:
+    """K independent frames in flight per GPU (lanes = edx contexts on their own streams sharing the meshes) and,
+    at N > 1, the gather of every finished frame into rank 0's memory.
+
+    Exchange (--gather ce, default): rank 0's receive buffer is symmetric memory mapped into every rank over
+    NVLink, and each lane's context has its slot of it as frame sink (edx_set_frame_sink): right behind a frame's
+    last kernel, on the lane's own stream, the COPY ENGINE pushes the finished buffer to rank 0 (no SM time, no host
+    work; nothing waits for a batch to fill, so the only transfer that cannot overlap rendering is the last
+    frame's). One 4-byte all-reduce per G frames tells rank 0 that they have landed and lets the lanes reuse the
+    buffers two batches later.
+    --gather nccl: dist.gather per batch of G frames. --gather stores: the resolve kernel writes its pixels straight
+    into rank 0's memory (measured slower: 32-byte row segments). --gather none: diagnosis only."""
+
+    def __init__(self, torch, dist, R, sc, local, rank, world, in_flight, mode, G, meshes=None):
+        self.torch, self.dist, self.R = torch, dist, R
+        self.sc, self.rank, self.world, self.G = sc, rank, world, G
+        self.dev = dev = torch.device("cuda", local)
+        W, H = sc.width, sc.height
+        self.shaded = sc.shader != 0
+        self.stream = torch.cuda.Stream(device=dev)       # timing events + the exchange
+        self.K = K = max(1, in_flight)
+        self.lanes = []
+        for _ in range(K):
+            ls = torch.cuda.Stream(device=dev)
+            lr = R.Renderer(local)
+            lr.SetStream(ls.cuda_stream)
+            lr.Initialize(W, H)
+            lr.SetTransform(sc.mv, sc.proj, sc.raster)
+            lr.SetPixelShader(sc.shader)
+            self.lanes.append((ls, lr))
+        self.r = self.lanes[0][1]
+        views = sc.get("views")
+        self.xf = R.PackedTransform(sc.mv, sc.proj, sc.raster)   # marshalled once; edx_set_transform still runs every step
+        self.views = None if views is None else [R.PackedTransform(*v) for v in views]
+        self.copies = mesh_copies(sc.num_verts, sc.num_tris)
+        self.own_meshes = meshes is None
+        self.meshes = meshes or [self.r.CreateMesh(sc.vertices, sc.indices) for _ in range(self.copies)]   # read-only while rendering: shared by the lanes
+        # render targets are torch tensors, double-buffered batches of G frames
+        self.tgt_color = [torch.zeros((G, H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.tgt_depth = [torch.zeros((G, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.result = self.tgt_color if self.shaded else self.tgt_depth
+        self.frame_bytes = W * H * 4
+        self.peer, self.recv, self.mode = None, None, mode
+        if world > 1 and mode in ("stores", "ce"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                sbuf = symm.empty((world, 2, G) + tuple(self.result[0].shape[1:]), dtype=self.result[0].dtype, device=dev)
+                hdl = symm.rendezvous(sbuf, dist.group.WORLD)
+                self.sbuf = sbuf
+                self.peer = hdl.get_buffer(0, sbuf.shape, sbuf.dtype)      # rank 0's buffer, addressable from this GPU
+                self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+            except Exception as e:       # pragma: no cover
+                log("symmetric memory unavailable (%s): using NCCL gather" % e)
+                self.peer = None
+        if self.peer is None and mode != "none":
+            self.mode = "nccl"
+        if world > 1 and rank == 0 and self.peer is None:
+            self.recv = [[torch.empty_like(self.result[0]) for _ in range(world)] for _ in range(2)]
+        # device addresses, looked up once: tensor indexing costs more host time than a frame takes
+        self.cptr = [[self.tgt_color[b][k].data_ptr() for k in range(G)] for b in range(2)]
+        self.dptr = [[self.tgt_depth[b][k].data_ptr() for k in range(G)] for b in range(2)]
+        self.pptr = None if self.peer is None else [[self.peer[rank, b, k].data_ptr() for k in range(G)] for b in range(2)]
+
+    # -- exchange ---------------------------------------------------------------------------------
+    def notify(self, b, n, works):
+        """End of batch buffer b (n frames): works[b] = an event that fires when rank 0 holds the batch. Lanes wait
+        on that EVENT before they overwrite buffer b - not on the control stream, which by then also waits for
+        later frames (that would drain the frames in flight at every batch boundary)."""
+        torch, dist = self.torch, self.dist
+        if self.mode == "none" or self.world == 1:
+            return
+        if self.peer is not None:
+            w = dist.all_reduce(self.flag, async_op=True)       # stream-ordered after this rank's copies / frames of the batch
+        elif n == self.G:
+            w = dist.gather(self.result[b], self.recv[b] if self.rank == 0 else None, dst=0, async_op=True)
+        else:                                                   # last, partial batch of the timed region
+            part = self.result[b][:n].contiguous()
+            rbuf = [torch.empty_like(part) for _ in range(self.world)] if self.rank == 0 else None
+            w = dist.gather(part, rbuf, dst=0, async_op=True)
+        w.wait()                                                # stream-level: the control stream continues after the exchange
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        works[b] = ev
+
+    def step(self, i, works, nl):
+        G, world, rank = self.G, self.world, self.rank
+        b, k = (i // G) & 1, i % G
+        ls, lr = self.lanes[i % nl]
+        if k == 0 and works[b] is not None:
+            for s2, _ in self.lanes[:nl]:
+                s2.wait_event(works[b])           # the exchange that still reads buffer b
+            works[b] = None
+        if self.mode == "stores" and world > 1:
+            dst = self.pptr[b][k]
+            lr.SetRenderTarget(dst if self.shaded else self.cptr[b][k], self.dptr[b][k] if self.shaded else dst)
+        else:
+            lr.SetRenderTarget(self.cptr[b][k], self.dptr[b][k])
+            if world > 1 and self.mode == "ce":
+                lr.SetFrameSink(self.pptr[b][k] if self.shaded else 0, 0 if self.shaded else self.pptr[b][k])
+        if self.views is not None:
+            lr.SetTransform(self.views[(i * world + rank) % len(self.views)])    # C5: view v is rendered by rank v mod N
+        else:
+            lr.SetTransform(self.xf)
+        lr.RenderMesh(self.meshes[i % len(self.meshes)])
+        if k == G - 1 and world > 1:
+            for s2, _ in self.lanes[:nl]:
+                self.stream.wait_stream(s2)       # the batch's frames (and their pushes), whichever lane rendered them
+            self.notify(b, G, works)
+
+    def flush(self, n_steps, works, nl):
+        """exchange the frames of a trailing partial batch, then wait for everything in flight"""
+        if n_steps % self.G and self.world > 1:
+            for s2, _ in self.lanes[:nl]:
+                self.stream.wait_stream(s2)
+            self.notify((n_steps // self.G) & 1, n_steps % self.G, works)
+        self.drain(works)
+
+    def drain(self, works):
+        for b in (0, 1):
+            if works[b] is not None:
+                works[b].synchronize()
+                works[b] = None
+
+    def sync_lanes(self):
+        for _, lr in self.lanes:
+            lr.Synchronize()                      # also vets the internal queues of the frames submitted so far
+
+    def timed_run(self, nl, steps, n_warm):
+        """n_warm untimed steps, then `steps` timed ones with `nl` frames in flight; returns (ms, t0, t1): device time
+        between two events on the control stream, barrier + synchronize on both sides, max over ranks."""
+        torch, dist, world = self.torch, self.dist, self.world
+        stream = self.stream
+        with torch.cuda.stream(stream):
+            works = [None, None]
+            for i in range(n_warm):
+                self.step(i, works, nl)
+                if i % 64 == 63:
+                    self.drain(works)
+                    self.sync_lanes()
+            self.flush(n_warm, works, nl)
+            self.sync_lanes()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record(stream)
+            for s2, _ in self.lanes[:nl]:
+                s2.wait_stream(stream)
+            for i in range(steps):
+                self.step(i, works, nl)
+            self.flush(steps, works, nl)
+            for s2, _ in self.lanes[:nl]:
+                stream.wait_stream(s2)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            if world > 1:
+                dist.barrier()
+            ms = ev0.elapsed_time(ev1)
+            self.sync_lanes()
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+        return ms, t0, t1
+
+    def stage_times(self, frames):
+        """per-kernel device time (CUDA events between the kernels, same stream), one frame at a time"""
+        r = self.r
+        r.SetRenderTarget(0, 0)
+        r.SetFrameSink(0, 0)
+        r.SetProfiling(True)
+        stage = {"geom": 0.0, "clip": 0.0, "tile": 0.0, "total": 0.0}
+        for i in range(frames):
+            r.RenderMesh(self.meshes[i % len(self.meshes)])
+            r.Synchronize()
+            st = r.GetStats()
+            for k in stage:
+                stage[k] += st["stage_ms"][k] / frames
+        r.SetProfiling(False)
+        return stage, r.GetStats()
+
+    def gather_text(self):
+        if self.world == 1:
+            return "none (1 GPU)"
+        what = "colour" if self.shaded else "depth"
+        return {"stores": "every finished %s buffer lands on rank 0 by NVLink peer stores from the resolve kernel itself (symmetric memory), one 4-byte all-reduce per %d frames",
+                "ce": "every finished %s buffer is pushed into rank 0's symmetric-memory buffer over NVLink by the copy engine right behind the frame's last kernel (edx_set_frame_sink: one D2D copy per frame on the lane's stream, no SM time, no host work); a 4-byte all-reduce per %d frames tells rank 0 they have landed",
+                "none": "NOT GATHERED (--gather none, diagnosis only) %s %d",
+                "nccl": "NCCL gather of every finished %s buffer to rank 0, per batch of %d frames, overlapped with the next batch"}[self.mode] % (what, self.G)
+
+    def nvlink_roofline(self, ms_step):
+        """What rank 0's NVLink ingress allows: (N-1) frames of frame_bytes per step."""
+        if self.world == 1:
+            return None
+        inbound = (self.world - 1) * self.frame_bytes
+        floor_ms = inbound / (NVLINK_INGRESS_GBS * 1e9) * 1e3
+        return {"bytes_into_rank0_per_step": inbound, "ingress_peak_gbs": NVLINK_INGRESS_GBS,
+                "peak_source": "round-1 measurement on this pool (7 senders, copy engine); NVLink 5 nominal is 900 GB/s per direction",
+                "floor_ms_per_step": floor_ms, "achieved_gbs": inbound / (ms_step * 1e-3) / 1e9,
+                "frac": floor_ms / ms_step}
+
+    def close(self, release_meshes=True):
+        if release_meshes and self.own_meshes:
+            for m in self.meshes:
+                m.Release()
+        for _, lr in self.lanes:
+            lr.close()
+
+
+def secondary_config(name, device, peak, R, with_cpu=True):
+    """Quick device-resident measurement of another BASELINE config (rank 0, N=1 only), with its CPU baseline."""
     t0 = time.time()
     sc = make_scene(name, 1.0)
     r = R.Renderer(device)
     r.Initialize(sc.width, sc.height)
     r.SetTransform(sc.mv, sc.proj, sc.raster)
     r.SetPixelShader(sc.shader)
-    mesh_bytes = sc.num_verts * 32 + sc.num_tris * 16
-    copies = max(1, min(4, int(600e6 // max(mesh_bytes, 1))))
+    copies = mesh_copies(sc.num_verts, sc.num_tris)
     meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]
     frames = 30 if sc.num_tris < 5_000_000 else 10
     ms = time_frames(r, meshes, frames, 3) / frames
@@ -259,6 +557,7 @@ def secondary_config(name, device, peak):
            "ms_per_frame_3_in_flight": ms_ring, "mtris_per_s_3_in_flight": sc.num_tris / ms_ring / 1e3,
            "gpix_per_s": sc.width * sc.height / ms / 1e6, "frames_per_s": 1000.0 / ms,
            "algorithmic_bytes": ab, "hbm_frac_whole_frame": ab / (ms * 1e-3) / 1e9 / peak,
+           "hbm_frac_whole_frame_3_in_flight": ab / (ms_ring * 1e-3) / 1e9 / peak,
            "fb_only_frac": (8 if sc.shader != 0 else 4) * sc.width * sc.height / (ms * 1e-3) / 1e9 / peak,
            "stage_ms": stage, "binned_tris": st["binned_tris"], "clipped_tris": st["clipped_tris"],
            "l2": "rotating %d mesh copies" % copies}
@@ -266,6 +565,47 @@ def secondary_config(name, device, peak):
         m.Release()
     r.close()
     log("secondary %s: %.3f ms/frame (%.1fs incl. generation)" % (name, ms, time.time() - t0))
+    if with_cpu:
+        try:
+            out["cpu_baseline"] = cpu_baseline(sc, cpu_seconds=12.0, max_frames=40)
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "error": str(e)}
+    return out, sc
+
+
+def config5(torch, dist, R, sc4, local, rank, world, args, peak):
+    """BASELINE.json configs[4]: 256 camera views of the 10M-triangle mesh, view i on GPU i mod N, every finished
+    colour buffer gathered to rank 0 inside the timed region. Strong scaling: the 256 views are the job."""
+    from edxraster_b200 import scenes
+    t0 = time.time()
+    sc = sc4 if sc4 is not None else make_scene("C4", args.scale)
+    sc = scenes.Scene(sc)
+    n_views = 256
+    sc["views"] = scenes.config5_views(sc, n_views)
+    farm = Farm(torch, dist, R, sc, local, rank, world, args.in_flight, "stores" if args.peer_stores else args.gather, 4)
+    per_rank = n_views // world
+    ms, _, _ = farm.timed_run(farm.K, per_rank, 8)
+    nt, nv, W, H = sc.num_tris, sc.num_verts, sc.width, sc.height
+    ab = algorithmic_bytes(nv, nt, W, H, True)
+    ms_view = ms / per_rank
+    out = {"workload": WORKLOADS["C5"], "views": n_views, "n_gpus": world, "scaling": "strong",
+           "ms_total": ms, "ms_per_view_per_gpu": ms_view, "frames_per_s": n_views / (ms * 1e-3),
+           "mtris_per_s": n_views * nt / ms / 1e3, "gpix_per_s": n_views * W * H / ms / 1e6,
+           "frames_in_flight_per_gpu": farm.K, "gather": farm.gather_text(),
+           "gathered_bytes": (world - 1) * per_rank * farm.frame_bytes,
+           "algorithmic_bytes_per_view": ab, "hbm_frac_whole_frame": ab / (ms_view * 1e-3) / 1e9 / peak,
+           "nvlink": farm.nvlink_roofline(ms_view)}
+    if rank == 0 and world == 1:
+        stage, st = farm.stage_times(5)
+        out["stage_ms"] = stage
+        out["binned_tris"], out["clipped_tris"] = st["binned_tris"], st["clipped_tris"]
+    farm.close()
+    if rank == 0 and world == 1:
+        try:
+            out["cpu_baseline"] = cpu_baseline(sc, cpu_seconds=12.0, max_frames=8, views=sc["views"])
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "error": str(e)}
+    log("C5: %d views on %d GPU(s) in %.2f ms (%.1fs incl. setup)" % (n_views, world, ms, time.time() - t0))
     return out
 
 
@@ -295,179 +635,34 @@ def ours_arm(args):
     sc = make_scene(args.workload, args.scale)
     W, H, nt, nv = sc.width, sc.height, sc.num_tris, sc.num_verts
     shaded = sc.shader != 0
-    # `stream` carries the timing events and the NCCL gathers. Frames are rendered by K lanes (edx contexts on
-    # their own streams sharing the meshes): K independent frames in flight per GPU.
-    stream = torch.cuda.Stream(device=dev)
-    K = max(1, args.in_flight)
-    lanes = []
-    for _ in range(K):
-        ls = torch.cuda.Stream(device=dev)
-        lr = R.Renderer(local)
-        lr.SetStream(ls.cuda_stream)
-        lr.Initialize(W, H)
-        lr.SetTransform(sc.mv, sc.proj, sc.raster)
-        lr.SetPixelShader(sc.shader)
-        lanes.append((ls, lr))
-    r = lanes[0][1]
-    views = sc.get("views")
-    xf = R.PackedTransform(sc.mv, sc.proj, sc.raster)       # marshalled once; edx_set_transform still runs every step
-    if views is not None:
-        views = [R.PackedTransform(*v) for v in views]
-    copies = 4 if nv * 32 + nt * 12 < 200e6 else 1          # C4/C5: one 440 MB mesh already exceeds L2
-    meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]    # read-only while rendering: shared by the lanes
-
-    # Render targets are torch tensors so NCCL sends them without a copy. Frames are gathered to rank 0 in
-    # batches of G (one grouped send/recv per G frames: issuing a collective costs more host time than a 60 us
-    # frame takes on the GPU), double-buffered so batch k is on the wire while batch k+1 renders. Every frame
-    # still reaches rank 0 inside the timed region.
-    G = 8
-    tgt_color = [torch.zeros((G, H, W, 4), dtype=torch.uint8, device=dev) for _ in range(2)]
-    tgt_depth = [torch.zeros((G, H, W), dtype=torch.float32, device=dev) for _ in range(2)]
-    result = tgt_color if shaded else tgt_depth
-    recv = None
-    # Optional exchange (--peer-stores): no gather pass at all. Rank 0's receive buffer is symmetric memory mapped
-    # into every rank over NVLink, and each rank's tile kernel stores its finished pixels straight into its slice
-    # of it (edx_set_render_target with the peer pointer); one 4-byte all-reduce per batch tells rank 0 the batch
-    # has landed. Measured on 4 B200s it is SLOWER than the batched NCCL gather (88 vs 73 us/step): the resolve
-    # writes 32-byte row segments, poor NVLink packets. Kept as an option; the default is the NCCL gather.
-    # --gather ce: the batch is pushed into the same symmetric buffer by the COPY ENGINE (one D2D copy over NVLink
-    # per batch, no SM time at all), again followed by the 4-byte all-reduce.
-    peer = None
     mode = "stores" if args.peer_stores else args.gather
-    if world > 1 and mode in ("stores", "ce"):
-        try:
-            import torch.distributed._symmetric_memory as symm
-            sbuf = symm.empty((world, 2, G) + tuple(result[0].shape[1:]), dtype=result[0].dtype, device=dev)
-            hdl = symm.rendezvous(sbuf, dist.group.WORLD)
-            peer = hdl.get_buffer(0, sbuf.shape, sbuf.dtype)      # rank 0's buffer, addressable from this GPU
-            flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        except Exception as e:       # pragma: no cover
-            log("symmetric memory unavailable (%s): using NCCL gather" % e)
-            peer = None
-    if peer is None and mode != "none":
-        mode = "nccl"
-    if world > 1 and rank == 0 and peer is None:
-        recv = [[torch.empty_like(result[0]) for _ in range(world)] for _ in range(2)]
-
-    def send_batch(b, n, works):
-        """Issue the exchange of batch buffer b on the control stream; works[b] = an event that fires when it is done.
-        Lanes wait on that EVENT before they overwrite buffer b - not on the control stream, which by then has also
-        waited for the next batch's frames (that would drain the frames in flight at every batch boundary)."""
-        if mode == "none" or world == 1:          # "none": diagnosis only, frames stay on their GPU
-            return
-        if peer is not None:
-            if mode == "ce":
-                peer[rank, b, :n].copy_(result[b][:n], non_blocking=True)     # cudaMemcpyAsync D2D into rank 0's memory
-            w = dist.all_reduce(flag, async_op=True)              # stream-ordered after this rank's frames of the batch
-        elif n == G:
-            w = dist.gather(result[b], recv[b] if rank == 0 else None, dst=0, async_op=True)
-        else:                                     # last, partial batch of the timed region
-            part = result[b][:n].contiguous()
-            rbuf = [torch.empty_like(part) for _ in range(world)] if rank == 0 else None
-            w = dist.gather(part, rbuf, dst=0, async_op=True)
-        w.wait()                                  # stream-level: the control stream continues after the exchange
-        ev = torch.cuda.Event()
-        ev.record(stream)
-        works[b] = ev
-
-    def step(i, works, nl):
-        b, k = (i // G) & 1, i % G
-        ls, lr = lanes[i % nl]
-        if k == 0 and works[b] is not None:
-            for s2, _ in lanes[:nl]:
-                s2.wait_event(works[b])           # the gather that still reads buffer b
-            works[b] = None
-        if mode == "stores":
-            dst = peer[rank, b, k].data_ptr()
-            lr.SetRenderTarget(dst if shaded else tgt_color[b][k].data_ptr(), tgt_depth[b][k].data_ptr() if shaded else dst)
-        else:
-            lr.SetRenderTarget(tgt_color[b][k].data_ptr(), tgt_depth[b][k].data_ptr())
-        if views is not None:
-            lr.SetTransform(views[(i * world + rank) % len(views)])    # C5: view v is rendered by rank v mod N
-        else:
-            lr.SetTransform(xf)
-        lr.RenderMesh(meshes[i % copies])
-        if k == G - 1 and world > 1:
-            for s2, _ in lanes[:nl]:
-                stream.wait_stream(s2)            # the batch's frames, whichever lane rendered them
-            send_batch(b, G, works)
-
-    def flush(n_steps, works, nl):
-        """gather the frames of a trailing partial batch, then wait for everything in flight"""
-        if n_steps % G and world > 1:
-            for s2, _ in lanes[:nl]:
-                stream.wait_stream(s2)
-            send_batch((n_steps // G) & 1, n_steps % G, works)
-        drain(works)
-
-    def drain(works):
-        for b in (0, 1):
-            if works[b] is not None:
-                works[b].synchronize()
-                works[b] = None
-
-    def sync_lanes():
-        for _, lr in lanes:
-            lr.Synchronize()                      # also vets the internal queues of the frames submitted so far
-
-    def timed_run(nl, steps, n_warm):
-        """n_warm untimed steps, then `steps` timed ones with `nl` frames in flight; returns (ms, t0, t1)"""
-        works = [None, None]
-        for i in range(n_warm):
-            step(i, works, nl)
-            if i % 64 == 63:
-                drain(works)
-                sync_lanes()
-        drain(works)
-        sync_lanes()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev0.record(stream)
-        for s2, _ in lanes[:nl]:
-            s2.wait_stream(stream)
-        for i in range(steps):
-            step(i, works, nl)
-        flush(steps, works, nl)
-        for s2, _ in lanes[:nl]:
-            stream.wait_stream(s2)
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        if world > 1:
-            dist.barrier()
-        ms = ev0.elapsed_time(ev1)
-        sync_lanes()
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, t0, t1
+    G = 4
+    farm = Farm(torch, dist, R, sc, local, rank, world, args.in_flight, mode, G)
+    K, lanes, stream, meshes, copies, r, xf = farm.K, farm.lanes, farm.stream, farm.meshes, farm.copies, farm.r, farm.xf
 
     sampler = ClockSampler(local)
-    with torch.cuda.stream(stream):
-        sampler.start()                           # NVML calls take ~1 ms each: sample through warm-up and the timed region
-        # warm-up: W steps plus a fixed 1000 more so clocks settle (a fixed count: every rank must issue the
-        # same number of gathers)
-        n_warm = ((max(args.warmup, 3) + 1000 + G - 1) // G) * G
-        ms_total, t0, t1 = timed_run(K, args.steps, n_warm)
-        sampler.stop()
-        launches_per_step = r.LastLaunchCount()
-        ms_step = ms_total / args.steps
-        value = world * nt / ms_step / 1e3        # Mtris/s, whole job
-        ms_one = None
-        if K > 1:                                 # the same loop with ONE frame in flight, for the record
-            ms_one = timed_run(1, args.steps, ((max(args.warmup, 3) + G - 1) // G) * G)[0] / args.steps
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()                           # NVML calls take ~1 ms each: sample through warm-up and the timed region
+    # warm-up: W steps plus a fixed 1000 more so clocks settle (a fixed count: every rank must issue the
+    # same number of exchanges)
+    n_warm = ((max(args.warmup, 3) + 1000 + G - 1) // G) * G
+    ms_total, t0, t1 = farm.timed_run(K, args.steps, n_warm)
+    sampler.stop()
+    launches_per_step = r.LastLaunchCount()
+    ms_step = ms_total / args.steps
+    value = world * nt / ms_step / 1e3        # Mtris/s, whole job
+    ms_one = None
+    if K > 1:                                 # the same loop with ONE frame in flight, for the record
+        ms_one = farm.timed_run(1, args.steps, ((max(args.warmup, 3) + G - 1) // G) * G)[0] / args.steps
 
+    with torch.cuda.stream(stream):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         # ---- end-to-end through the C ABI with HOST buffers: upload mesh, render, read result back ----
         hv = torch.from_numpy(np.ascontiguousarray(sc.vertices)).pin_memory()
         hi = torch.from_numpy(np.ascontiguousarray(sc.indices).view(np.int32)).pin_memory()
         houts = [torch.empty((H, W), dtype=torch.float32).pin_memory() if not shaded else None for _ in lanes]
         for _, lr in lanes:
             lr.SetRenderTarget(0, 0)
+            lr.SetFrameSink(0, 0)
         # streamed geometry is written by its lane's upload: one private mesh per lane (lane 0 reuses a shared one)
         lane_mesh = [meshes[0]] + [lr.CreateMesh(sc.vertices, sc.indices) for _, lr in lanes[1:]]
         e2e_steps = max(3, min(args.steps, 20 if nt < 5_000_000 else 5))
@@ -517,18 +712,30 @@ def ours_arm(args):
         h2d = nv * 32 + nt * 12 + 3 * 64
         d2h = W * H * 4
 
-        # ---- per-kernel device time (CUDA events between the kernels, same stream) ----
-        r.SetProfiling(True)
-        stage = {"geom": 0.0, "clip": 0.0, "tile": 0.0, "total": 0.0}
-        prof_frames = max(5, min(args.steps, 20))
-        for i in range(prof_frames):
-            r.RenderMesh(meshes[i % copies])
-            r.Synchronize()
-            st = r.GetStats()
-            for k in stage:
-                stage[k] += st["stage_ms"][k] / prof_frames
-        r.SetProfiling(False)
-        stats = r.GetStats()
+    stage, stats = farm.stage_times(max(5, min(args.steps, 20)))
+    for m in lane_mesh[1:]:
+        m.Release()
+    gather_text, nvlink = farm.gather_text(), farm.nvlink_roofline(ms_step)
+    farm.close()
+
+    # ---- BASELINE.json configs[4] at this N (every rank takes part), then the other configs at N = 1 ----
+    also = {}
+    sc4 = None
+    if not args.no_extra and args.workload == "C2":
+        if world == 1:
+            for name in ("C1", "C3", "C4"):
+                try:
+                    also[name], scx = secondary_config(name, local, peak, R)
+                    if name == "C4":
+                        sc4 = scx
+                except Exception as e:
+                    also[name] = {"error": str(e)}
+        try:
+            also["C5"] = config5(torch, dist, R, sc4, local, rank, world, args, peak)
+        except Exception as e:       # pragma: no cover
+            if world > 1:
+                raise
+            also["C5"] = {"error": str(e)}
 
     if rank != 0:
         if world > 1:
@@ -552,16 +759,11 @@ def ours_arm(args):
         "metric": "Mtris/s", "value": value, "unit": "Mtris/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 depth / i32 28.4 fixed-point coverage", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "triangles": nt, "vertices": nv, "resolution": [W, H],
-                   "frames_per_step_per_gpu": 1, "frames_in_flight_per_gpu": K,
-                   "in_flight": "each GPU keeps %d independent frames in flight (contexts on their own streams sharing the meshes); "
-                                "every frame is rendered completely and, at N > 1, gathered inside the timed region" % K,
-                   "l2": "inputs larger than L2: round-robin over %d device cop%s of the mesh (%d MB of SoA streams)" % (copies, "ies" if copies > 1 else "y", copies * (nv * 32 + nt * 12) // 1000000),
-                   "gather": ("none (1 GPU)" if world == 1 else
-                              ("every finished %s buffer lands on rank 0 by NVLink peer stores from the resolve kernel itself (symmetric memory), one 4-byte all-reduce per %d frames" if mode == "stores" else
-                               "every finished %s buffer is pushed into rank 0's symmetric-memory buffer over NVLink by the copy engine (one D2D copy per batch of %d frames, no SM time), then a 4-byte all-reduce" if mode == "ce" else
-                               "NOT GATHERED (--gather none, diagnosis only) %s %d" if mode == "none" else
-                               "NCCL gather of every finished %s buffer to rank 0, per batch of %d frames, overlapped with the next batch") % ("colour" if shaded else "depth", G))},
+        "config": config_block(args.workload, nv, nt, W, H),
+        "execution": {"frames_in_flight_per_gpu": K,
+                      "in_flight": "each GPU keeps %d independent frames in flight (contexts on their own streams sharing the meshes); "
+                                   "every frame is rendered completely and, at N > 1, gathered inside the timed region" % K,
+                      "gather": gather_text},
         "frames_per_s": world * 1000.0 / ms_step, "gpix_per_s": world * W * H / ms_step / 1e6,
         "one_frame_in_flight": None if ms_one is None else {"ms_per_step": ms_one, "value": world * nt / ms_one / 1e3},
         "clocks": sampler.summary(t0, t1),
@@ -577,39 +779,19 @@ def ours_arm(args):
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ab, "kernel_ms": dom_ms,
                      "stage_ms": stage, "whole_frame_frac": ab / (ms_step * 1e-3) / 1e9 / peak,
-                     "fb_only_frac": (8 if shaded else 4) * W * H / (ms_step * 1e-3) / 1e9 / peak},
+                     "fb_only_frac": (8 if shaded else 4) * W * H / (ms_step * 1e-3) / 1e9 / peak,
+                     "nvlink": nvlink},
         "path_stats": {"binned_tris": stats["binned_tris"], "clipped_tris": stats["clipped_tris"], "regrows": stats["regrow_count"]},
     }
-    for m in meshes + lane_mesh[1:]:
-        m.Release()
-    for _, lr in lanes:
-        lr.close()
-
     if world == 1:
         # CPU baseline on this box's host cores: bounded sample of the same workload
         try:
-            ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            probe, threads, used, _ = cpu_frames(sc, ncpu, 1, 1)
-            # bounded sample: about 20 s of CPU work (wall time x threads), 3..40 full frames of the same workload
-            nfr = int(min(40, max(3, round(20.0 / max(probe[0] * threads, 1e-6)))))
-            times, threads, used, _ = cpu_frames(sc, ncpu, nfr, 1)
-            v = used * len(times) / sum(times) / 1e6
-            line["cpu_baseline"] = {"value": v, "unit": "Mtris/s", "cores": threads, "kind": "port",
-                                    "sample": "%d full frames of the same workload after 1 warm-up (%.3f s each, ~%.0f s of CPU work on %d threads)" % (len(times), sum(times) / len(times), sum(times) * threads, threads),
-                                    "note": "oracle/ timing build (CPU restatement of the reference SSE path; the reference cannot be built offline)"}
-        except Exception as e:       # the oracle is only a reported baseline
+            line["cpu_baseline"] = cpu_baseline(sc, cpu_seconds=20.0)
+        except Exception as e:       # the CPU arm is only a reported baseline
             line["cpu_baseline"] = {"value": None, "error": str(e)}
-        if not args.no_extra and args.workload == "C2":
-            also = {}
-            for name in ("C1", "C3", "C4"):
-                if name == args.workload:
-                    continue
-                try:
-                    also[name] = secondary_config(name, local, peak)
-                except Exception as e:
-                    also[name] = {"error": str(e)}
-            line["other_configs"] = also
-    else:
+    if also:
+        line["other_configs"] = also
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     real_stdout.write(json.dumps(line) + "\n")

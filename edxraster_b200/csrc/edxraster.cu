@@ -50,6 +50,7 @@ struct edx_context {
     unsigned long long* keys = nullptr;
     uchar4* color = nullptr; float* depth = nullptr; uint32_t* ids = nullptr;
     uchar4* extColor = nullptr; float* extDepth = nullptr;      // caller-owned render targets (optional)
+    void* sinkColor = nullptr; void* sinkDepth = nullptr;       // edx_set_frame_sink: where the copy engine pushes each finished frame
     BigRec* big = nullptr; uint32_t bigCap = 0;
     uint32_t* bigBox = nullptr; uint32_t bigBoxCap = 0;
     ClipItem* clipQueue = nullptr; uint32_t clipQueueCap = 0;
@@ -223,6 +224,11 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
         EDX_CUDA(c, launch(msaa_resolve_kernel, dim3((c->keyStride + 255) / 256), dim3(256), 0));
     }
     EDX_CUDA(c, launch(frame_end_kernel, dim3(1), dim3(32), 0));       // counters -> pinned host memory, reset for the next frame
+    // frame sink (edx_set_frame_sink): the copy engine pushes the finished buffers, e.g. into the root GPU's memory over NVLink
+    if (c->sinkColor && c->shader != EDX_SHADER_DEPTH_ONLY && c->msaaLog2 == 0)
+        EDX_CUDA(c, cudaMemcpyAsync(c->sinkColor, P.color, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->sinkDepth && c->msaaLog2 == 0)
+        EDX_CUDA(c, cudaMemcpyAsync(c->sinkDepth, P.depth, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToDevice, c->stream));
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[3], c->stream));
     EDX_CUDA(c, cudaGetLastError());
     return EDX_OK;
@@ -434,8 +440,8 @@ int edx_set_msaa_mode(edx_context* c, int log2)
     if (!c) return EDX_ERR_INVALID;
     if (log2 < 0 || log2 > 5) return fail(c, EDX_ERR_INVALID, "sample_count_log2 must be 0..5 (FrameBuffer.cpp:107-191 has tables up to 32x)");
     if (log2 == c->msaaLog2) return EDX_OK;          // the viewer calls this every frame (Main.cpp:97)
-    if (c->extColor || c->extDepth) {
-        if (log2 != 0) return fail(c, EDX_ERR_UNSUPPORTED, "caller-owned render targets are single-sample only");
+    if (c->extColor || c->extDepth || c->sinkColor || c->sinkDepth) {
+        if (log2 != 0) return fail(c, EDX_ERR_UNSUPPORTED, "caller-owned render targets and frame sinks are single-sample only");
     }
     c->msaaLog2 = log2;
     if (!c->initialized) return EDX_OK;
@@ -790,6 +796,15 @@ int edx_get_derived_state(const edx_context* c, float mvp[16], float eye[3], flo
 
 void* edx_device_color(edx_context* c) { return c ? (c->extColor ? c->extColor : c->color) : nullptr; }
 void* edx_device_depth(edx_context* c) { return c ? (c->extDepth ? c->extDepth : c->depth) : nullptr; }
+
+int edx_set_frame_sink(edx_context* c, void* color, void* depth)
+{
+    if (!c) return EDX_ERR_INVALID;
+    if ((color || depth) && c->msaaLog2 != 0) return fail(c, EDX_ERR_UNSUPPORTED, "frame sinks are single-sample only");
+    c->sinkColor = color;
+    c->sinkDepth = depth;
+    return EDX_OK;
+}
 
 int edx_set_render_target(edx_context* c, void* color, void* depth)
 {

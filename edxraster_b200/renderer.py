@@ -211,6 +211,11 @@ class Renderer:
     def SetRenderTarget(self, color_ptr, depth_ptr):
         self._check(self._lib.edx_set_render_target(self._h, C.c_void_p(color_ptr or None), C.c_void_p(depth_ptr or None)))
 
+    def SetFrameSink(self, color_ptr, depth_ptr):
+        """After every frame, push the finished colour / depth buffer to these device addresses (own or peer-mapped
+        memory) with the copy engine, stream-ordered behind the frame: the frame-parallel gather."""
+        self._check(self._lib.edx_set_frame_sink(self._h, C.c_void_p(color_ptr or None), C.c_void_p(depth_ptr or None)))
+
     def ReadDepthInto(self, host_ptr):
         """Copy the depth buffer to caller memory (pinned for full PCIe speed); synchronises."""
         self._check(self._lib.edx_read_depth(self._h, C.cast(C.c_void_p(host_ptr), C.POINTER(C.c_float))))

@@ -513,6 +513,8 @@ public:
     bool GetDepthBuffer(float* out) const { return mCtx && edx_read_depth(mCtx, out) == EDX_OK; }
     bool WriteFrame(const char* path) const { return mCtx && edx_write_frame_to_file(mCtx, path) == EDX_OK; }
     void Synchronize() { Call(edx_synchronize(mCtx)); }
+    // frame-parallel gather: every finished frame is pushed to these device addresses (own or peer-mapped) by the copy engine
+    void SetFrameSink(void* remoteColor, void* remoteDepth) { Call(edx_set_frame_sink(mCtx, remoteColor, remoteDepth)); }
     int LastStatus() const { return mStatus; }
     const char* LastError() const { return mCtx ? edx_last_error(mCtx) : "no CUDA device (edx_create failed)"; }
     edx_context* Handle() const { return mCtx; }

@@ -164,6 +164,14 @@ void* edx_device_depth(edx_context* ctx);
 /* render into caller-owned device buffers (width*height RGBA8 / float32), e.g. torch tensors that
  * an NCCL gather then sends without a copy; NULL restores the context's own buffer. */
 int edx_set_render_target(edx_context* ctx, void* device_color, void* device_depth);
+/* Frame-parallel gather (the call site it replaces is the per-frame read-back loop of
+ * RealtimeViewer/Main.cpp:71-75 run once per GPU): after every frame this context renders, the finished colour
+ * and / or depth buffer (width*height RGBA8 / float32) is pushed to `remote_color` / `remote_depth` by the COPY
+ * ENGINE, stream-ordered behind the frame on the context's stream (no SM time). The addresses are device pointers
+ * this GPU can reach - its own memory, or a peer's mapped over NVLink (cudaDeviceEnablePeerAccess, or a
+ * symmetric-memory mapping) - typically this rank's slot of the root GPU's frame store. NULL, NULL switches it off.
+ * Single-sample only. The caller owns the protocol that tells the root a slot has landed. */
+int edx_set_frame_sink(edx_context* ctx, void* remote_color, void* remote_depth);
 /* Sort-first split of ONE frame over several contexts / GPUs: this context rasterises, resolves
  * and writes only the 64x64-pixel bins b (row-major) with b % parts == part; the rest of its frame buffer is left
  * untouched. Every context still runs the geometry stages on the whole mesh. parts = 1 restores the full frame. */
