@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libedxraster_b200.so")
+# EDX_LIB: load another build of the same library (the diagnostic `make -C csrc debug` build); never a different implementation
+LIB_PATH = os.environ.get("EDX_LIB") or os.path.join(_HERE, "libedxraster_b200.so")
 
 # every symbol include/edxraster_c.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -41,7 +42,7 @@ class TextureDesc(C.Structure):         # edx_texture_desc
 class Stats(C.Structure):
     _fields_ = [("submitted_tris", C.c_uint64), ("clipped_tris", C.c_uint64), ("binned_tris", C.c_uint64),
                 ("clip_records", C.c_uint64), ("regrow_count", C.c_uint32), ("tile_pairs", C.c_uint32),
-                ("stage_ms", C.c_float * 8)]
+                ("mid_tris", C.c_uint64), ("stage_ms", C.c_float * 8)]
 
 
 _lib = None

@@ -40,6 +40,14 @@ struct __align__(16) BigRec {
     float gy, zref, perr; uint32_t pad;
 };
 
+// Post-setup triangle routed to the warp-per-triangle path (48 bytes, three 16-byte loads): its pixel-centre box is
+// larger than the direct path takes and smaller than midMax on both sides.
+struct __align__(16) MidRec {
+    int v0x, v0y, v1x, v1y;
+    int v2x, v2y; float z0, z1;
+    float z2, invDet; uint32_t prim; uint32_t pad;
+};
+
 // What the resolve pass needs to shade a pixel owned by a fan triangle of a clipped polygon (96 bytes).
 struct __align__(16) ClipRec {
     int v0x, v0y, v1x, v1y;
@@ -64,14 +72,16 @@ struct Counters {
     uint32_t nClipQueue;     // straddling triangles queued for the clipper
     uint32_t nClipRecs;      // fan-triangle records written by the clipper
     uint32_t nDump;
-    uint32_t done;           // (unused since frame_end_kernel replaced the per-CTA ticket)
+    uint32_t nMid;           // triangles appended to the warp-per-triangle path
     // Never reset on the device: frames whose queues overflowed, and the largest demand seen. A caller may
     // submit several frames before the next synchronising call; that call learns from these whether any of
     // them (not just the last) was incomplete.
     uint32_t overFrames;
     uint32_t maxBig, maxClipQueue, maxClipRecs;
     uint32_t tilePairs;      // (triangle, bin) pairs that survived the bin-level culls this frame: the tile path's load
-    uint32_t pad[2];
+    uint32_t maxMid, padMid;
+    uint32_t nWork;          // list front end: triangle clusters that survived cull_kernel this frame
+    uint32_t ticket;         // list front end: work items handed out beyond the first gridDim.x
     unsigned long long dbg[8];   // EDX_DEBUG_STATS builds: summed per-CTA cycle counts of the tile kernel's phases
 };
 
@@ -92,6 +102,7 @@ struct FrameParams {
     float albedo[3];
     int width, height, binsX, binsY;
     int shader, smallMax, smallMaxClip, hiz, hierarchical, captureIds, dump;
+    int midMax;              // pixel-centre boxes below this (and not small) are rasterised one warp per triangle; 0 = none
     int part, parts;         // sort-first split: this context owns the bins b with b % parts == part (parts = 1: all)
     int clusterCull;         // skip whole 256-triangle clusters whose bounding box is outside one clip plane
     int fuseClip;            // clip single-plane straddlers inside geom_kernel instead of queueing them
@@ -99,6 +110,16 @@ struct FrameParams {
     uint32_t keyStride;      // keys per sample plane
     int leanResolve;         // lean_resolve_kernel runs before tile_kernel this frame
     int rasterAffineXY;      // raster matrix has no z column and w' == 1: skip the unused z/w and w' arithmetic
+    // Front end of the frame: 0 = geom_kernel, one CTA per 256-triangle cluster, vertex work per
+    // triangle corner; 1 = cull_kernel compacts the clusters that survive the frustum test into `workList` and a
+    // persistent geom_list_kernel walks it; 2 = as 1 plus vertex_kernel: stages a1/a2/a5/a6 once per VERTEX
+    // (Renderer.cpp:120-127,139-147) into `vrec`, which the geometry kernel and the resolve pass then gather.
+    int frontEnd;
+    const float4* vclusterBox;           // per 256-vertex cluster: object-space AABB, built at upload
+    uint32_t nTriClusters, nVertClusters;
+    uint32_t* workList;                  // surviving triangle clusters (any order: submission order lives in the prim id)
+    uint32_t* vcFlag;                    // per vertex cluster: 0 = processed by vertex_kernel, else a clip-plane bit every vertex of it is outside of
+    int4* vrec;                          // per vertex: snapped x, y (28.4), z*invW, invW - or 0, 0, 0, VREC_OUTSIDE | clip code
     // mesh (SoA streams built at upload)
     const float4* pos4;      // x, y, z, texcoord.v
     const float4* nrm4;      // nx, ny, nz, texcoord.u
@@ -110,6 +131,7 @@ struct FrameParams {
     uint32_t nTex; int texFilter;        // RenderStates::TexFilter (RenderStates.h:23,60)
     // frame state
     unsigned long long* keys;            // 64-bit visibility keys, bin/tile/block-tiled, L2 resident
+    MidRec* mid; uint32_t midCap;
     BigRec* big; uint32_t bigCap;
     uint32_t* bigBox;                    // per tile-path triangle: its bin bounding box, 4 x u8 (x0, x1, y0, y1)
     ClipItem* clipQueue; uint32_t clipQueueCap;
@@ -123,6 +145,15 @@ struct FrameParams {
 
 struct V4 { float x, y, z, w; };
 
+// Per-vertex record of a vertex outside the frustum: its invW word is a quiet NaN whose low six bits are the clip code
+// (never zero here). A real invW is 1/w of a vertex with code 0; if that is NaN it is stored as 0x7FFFFFFF.
+constexpr uint32_t VREC_OUTSIDE = 0x7FC00000u;
+__device__ __forceinline__ uint32_t vrec_code(int w)
+{
+    const uint32_t b = (uint32_t)w;
+    return (b & 0x7FFFFFC0u) == VREC_OUTSIDE ? (b & 63u) : 0u;
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp32 helpers that can never be contracted
 // ---------------------------------------------------------------------------------------------
@@ -130,6 +161,9 @@ __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// 1.0f / x: the correctly rounded reciprocal IS the correctly rounded quotient of 1 and x (IEEE 754), in about half the
+// instructions of the general division
+__device__ __forceinline__ float frcp(float x) { return __frcp_rn(x); }
 // ((a*x + b*y) + c*z) + d : the row . vector order of Matrix::TransformPoint (SURVEY.md §8c shim 1/2)
 __device__ __forceinline__ float row_dot(float a, float b, float c, float d, float x, float y, float z)
 {
@@ -164,7 +198,7 @@ __device__ __forceinline__ bool surely_inside(const V4& v)
     return fabsf(v.x) <= v.w && fabsf(v.y) <= v.w && v.z >= 0.0f && v.z <= v.w;
 }
 // 1/w of Renderer.cpp:144 (1.0f / 1.0f == 1.0f exactly)
-__device__ __forceinline__ float inv_w(float w) { return w == 1.0f ? 1.0f : __fdiv_rn(1.0f, w); }
+__device__ __forceinline__ float inv_w(float w) { return w == 1.0f ? 1.0f : frcp(w); }
 __device__ __forceinline__ uint32_t clip_code(const V4& v)
 {
     uint32_t c = 0;
@@ -223,7 +257,7 @@ __device__ __forceinline__ bool finish_setup(SetupTri& s)
     uint32_t B2 = (uint32_t)s.v2y - (uint32_t)s.v0y, C2 = (uint32_t)s.v0x - (uint32_t)s.v2x;
     int det = (int)(C2 * B1 - C1 * B2);
     if (det <= 0) return false;
-    s.invDet = fdiv(1.0f, __int2float_rn(det));
+    s.invDet = frcp(__int2float_rn(det));
     return true;
 }
 

@@ -91,6 +91,38 @@ __global__ void __launch_bounds__(256) cluster_bounds_kernel(const float4* __res
     }
 }
 
+// The same for each block of 256 consecutive VERTICES (= one vertex_kernel work item of the list front end).
+__global__ void __launch_bounds__(256) vertex_cluster_bounds_kernel(const float4* __restrict__ pos4, uint32_t nVerts, float4* __restrict__ boxes)
+{
+    __shared__ float red[6][8];
+    const uint32_t v = blockIdx.x * 256u + threadIdx.x;
+    float lo[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, hi[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+    bool bad = false;
+    if (v < nVerts) {
+        const float4 p = __ldg(pos4 + v);
+        const float c[3] = { p.x, p.y, p.z };
+        #pragma unroll
+        for (int a = 0; a < 3; a++) { lo[a] = hi[a] = c[a]; bad |= !(fabsf(c[a]) < 3.0e38f); }
+    }
+    #pragma unroll
+    for (int a = 0; a < 3; a++)
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xFFFFFFFFu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xFFFFFFFFu, hi[a], o));
+        }
+    const bool anyBad = __syncthreads_or(bad);
+    if ((threadIdx.x & 31) == 0)
+        for (int a = 0; a < 3; a++) { red[a][threadIdx.x >> 5] = lo[a]; red[3 + a][threadIdx.x >> 5] = hi[a]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            for (int a = 0; a < 3; a++) { red[a][0] = fminf(red[a][0], red[a][w]); red[3 + a][0] = fmaxf(red[3 + a][0], red[3 + a][w]); }
+        boxes[2 * blockIdx.x] = make_float4(red[0][0], red[1][0], red[2][0], anyBad ? 0.0f : 1.0f);
+        boxes[2 * blockIdx.x + 1] = make_float4(red[3][0], red[4][0], red[5][0], 0.0f);
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_keys_kernel(ulonglong2* __restrict__ keys, size_t nPairs)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,6 +286,16 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                 r0 += sC0; r1 += sC1; r2 += sC2;
             }
         }
+    } else if (x1 - x0 < P.midMax && y1 - y0 < P.midMax) {
+        // Mid-size triangle: a lone thread would serialise hundreds of pixel tests (and stall its warp), a whole-bin
+        // sweep is too heavy a machine for it. mid_kernel gives it one warp.
+        const uint32_t at = warp_append(&P.counters->nMid);
+        if (at < P.midCap) {
+            int4* dst = reinterpret_cast<int4*>(P.mid + at);
+            dst[0] = make_int4(s.v0x, s.v0y, s.v1x, s.v1y);
+            dst[1] = make_int4(s.v2x, s.v2y, __float_as_int(z0), __float_as_int(z1));
+            dst[2] = make_int4(__float_as_int(z2), __float_as_int(s.invDet), (int)prim, 0);
+        }
     } else {
         const uint32_t at = warp_append(&P.counters->nBig);
         if (at < P.bigCap) {
@@ -285,45 +327,9 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
 // ---------------------------------------------------------------------------------------------
 __device__ void clip_single_plane(const FrameParams& P, uint32_t t, const V4& c0, const V4& c1, const V4& c2, uint32_t planes);
 
-__global__ void __launch_bounds__(256, 5) geom_kernel(const __grid_constant__ FrameParams P)
+// Stages a1, a2, a5, a6 for one submitted triangle with its vertex work done per corner (front end 0 / 1), then routing.
+__device__ __forceinline__ void geom_triangle(const FrameParams& P, uint32_t t)
 {
-    // Programmatic dependent launch: the grid may be scheduled while the previous kernel in the stream is
-    // still draining; everything before this point touches no global memory.
-    cudaGridDependencySynchronize();
-    if (P.clusterCull) {
-        // Cluster cull: if all 8 corners of this CTA's 256-triangle bounding box are outside the SAME clip plane
-        // by a margin that dominates fp32 rounding of the transform, every vertex of the cluster is outside that
-        // plane too, i.e. every triangle would be rejected by Clipper.h:109. Exact, and the CTA loads nothing else.
-        // Eight lanes of warp 0 take one corner each; the verdict reaches the CTA through shared memory.
-        __shared__ uint32_t sOut;
-        if (threadIdx.x < 32) {
-            const float4 bl = __ldg(P.clusterBox + 2 * blockIdx.x), bh = __ldg(P.clusterBox + 2 * blockIdx.x + 1);
-            const float* M = P.mvp;
-            // Largest magnitude any vertex of the box can reach in each row's sum: bounds the fp32 rounding error
-            // (4 roundings, < 2.5e-7 of this) of EVERY vertex in the box; the margin is 16x that.
-            const float ax = fmaxf(fabsf(bl.x), fabsf(bh.x)), ay = fmaxf(fabsf(bl.y), fabsf(bh.y)), az = fmaxf(fabsf(bl.z), fabsf(bh.z));
-            const float mx = fabsf(M[0]) * ax + fabsf(M[1]) * ay + fabsf(M[2]) * az + fabsf(M[3]);
-            const float my = fabsf(M[4]) * ax + fabsf(M[5]) * ay + fabsf(M[6]) * az + fabsf(M[7]);
-            const float mz = fabsf(M[8]) * ax + fabsf(M[9]) * ay + fabsf(M[10]) * az + fabsf(M[11]);
-            const float mw = fabsf(M[12]) * ax + fabsf(M[13]) * ay + fabsf(M[14]) * az + fabsf(M[15]);
-            const float ex = 4e-6f * (mx + mw), ey = 4e-6f * (my + mw), ez = 4e-6f * (mz + mw);
-            const int k = threadIdx.x & 7;
-            const V4 c = to_clip(M, (k & 1) ? bh.x : bl.x, (k & 2) ? bh.y : bl.y, (k & 4) ? bh.z : bl.z);
-            uint32_t o = 0;
-            if (c.x < -c.w - ex) o |= LEFT_BIT;
-            if (c.x > c.w + ex) o |= RIGHT_BIT;
-            if (c.y < -c.w - ey) o |= BOTTOM_BIT;
-            if (c.y > c.w + ey) o |= TOP_BIT;
-            if (c.z > c.w + ez) o |= FAR_BIT;
-            if (c.z < -ez) o |= NEAR_BIT;
-            o = __reduce_and_sync(0xFFFFFFFFu, o);          // lanes 8..31 repeat corners 0..7
-            if (threadIdx.x == 0) sOut = bl.w != 0.0f ? o : 0u;
-        }
-        __syncthreads();
-        if (sOut) return;
-    }
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= P.nTris) return;
     uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
     float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
     V4 c0 = to_clip(P.mvp, p0.x, p0.y, p0.z);
@@ -364,6 +370,184 @@ __global__ void __launch_bounds__(256, 5) geom_kernel(const __grid_constant__ Fr
     // Renderer.cpp:139-147: invW = 1/w, z = z * invW
     const float iw0 = inv_w(c0.w), iw1 = inv_w(c1.w), iw2 = inv_w(c2.w);
     route_triangle(P, s, fmul(c0.z, iw0), fmul(c1.z, iw1), fmul(c2.z, iw2), iw0, iw1, iw2, t * 8u, P.smallMax);
+}
+
+__global__ void __launch_bounds__(256, 5) geom_kernel(const __grid_constant__ FrameParams P)
+{
+    // Programmatic dependent launch: the grid may be scheduled while the previous kernel in the stream is
+    // still draining; everything before this point touches no global memory.
+    cudaGridDependencySynchronize();
+    if (P.clusterCull) {
+        // Cluster cull: if all 8 corners of this CTA's 256-triangle bounding box are outside the SAME clip plane
+        // by a margin that dominates fp32 rounding of the transform, every vertex of the cluster is outside that
+        // plane too, i.e. every triangle would be rejected by Clipper.h:109. Exact, and the CTA loads nothing else.
+        // Eight lanes of warp 0 take one corner each; the verdict reaches the CTA through shared memory.
+        __shared__ uint32_t sOut;
+        if (threadIdx.x < 32) {
+            const float4 bl = __ldg(P.clusterBox + 2 * blockIdx.x), bh = __ldg(P.clusterBox + 2 * blockIdx.x + 1);
+            const float* M = P.mvp;
+            // Largest magnitude any vertex of the box can reach in each row's sum: bounds the fp32 rounding error
+            // (4 roundings, < 2.5e-7 of this) of EVERY vertex in the box; the margin is 16x that.
+            const float ax = fmaxf(fabsf(bl.x), fabsf(bh.x)), ay = fmaxf(fabsf(bl.y), fabsf(bh.y)), az = fmaxf(fabsf(bl.z), fabsf(bh.z));
+            const float mx = fabsf(M[0]) * ax + fabsf(M[1]) * ay + fabsf(M[2]) * az + fabsf(M[3]);
+            const float my = fabsf(M[4]) * ax + fabsf(M[5]) * ay + fabsf(M[6]) * az + fabsf(M[7]);
+            const float mz = fabsf(M[8]) * ax + fabsf(M[9]) * ay + fabsf(M[10]) * az + fabsf(M[11]);
+            const float mw = fabsf(M[12]) * ax + fabsf(M[13]) * ay + fabsf(M[14]) * az + fabsf(M[15]);
+            const float ex = 4e-6f * (mx + mw), ey = 4e-6f * (my + mw), ez = 4e-6f * (mz + mw);
+            const int k = threadIdx.x & 7;
+            const V4 c = to_clip(M, (k & 1) ? bh.x : bl.x, (k & 2) ? bh.y : bl.y, (k & 4) ? bh.z : bl.z);
+            uint32_t o = 0;
+            if (c.x < -c.w - ex) o |= LEFT_BIT;
+            if (c.x > c.w + ex) o |= RIGHT_BIT;
+            if (c.y < -c.w - ey) o |= BOTTOM_BIT;
+            if (c.y > c.w + ey) o |= TOP_BIT;
+            if (c.z > c.w + ez) o |= FAR_BIT;
+            if (c.z < -ez) o |= NEAR_BIT;
+            o = __reduce_and_sync(0xFFFFFFFFu, o);          // lanes 8..31 repeat corners 0..7
+            if (threadIdx.x == 0) sOut = bl.w != 0.0f ? o : 0u;
+        }
+        __syncthreads();
+        if (sOut) return;
+    }
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.nTris) return;
+    geom_triangle(P, t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// List front end (FrameParams::frontEnd 1 / 2), for large meshes:
+//   cull_kernel       one THREAD per cluster: the frustum test geom_kernel's CTAs do for themselves, once, for every
+//                     256-triangle cluster (survivors are compacted into workList) and every 256-vertex cluster (flag).
+//                     geom_kernel pays a launch + a dependent load + a barrier per culled CTA (a fifth of its
+//                     stall samples on the 10M-triangle grid); here culled clusters cost one thread each.
+//   vertex_kernel     stages a1, a2, a5 (project, raster transform, snap), a6 once per vertex of every unflagged
+//                     vertex cluster (Renderer::VertexProcessing is per vertex too, Renderer.cpp:120-127) -> vrec.
+//   geom_list_kernel  persistent: CTAs take surviving clusters off the list (static first item, then tickets).
+// ---------------------------------------------------------------------------------------------
+// Clip planes that ALL eight corners of the box are outside of, by a margin that dominates the fp32 rounding of the
+// transform of any point in the box: every vertex inside the box then has that bit in its clip code. 0 for an
+// invalid box (NaN / inf coordinates).
+__device__ __forceinline__ uint32_t box_outside_planes(const float* M, const float4 bl, const float4 bh)
+{
+    if (bl.w == 0.0f) return 0u;
+    const float ax = fmaxf(fabsf(bl.x), fabsf(bh.x)), ay = fmaxf(fabsf(bl.y), fabsf(bh.y)), az = fmaxf(fabsf(bl.z), fabsf(bh.z));
+    const float mx = fabsf(M[0]) * ax + fabsf(M[1]) * ay + fabsf(M[2]) * az + fabsf(M[3]);
+    const float my = fabsf(M[4]) * ax + fabsf(M[5]) * ay + fabsf(M[6]) * az + fabsf(M[7]);
+    const float mz = fabsf(M[8]) * ax + fabsf(M[9]) * ay + fabsf(M[10]) * az + fabsf(M[11]);
+    const float mw = fabsf(M[12]) * ax + fabsf(M[13]) * ay + fabsf(M[14]) * az + fabsf(M[15]);
+    const float ex = 4e-6f * (mx + mw), ey = 4e-6f * (my + mw), ez = 4e-6f * (mz + mw);
+    uint32_t all = 63u;
+    #pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const V4 c = to_clip(M, (k & 1) ? bh.x : bl.x, (k & 2) ? bh.y : bl.y, (k & 4) ? bh.z : bl.z);
+        uint32_t o = 0;
+        if (c.x < -c.w - ex) o |= LEFT_BIT;
+        if (c.x > c.w + ex) o |= RIGHT_BIT;
+        if (c.y < -c.w - ey) o |= BOTTOM_BIT;
+        if (c.y > c.w + ey) o |= TOP_BIT;
+        if (c.z > c.w + ez) o |= FAR_BIT;
+        if (c.z < -ez) o |= NEAR_BIT;
+        all &= o;
+    }
+    return all;
+}
+
+__global__ void __launch_bounds__(256) cull_kernel(const __grid_constant__ FrameParams P)
+{
+    cudaGridDependencySynchronize();
+    const uint32_t j = blockIdx.x * 256u + threadIdx.x;
+    if (j < P.nTriClusters) {
+        const uint32_t out = P.clusterCull ? box_outside_planes(P.mvp, __ldg(P.clusterBox + 2 * j), __ldg(P.clusterBox + 2 * j + 1)) : 0u;
+        if (!out) P.workList[warp_append(&P.counters->nWork)] = j;
+    } else if (j - P.nTriClusters < P.nVertClusters && P.frontEnd == 2) {
+        const uint32_t v = j - P.nTriClusters;
+        P.vcFlag[v] = P.clusterCull ? box_outside_planes(P.mvp, __ldg(P.vclusterBox + 2 * v), __ldg(P.vclusterBox + 2 * v + 1)) : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) vertex_kernel(const __grid_constant__ FrameParams P)
+{
+    cudaGridDependencySynchronize();
+    for (uint32_t vc = blockIdx.x; vc < P.nVertClusters; vc += gridDim.x) {
+        if (P.vcFlag[vc]) continue;                     // every vertex of it is outside one plane: the flag stands in for the records
+        const uint32_t v = vc * 256u + threadIdx.x;
+        if (v >= P.nVerts) continue;
+        const float4 p = __ldg(P.pos4 + v);
+        const V4 c = to_clip(P.mvp, p.x, p.y, p.z);                          // a1
+        const uint32_t code = surely_inside(c) ? 0u : clip_code(c);         // a2
+        int4 rec;
+        if (code) {
+            rec = make_int4(0, 0, 0, (int)(VREC_OUTSIDE | code));
+        } else {
+            int sx, sy;
+            project_snap(P.raster, P.rasterAffineXY != 0, c, sx, sy);       // a5: the part of Setup that depends on one vertex only
+            const float iw = inv_w(c.w);                                     // a6
+            const float zw = fmul(c.z, iw);
+            rec = make_int4(sx, sy, __float_as_int(zw), iw != iw ? 0x7FFFFFFF : __float_as_int(iw));
+        }
+        P.vrec[v] = rec;
+    }
+}
+
+__device__ __forceinline__ int4 load_vrec(const FrameParams& P, uint32_t i)
+{
+    const uint32_t f = __ldg(P.vcFlag + (i >> 8));
+    return f ? make_int4(0, 0, 0, (int)(VREC_OUTSIDE | f)) : __ldg(P.vrec + i);
+}
+
+// One submitted triangle from the per-vertex records (front end 2). Same arithmetic as geom_triangle - what
+// project_snap / inv_w / z*invW compute depends on the vertex only - so the results are bit-identical.
+__device__ __forceinline__ void geom_triangle_vrec(const FrameParams& P, uint32_t t)
+{
+    const uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
+    const int4 r0 = load_vrec(P, i0), r1 = load_vrec(P, i1), r2 = load_vrec(P, i2);
+    const uint32_t k0 = vrec_code(r0.w), k1 = vrec_code(r1.w), k2 = vrec_code(r2.w);
+    if (k0 | k1 | k2) {
+        if (k0 & k1 & k2) return;                        // Clipper.h:109
+        // Straddler (rare): its clip-space vertices travel with it, so transform the three corners here. A flagged
+        // cluster only reports ONE plane bit per vertex, so the reject test is repeated with the exact codes.
+        const float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
+        const V4 c0 = to_clip(P.mvp, p0.x, p0.y, p0.z), c1 = to_clip(P.mvp, p1.x, p1.y, p1.z), c2 = to_clip(P.mvp, p2.x, p2.y, p2.z);
+        if (clip_code(c0) & clip_code(c1) & clip_code(c2)) return;
+        const uint32_t at = warp_append(&P.counters->nClipQueue);
+        if (at < P.clipQueueCap) {
+            float4* q = reinterpret_cast<float4*>(P.clipQueue + at);
+            q[0] = make_float4(c0.x, c0.y, c0.z, c0.w); q[1] = make_float4(c1.x, c1.y, c1.z, c1.w);
+            q[2] = make_float4(c2.x, c2.y, c2.z, c2.w); q[3] = make_float4(__uint_as_float(t), 0.0f, 0.0f, 0.0f);
+        }
+        return;
+    }
+    SetupTri s;
+    s.v0x = r0.x; s.v0y = r0.y; s.v1x = r1.x; s.v1y = r1.y; s.v2x = r2.x; s.v2y = r2.y;
+    if (!P.dump) {
+        const bool ms = P.samples > 1;               // exact early cull: no pixel centre in the box
+        if (max(0, first_pixel(min3i(s.v0x, s.v1x, s.v2x), ms)) > min(P.width - 1, last_pixel(max3i(s.v0x, s.v1x, s.v2x), ms)) ||
+            max(0, first_pixel(min3i(s.v0y, s.v1y, s.v2y), ms)) > min(P.height - 1, last_pixel(max3i(s.v0y, s.v1y, s.v2y), ms)))
+            return;
+    }
+    if (!finish_setup(s)) return;
+    route_triangle(P, s, __int_as_float(r0.z), __int_as_float(r1.z), __int_as_float(r2.z),
+                   __int_as_float(r0.w), __int_as_float(r1.w), __int_as_float(r2.w), t * 8u, P.smallMax);
+}
+
+template <bool VREC>
+__global__ void __launch_bounds__(256, 5) geom_list_kernel(const __grid_constant__ FrameParams P)
+{
+    __shared__ uint32_t sNext;
+    cudaGridDependencySynchronize();
+    const uint32_t n = P.counters->nWork;
+    uint32_t cur = blockIdx.x;
+    while (cur < n) {
+        if (threadIdx.x == 0) sNext = atomicAdd(&P.counters->ticket, 1u) + gridDim.x;   // fetched while this cluster is processed
+        const uint32_t t = __ldg(P.workList + cur) * 256u + threadIdx.x;
+        if (t < P.nTris) {
+            if (VREC) geom_triangle_vrec(P, t);
+            else geom_triangle(P, t);
+        }
+        __syncthreads();
+        cur = sNext;
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -482,7 +666,9 @@ __device__ __noinline__ void emit_fan(const FrameParams& P, uint32_t t, int fan,
         #pragma unroll
         for (int m = 0; m < 6; m++) dst[m] = src[m];
     }
-    if (ok) route_triangle(P, s, zA, fmul(f1.z, iwB), fmul(f2.z, iwC), iwA, iwB, iwC, t * 8u + (uint32_t)fan, P.smallMaxClip);
+    // without a record the resolve pass could not shade this fan triangle: the frame is incomplete and will be re-run
+    // with larger queues (finish_frame), so do not leave keys that point at a record that was never written
+    if (ok && haveRecs) route_triangle(P, s, zA, fmul(f1.z, iwB), fmul(f2.z, iwC), iwA, iwB, iwC, t * 8u + (uint32_t)fan, P.smallMaxClip);
 }
 
 __device__ __forceinline__ V4 pick3(const V4* c, uint32_t i) { return i == 0 ? c[0] : (i == 1 ? c[1] : c[2]); }
@@ -608,6 +794,70 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
 }
 
 // ---------------------------------------------------------------------------------------------
+// mid_kernel: stages a10, a12, a13 for mid-size triangles, one WARP per triangle. The lanes form an 8 x 4 pixel
+// block that steps over the triangle's pixel-centre box; each lane evaluates the three biased edge functions of its
+// pixel (Rasterizer.h:162) from integer steps, and covered pixels go through the same barycentric / depth / key
+// arithmetic as everywhere else into the L2-resident key buffer (atomicMin = the sequential depth test).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mid_kernel(const __grid_constant__ FrameParams P)
+{
+    cudaGridDependencySynchronize();
+    const uint32_t n = min(P.counters->nMid, P.midCap);
+    const uint32_t lane = threadIdx.x & 31u, nWarps = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const bool ms = P.samples > 1;
+    const int lx = (int)(lane & 7u), ly = (int)(lane >> 3);
+    for (uint32_t q = gw; q < n; q += nWarps) {
+        const int4* rp = reinterpret_cast<const int4*>(P.mid + q);
+        const int4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);      // same address in every lane: one broadcast transaction each
+        const float z0 = __int_as_float(b.z), z1 = __int_as_float(b.w), z2 = __int_as_float(c.x), invDet = __int_as_float(c.y);
+        const uint32_t prim = (uint32_t)c.z;
+        Edges e;
+        e.init(a.x, a.y, a.z, a.w, b.x, b.y);
+        const int x0 = max(0, first_pixel(min3i(a.x, a.z, b.x), ms)), x1 = min(P.width - 1, last_pixel(max3i(a.x, a.z, b.x), ms));
+        const int y0 = max(0, first_pixel(min3i(a.y, a.w, b.y), ms)), y1 = min(P.height - 1, last_pixel(max3i(a.y, a.w, b.y), ms));
+        // biased edge values at this lane's pixel of the first block; a block step is 8 pixels in x, 4 in y
+        const int cx = ((x0 + lx) << 4) + 8, cy = ((y0 + ly) << 4) + 8;
+        uint32_t r0 = (uint32_t)e.e0(cx, cy), r1 = (uint32_t)e.e1(cx, cy), r2 = (uint32_t)e.e2(cx, cy);
+        const uint32_t sB0 = e.B0 << 7, sB1 = e.B1 << 7, sB2 = e.B2 << 7;     // 8 pixels = 128 sub-pixels
+        const uint32_t sC0 = e.C0 << 6, sC1 = e.C1 << 6, sC2 = e.C2 << 6;     // 4 pixels = 64 sub-pixels
+        for (int by = y0; by <= y1; by += 4) {
+            uint32_t a0 = r0, a1 = r1, a2 = r2;
+            const int y = by + ly;
+            for (int bx = x0; bx <= x1; bx += 8) {
+                const int x = bx + lx;
+                if (x <= x1 && y <= y1) {
+                    if (!ms) {
+                        if ((int)(a0 | a1 | a2) >= 0) {
+                            float l0, l1;
+                            barycentric((int)(a1 - (uint32_t)e.bias1), (int)(a2 - (uint32_t)e.bias2), invDet, l0, l1);
+                            const float d = depth_at(l0, l1, z0, z1, z2);
+                            if (d <= 1.0f && owns_pixel(x, y, P.binsX, P.part, P.parts))
+                                atomicMin(P.keys + key_index(x, y, P.binsX), make_key(d, prim));
+                        }
+                    } else {
+                        const int* off = c_sampleOffsets[P.msLevel];
+                        const uint32_t ki = key_index(x, y, P.binsX);
+                        const bool owned = owns_pixel(x, y, P.binsX, P.part, P.parts);
+                        for (int sId = 0; sId < P.samples; sId++) {
+                            const uint32_t ox = (uint32_t)off[2 * sId], oy = ox;      // DESIGN.md shim 17
+                            const uint32_t f0 = a0 + ox * e.B0 + oy * e.C0, f1 = a1 + ox * e.B1 + oy * e.C1, f2 = a2 + ox * e.B2 + oy * e.C2;
+                            if ((int)(f0 | f1 | f2) >= 0) {
+                                float l0, l1;
+                                barycentric((int)(f1 - (uint32_t)e.bias1), (int)(f2 - (uint32_t)e.bias2), invDet, l0, l1);
+                                const float d = depth_at(l0, l1, z0, z1, z2);
+                                if (d <= 1.0f && owned) atomicMin(P.keys + (size_t)sId * P.keyStride + ki, make_key(d, prim));
+                            }
+                        }
+                    }
+                }
+                a0 += sB0; a1 += sB1; a2 += sB2;
+            }
+            r0 += sC0; r1 += sC1; r2 += sC2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // tile_kernel helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t order_f32(float f)
@@ -716,7 +966,7 @@ __device__ __forceinline__ uint8_t to_u8(float c)       // Color4b::FromFloats (
     return (uint8_t)__float2int_rz(s);
 }
 
-__device__ __forceinline__ float rsqrt_exact(float x) { return fdiv(1.0f, __fsqrt_rn(x)); }   // DESIGN.md shim 9
+__device__ __forceinline__ float rsqrt_exact(float x) { return frcp(__fsqrt_rn(x)); }   // DESIGN.md shim 9
 
 // ---------------------------------------------------------------------------------------------
 // Texture2D<Color>::Sample (EDXUtil, absent): DESIGN.md shims 18-24, operation for operation as defined there.
@@ -811,7 +1061,7 @@ __device__ __forceinline__ void tex_sample(const FrameParams& P, const TexDesc* 
             tex_trilinear(P, t, fadd(u, fmul(mu, s)), fadd(v, fmul(mv, s)), width, cr, cg, cb);
             ar = fadd(ar, cr); ag = fadd(ag, cg); ab = fadd(ab, cb);
         }
-        const float inv = fdiv(1.0f, (float)n);
+        const float inv = frcp((float)n);
         r = fmul(ar, inv); g = fmul(ag, inv); b = fmul(ab, inv);
     }
 }
@@ -847,7 +1097,7 @@ __device__ __noinline__ float3 albedo_textured(const FrameParams& P, const TexQu
         barycentric((int)(q.B1 * ex + q.C1 * ey), (int)(q.B2 * ex + q.C2 * ey), q.invDet, q0, q1);
         float q2 = fsub(fsub(1.0f, q0), q1);
         q0 = fmul(q0, q.iw0); q1 = fmul(q1, q.iw1); q2 = fmul(q2, q.iw2);
-        const float iq = fdiv(1.0f, fadd(fadd(q0, q1), q2));
+        const float iq = frcp(fadd(fadd(q0, q1), q2));
         q0 = fmul(q0, iq); q1 = fmul(q1, iq);
         q2 = fsub(fsub(1.0f, q0), q1);
         u = blend3(q0, q1, q2, q.tu[0], q.tu[1], q.tu[2]);
@@ -874,24 +1124,44 @@ __device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim
     const uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
     const float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
     const float4 n0 = __ldg(P.nrm4 + i0), n1 = __ldg(P.nrm4 + i1), n2 = __ldg(P.nrm4 + i2);
-    const V4 c0 = to_clip(P.mvp, p0.x, p0.y, p0.z), c1 = to_clip(P.mvp, p1.x, p1.y, p1.z), c2 = to_clip(P.mvp, p2.x, p2.y, p2.z);
 
     int v1x, v1y, v2x, v2y, v0y, v0x;
     float invDet, iw0, iw1, iw2;
     float A[3][6];                     // position.xyz, normal.xyz of the three (fan) vertices
     float TU[3], TV[3];                // their texture coordinates (only the textured shader reads them)
     const bool textured = TEX;
-    if ((clip_code(c0) | clip_code(c1) | clip_code(c2)) == 0) {
-        SetupTri s;
-        setup_tri(P.raster, P.rasterAffineXY != 0, c0, c1, c2, s);
-        v0x = s.v0x; v0y = s.v0y; v1x = s.v1x; v1y = s.v1y; v2x = s.v2x; v2y = s.v2y; invDet = s.invDet;
-        iw0 = inv_w(c0.w); iw1 = inv_w(c1.w); iw2 = inv_w(c2.w);
+    bool unclipped;
+    if (P.vrec) {
+        // front end 2: the owner's vertices were set up once per vertex this frame; gather the records instead of
+        // transforming, projecting, snapping and inverting w again for every pixel
+        const int4 r0 = load_vrec(P, i0), r1 = load_vrec(P, i1), r2 = load_vrec(P, i2);
+        unclipped = (vrec_code(r0.w) | vrec_code(r1.w) | vrec_code(r2.w)) == 0u;
+        if (unclipped) {
+            SetupTri s;
+            s.v0x = r0.x; s.v0y = r0.y; s.v1x = r1.x; s.v1y = r1.y; s.v2x = r2.x; s.v2y = r2.y;
+            finish_setup(s);
+            v0x = s.v0x; v0y = s.v0y; v1x = s.v1x; v1y = s.v1y; v2x = s.v2x; v2y = s.v2y; invDet = s.invDet;
+            iw0 = __int_as_float(r0.w); iw1 = __int_as_float(r1.w); iw2 = __int_as_float(r2.w);
+        }
+    } else {
+        const V4 c0 = to_clip(P.mvp, p0.x, p0.y, p0.z), c1 = to_clip(P.mvp, p1.x, p1.y, p1.z), c2 = to_clip(P.mvp, p2.x, p2.y, p2.z);
+        unclipped = (clip_code(c0) | clip_code(c1) | clip_code(c2)) == 0;
+        if (unclipped) {
+            SetupTri s;
+            setup_tri(P.raster, P.rasterAffineXY != 0, c0, c1, c2, s);
+            v0x = s.v0x; v0y = s.v0y; v1x = s.v1x; v1y = s.v1y; v2x = s.v2x; v2y = s.v2y; invDet = s.invDet;
+            iw0 = inv_w(c0.w); iw1 = inv_w(c1.w); iw2 = inv_w(c2.w);
+        }
+    }
+    if (unclipped) {
         A[0][0] = p0.x; A[0][1] = p0.y; A[0][2] = p0.z; A[0][3] = n0.x; A[0][4] = n0.y; A[0][5] = n0.z;
         A[1][0] = p1.x; A[1][1] = p1.y; A[1][2] = p1.z; A[1][3] = n1.x; A[1][4] = n1.y; A[1][5] = n1.z;
         A[2][0] = p2.x; A[2][1] = p2.y; A[2][2] = p2.z; A[2][3] = n2.x; A[2][4] = n2.y; A[2][5] = n2.z;
         TU[0] = n0.w; TU[1] = n1.w; TU[2] = n2.w; TV[0] = p0.w; TV[1] = p1.w; TV[2] = p2.w;
     } else {
-        const ClipRec* rp = P.clipRecs + (__ldg(P.clipSlot + t) + fan);
+        const uint32_t recAt = __ldg(P.clipSlot + t) + fan;
+        if (recAt >= P.clipRecCap) return make_uchar4(0, 0, 0, 255);       // overflowed frame (re-run by finish_frame): never read past the records
+        const ClipRec* rp = P.clipRecs + recAt;
         const int4 w0 = __ldg(reinterpret_cast<const int4*>(rp));
         const int4 w1 = __ldg(reinterpret_cast<const int4*>(rp) + 1);
         const float4 w2 = __ldg(reinterpret_cast<const float4*>(rp) + 2);
@@ -928,7 +1198,7 @@ __device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim
     // Fragment::Interpolate, Shader.h:151-159
     float b2 = fsub(fsub(1.0f, b0), b1);
     b0 = fmul(b0, iw0); b1 = fmul(b1, iw1); b2 = fmul(b2, iw2);
-    const float invB = fdiv(1.0f, fadd(fadd(b0, b1), b2));
+    const float invB = frcp(fadd(fadd(b0, b1), b2));
     b0 = fmul(b0, invB); b1 = fmul(b1, invB);
     b2 = fsub(fsub(1.0f, b0), b1);
     const float posx = blend3(b0, b1, b2, A[0][0], A[1][0], A[2][0]);
@@ -1114,17 +1384,17 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     // every load first (nine independent L2 reads in flight), then the stores from registers; no fence: the host
     // reads the pinned copy only after the stream has completed this kernel
     volatile Counters* d = P.counters;
-    const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs;
+    const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid;
     uint32_t overFrames = d->overFrames;
-    const uint32_t maxBig = max(d->maxBig, nBig), maxClipQueue = max(d->maxClipQueue, nClipQueue), maxClipRecs = max(d->maxClipRecs, nClipRecs);
+    const uint32_t maxBig = max(d->maxBig, nBig), maxClipQueue = max(d->maxClipQueue, nClipQueue), maxClipRecs = max(d->maxClipRecs, nClipRecs), maxMid = max(d->maxMid, nMid);
 #ifdef EDX_DEBUG_STATS
     for (int i = 0; i < 8; i++) { P.hostCounters->dbg[i] = P.counters->dbg[i]; P.counters->dbg[i] = 0; }
 #endif
-    if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap) overFrames++;
-    d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->done = 0; d->tilePairs = 0;
-    d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs;
+    if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap || nMid > P.midCap) overFrames++;
+    d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0;
+    d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs; d->maxMid = maxMid;
     volatile Counters* h = P.hostCounters;
-    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs;
+    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid;
     h->overFrames = overFrames; h->maxBig = maxBig; h->maxClipQueue = maxClipQueue; h->maxClipRecs = maxClipRecs;
 }
 
@@ -1187,6 +1457,7 @@ __global__ void __launch_bounds__(256) lean_resolve_kernel(const __grid_constant
 }
 
 #ifdef EDX_DEBUG_STATS
+__device__ unsigned long long g_binDbg[8192][6];   // per bin: cycles cand / sweep / flush+final raster / resolve, candidates, survivors
 __device__ uint32_t g_tileResident[512];       // [sm] live tile_kernel CTAs, [256 + sm] the most seen at once
 struct ResidentScope {
     uint32_t sm;
@@ -1359,6 +1630,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         atomicAdd(&P.counters->dbg[2], (unsigned long long)tFlush); atomicAdd(&P.counters->dbg[3], (unsigned long long)tFinal);
         atomicAdd(&P.counters->dbg[4], (unsigned long long)nFlush); atomicAdd(&P.counters->dbg[5], (unsigned long long)nSurvTot);
         atomicAdd(&P.counters->dbg[6], 1ull);
+        if (bin < 8192) { g_binDbg[bin][0] = tCand; g_binDbg[bin][1] = tSweep - tFlush; g_binDbg[bin][2] = tFlush + tFinal; g_binDbg[bin][5] = nSurvTot; }
     }
     tMark = clock64();
 #endif
@@ -1383,7 +1655,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     }
 #ifdef EDX_DEBUG_STATS
     __syncthreads();
-    if (tid == 0) atomicAdd(&P.counters->dbg[7], (unsigned long long)(clock64() - tMark));
+    if (tid == 0) { atomicAdd(&P.counters->dbg[7], (unsigned long long)(clock64() - tMark)); if (bin < 8192) g_binDbg[bin][3] = clock64() - tMark; }
 #endif
 }
 
@@ -1426,7 +1698,7 @@ __global__ void __launch_bounds__(256) msaa_resolve_kernel(const __grid_constant
             }
         }
         if (P.shader != SH_DEPTH_ONLY) {
-            const float inv = fdiv(1.0f, (float)P.samples);
+            const float inv = frcp((float)P.samples);
             P.color[at] = make_uchar4(to_u8(fmul(acc[0], inv)), to_u8(fmul(acc[1], inv)), to_u8(fmul(acc[2], inv)), to_u8(fmul(acc[3], inv)));
         }
     }

@@ -24,6 +24,7 @@ struct edx_mesh {
     // Mesh::mTextures + per-triangle slot (Utils/Mesh.h:23,54-59); nTex == 0: the context's constant albedo
     TexDesc* texDesc = nullptr; uchar4* texels = nullptr; uint32_t* texIds = nullptr; uint32_t nTex = 0;
     float4* clusterBox = nullptr;                          // 2 x float4 per 256-triangle cluster
+    float4* vclusterBox = nullptr;                         // 2 x float4 per 256-vertex cluster (list front end)
     void* staging = nullptr; size_t stagingBytes = 0;     // device-side landing area for the AoS upload
     uint32_t nVerts = 0, nTris = 0, capVerts = 0, capTris = 0;
     bool coherent = false;                                 // triangle order is spatially coherent: cluster culling pays
@@ -42,7 +43,14 @@ struct edx_context {
     float eye[3], light[3], albedo[3];
     int shader = EDX_SHADER_LAMBERT_ALBEDO;   // the reference installs LambertianAlbedoPixelShader (Renderer.cpp:41)
     int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
-    int smallMax = 32, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1, part = 0, parts = 1;
+    int smallMax = 8, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1, part = 0, parts = 1;
+    MidRec* mid = nullptr; uint32_t midCap = 0;
+    int midMax = 64;                         // boxes from smallMax up to this go to mid_kernel (one warp per triangle); 0 = none
+    int frontEnd = -1;                       // -1 auto, 0 geom_kernel, 1 cull + list, 2 cull + per-vertex stage + list (FrameParams::frontEnd)
+    int frontEndUsed = 0;
+    uint32_t* workList = nullptr; uint32_t workListCap = 0;
+    uint32_t* vcFlag = nullptr; uint32_t vcFlagCap = 0;
+    int4* vrec = nullptr; uint32_t vrecCap = 0;
     int leanResolve = 0;                     // 0 never (default: measured slower with frames in flight), 1 when the last vetted frame had an empty tile path, 2 always
     int clipCarveout = 0;                    // 0 auto (follow the tile path's load), 1 prefer L1, 2 prefer shared memory
     bool colorDirty = false;
@@ -143,7 +151,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     memcpy(P.eye, c->eye, 12); memcpy(P.light, c->light, 12); memcpy(P.albedo, c->albedo, 12);
     P.width = (int)c->width; P.height = (int)c->height; P.binsX = (int)c->binsX; P.binsY = (int)c->binsY;
     P.shader = c->shader; P.smallMax = c->smallMax; P.smallMaxClip = c->smallMaxClip; P.hiz = c->hiz; P.hierarchical = c->hierarchical;
-    P.captureIds = c->captureIds; P.dump = 0;
+    P.captureIds = c->captureIds; P.dump = 0; P.midMax = c->midMax; P.mid = c->mid; P.midCap = c->midCap;
     P.part = c->part; P.parts = c->parts;
     P.fuseClip = c->fuseClip; P.clusterCull = (c->clusterCull == 1 && m->coherent) || c->clusterCull == 2;
     P.msLevel = c->msaaLog2; P.samples = 1 << c->msaaLog2; P.keyStride = c->keyStride;
@@ -151,6 +159,8 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.rasterAffineXY = (Rm[2] == 0.0f && Rm[6] == 0.0f && Rm[12] == 0.0f && Rm[13] == 0.0f && Rm[14] == 0.0f && Rm[15] == 1.0f) ? 1 : 0;
     P.pos4 = m->pos4; P.nrm4 = m->nrm4; P.i0 = m->i0; P.i1 = m->i1; P.i2 = m->i2; P.clusterBox = m->clusterBox;
     P.nTris = m->nTris; P.nVerts = m->nVerts;
+    P.vclusterBox = m->vclusterBox; P.nTriClusters = (m->nTris + 255) / 256; P.nVertClusters = (m->nVerts + 255) / 256;
+    P.frontEnd = 0; P.workList = c->workList; P.vcFlag = c->vcFlag; P.vrec = nullptr;
     P.tex = m->texDesc; P.texels = m->texels; P.texIds = m->texIds; P.nTex = m->nTex; P.texFilter = c->texFilter;
     P.keys = c->keys;
     P.big = c->big; P.bigCap = c->bigCap; P.bigBox = c->bigBox;
@@ -167,12 +177,37 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     // initial queue sizes; grown on demand after a frame reports it needed more
     if (int r = grow(c, c->big, c->bigCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
     if (int r = grow(c, c->bigBox, c->bigBoxCap, c->bigCap)) return r;
+    if (int r = grow(c, c->mid, c->midCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
     if (int r = grow(c, c->clipQueue, c->clipQueueCap, std::max<uint64_t>(1u << 14, m->nTris / 32))) return r;
     if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
-    if (int r = grow(c, c->clipSlot, c->clipSlotCap, m->nTris)) return r;      // in the context, so a mesh is read-only while it renders
+    {
+        const uint32_t before = c->clipSlotCap;
+        if (int r = grow(c, c->clipSlot, c->clipSlotCap, m->nTris)) return r;  // in the context, so a mesh is read-only while it renders
+        // slots are written for straddlers only; a fresh allocation must not hold addresses (an overflowed frame's
+        // resolve may look one up before the frame is re-run)
+        if (c->clipSlotCap != before) EDX_CUDA(c, cudaMemsetAsync(c->clipSlot, 0, (size_t)c->clipSlotCap * 4, c->stream));
+    }
+
+    // Front end: large meshes cull their clusters once, on the device, into a work list; meshes that share vertices
+    // between triangles (at least two corners per vertex) additionally do the per-vertex work once per vertex.
+    int fe = c->frontEnd;
+    if (fe < 0) {
+        const bool large = m->nTris >= (1u << 18);
+        const bool shared = 2ull * m->nVerts <= 3ull * m->nTris;
+        const bool cull = (c->clusterCull == 1 && m->coherent) || c->clusterCull == 2;
+        fe = !large ? 0 : (shared ? 2 : (cull ? 1 : 0));
+    }
+    if (fe) {
+        if (int r = grow(c, c->workList, c->workListCap, (m->nTris + 255) / 256)) return r;
+        if (int r = grow(c, c->vcFlag, c->vcFlagCap, (m->nVerts + 255) / 256)) return r;
+        if (fe == 2) if (int r = grow(c, c->vrec, c->vrecCap, m->nVerts)) return r;
+    }
+    c->frontEndUsed = fe;
 
     FrameParams P;
     fill_params(c, m, P);
+    P.frontEnd = fe;
+    if (fe == 2) P.vrec = c->vrec;
     if (dumpBuf) { P.dump = 1; P.dumpBuf = dumpBuf; P.dumpCap = dumpCap; }
 
     if (c->shader == EDX_SHADER_DEPTH_ONLY && c->colorDirty) {
@@ -196,9 +231,18 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
         return cudaLaunchKernelEx(&cfg, kernel, P);
     };
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[0], c->stream));
-    if (m->nTris) EDX_CUDA(c, launch(geom_kernel, dim3((m->nTris + 255) / 256), dim3(256), 0));
+    if (m->nTris && fe == 0) {
+        EDX_CUDA(c, launch(geom_kernel, dim3((m->nTris + 255) / 256), dim3(256), 0));
+    } else if (m->nTris) {
+        const uint32_t nTC = (m->nTris + 255) / 256, nVC = (m->nVerts + 255) / 256;
+        EDX_CUDA(c, launch(cull_kernel, dim3((nTC + (fe == 2 ? nVC : 0) + 255) / 256), dim3(256), 0));
+        if (fe == 2) EDX_CUDA(c, launch(vertex_kernel, dim3(std::min(nVC, 148u * 8u)), dim3(256), 0));
+        if (fe == 2) EDX_CUDA(c, launch(geom_list_kernel<true>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0));
+        else EDX_CUDA(c, launch(geom_list_kernel<false>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0));
+    }
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[1], c->stream));
     if (m->nTris) EDX_CUDA(c, launch(clip_kernel, dim3(148 * 4), dim3(128), 0));
+    if (m->nTris && c->midMax > 0) EDX_CUDA(c, launch(mid_kernel, dim3(148 * 4), dim3(128), 0));
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[2], c->stream));
     const bool textured = c->shader == EDX_SHADER_LAMBERT_ALBEDO && m->nTex != 0;
     const bool lean = c->msaaLog2 == 0 && (c->leanResolve == 2 || (c->leanResolve == 1 && c->stats.binned_tris == 0));
@@ -263,9 +307,9 @@ int finish_frame(edx_context* c)
     uint32_t repaired = 0;
     for (int attempt = 0; attempt < 8; attempt++) {
         const Counters k = *c->hostCounters;
-        const bool over = k.nBig > c->bigCap || k.nClipQueue > c->clipQueueCap || k.nClipRecs > c->clipRecCap;
+        const bool over = k.nBig > c->bigCap || k.nClipQueue > c->clipQueueCap || k.nClipRecs > c->clipRecCap || k.nMid > c->midCap;
         c->stats.binned_tris = k.nBig; c->stats.clipped_tris = k.nClipQueue; c->stats.clip_records = k.nClipRecs;
-        c->stats.tile_pairs = k.tilePairs;
+        c->stats.tile_pairs = k.tilePairs; c->stats.mid_tris = k.nMid;
 #ifdef EDX_DEBUG_STATS
         if (getenv("EDX_DEBUG_PRINT")) {
             uint32_t h[512];
@@ -275,6 +319,25 @@ int finish_frame(edx_context* c)
                 fprintf(stderr, "[edx dbg] tile_kernel CTAs resident per SM (max seen): %d SMs x1, %d SMs x2, %d SMs x3+\n", hist[1], hist[2], hist[3]);
                 memset(h, 0, sizeof(h));
                 cudaMemcpyToSymbol(g_tileResident, h, sizeof(h));
+            }
+        }
+        if (getenv("EDX_DEBUG_PRINT") && k.dbg[6]) {
+            static unsigned long long hb[8192][6];
+            if (cudaMemcpyFromSymbol(hb, g_binDbg, sizeof(hb)) == cudaSuccess) {
+                const int nb = std::min<int>(8192, c->binsX * c->binsY);
+                std::vector<int> order(nb);
+                for (int i = 0; i < nb; i++) order[i] = i;
+                auto tot = [&](int i) { return hb[i][0] + hb[i][1] + hb[i][2] + hb[i][3]; };
+                std::sort(order.begin(), order.end(), [&](int a, int b) { return tot(a) > tot(b); });
+                unsigned long long sum = 0;
+                for (int i = 0; i < nb; i++) sum += tot(i);
+                fprintf(stderr, "[edx dbg] per-bin cycles: mean %llu; heaviest bins (bin: cand sweep raster resolve | survivors)\n", sum / std::max(nb, 1));
+                for (int i = 0; i < std::min(nb, 10); i++) {
+                    const int b = order[i];
+                    fprintf(stderr, "[edx dbg]   bin %4d (%2d,%2d): %7llu %7llu %7llu %7llu | %llu\n", b, b % (int)c->binsX, b / (int)c->binsX, hb[b][0], hb[b][1], hb[b][2], hb[b][3], hb[b][5]);
+                }
+                memset(hb, 0, sizeof(hb));
+                cudaMemcpyToSymbol(g_binDbg, hb, sizeof(hb));
             }
         }
         if (getenv("EDX_DEBUG_PRINT") && k.dbg[6])
@@ -296,6 +359,7 @@ int finish_frame(edx_context* c)
             if (lost) {
                 if (int r = grow(c, c->big, c->bigCap, (uint64_t)k.maxBig + (k.maxClipQueue > c->clipQueueCap ? 7ull * k.maxClipQueue : 0))) return r;
                 if (int r = grow(c, c->bigBox, c->bigBoxCap, c->bigCap)) return r;
+                if (int r = grow(c, c->mid, c->midCap, (uint64_t)k.maxMid + (k.maxClipQueue > c->clipQueueCap ? 7ull * k.maxClipQueue : 0))) return r;
                 if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(k.maxClipRecs, 7ull * std::min<uint64_t>(k.maxClipQueue, c->clipQueueCap)))) return r;
                 if (int r = grow(c, c->clipQueue, c->clipQueueCap, k.maxClipQueue)) return r;
                 c->stats.regrow_count++;
@@ -308,6 +372,7 @@ int finish_frame(edx_context* c)
         // a clip-queue overflow hides fan triangles, so size the dependent queues generously too
         if (int r = grow(c, c->big, c->bigCap, (uint64_t)k.nBig + (k.nClipQueue > c->clipQueueCap ? 7ull * k.nClipQueue : 0))) return r;
         if (int r = grow(c, c->bigBox, c->bigBoxCap, c->bigCap)) return r;
+        if (int r = grow(c, c->mid, c->midCap, (uint64_t)k.nMid + (k.nClipQueue > c->clipQueueCap ? 7ull * k.nClipQueue : 0))) return r;
         if (int r = grow(c, c->clipQueue, c->clipQueueCap, k.nClipQueue)) return r;
         if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(k.nClipRecs, 7ull * std::min<uint64_t>(k.nClipQueue, c->clipQueueCap)))) return r;
         c->stats.regrow_count++;
@@ -330,6 +395,7 @@ int upload_mesh(edx_context* c, edx_mesh* m, const void* vertices, uint32_t nv, 
     if (nv) {
         EDX_CUDA(c, cudaMemcpyAsync(m->staging, vertices, vb, cudaMemcpyHostToDevice, c->stream));
         split_vertices_kernel<<<(nv + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(m->staging), m->pos4, m->nrm4, nv);
+        vertex_cluster_bounds_kernel<<<(nv + 255) / 256, 256, 0, c->stream>>>(m->pos4, nv, m->vclusterBox);
     }
     if (nt) {
         EDX_CUDA(c, cudaMemcpyAsync(m->staging, indices, ib, cudaMemcpyHostToDevice, c->stream));
@@ -387,6 +453,7 @@ void edx_destroy(edx_context* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     release_frame_buffers(c);
     dev_free(c->big); dev_free(c->bigBox); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->clipSlot); dev_free(c->counters);
+    dev_free(c->workList); dev_free(c->vcFlag); dev_free(c->vrec); dev_free(c->mid);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& e : c->evTimer) if (e) cudaEventDestroy(e);
     for (auto& e : c->evStage) if (e) cudaEventDestroy(e);
@@ -484,8 +551,10 @@ int edx_set_option(edx_context* c, const char* name, int value)
 {
     if (!c || !name) return EDX_ERR_INVALID;
     if (!strcmp(name, "small_max")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max in [0,64]"); c->smallMax = value; return EDX_OK; }
+    if (!strcmp(name, "mid_max")) { if (value < 0 || value > 1024) return fail(c, EDX_ERR_INVALID, "mid_max in [0,1024]"); c->midMax = value; return EDX_OK; }
     if (!strcmp(name, "small_max_clip")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max_clip in [0,64]"); c->smallMaxClip = value; return EDX_OK; }
     if (!strcmp(name, "cluster_cull")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "cluster_cull: 0 off, 1 auto, 2 always"); c->clusterCull = value; return EDX_OK; }
+    if (!strcmp(name, "front_end")) { if (value < -1 || value > 2) return fail(c, EDX_ERR_INVALID, "front_end: -1 auto, 0 per-cluster CTAs, 1 cull + work list, 2 cull + per-vertex stage + work list"); c->frontEnd = value; return EDX_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }
@@ -509,6 +578,7 @@ int edx_mesh_create(edx_context* c, const void* vertices, uint32_t nv, const uin
     if (e == cudaSuccess) e = cudaMalloc(&m->i1, (size_t)m->capTris * 4);
     if (e == cudaSuccess) e = cudaMalloc(&m->i2, (size_t)m->capTris * 4);
     if (e == cudaSuccess) e = cudaMalloc(&m->clusterBox, (size_t)((m->capTris + 255) / 256) * 32);
+    if (e == cudaSuccess) e = cudaMalloc(&m->vclusterBox, (size_t)((m->capVerts + 255) / 256) * 32);
     if (e != cudaSuccess) { edx_mesh_destroy(c, m); return fail(c, EDX_ERR_OOM, cudaGetErrorString(e)); }
     if (int r = upload_mesh(c, m, vertices, nv, indices, nt)) { edx_mesh_destroy(c, m); return r; }
     if (tex_ids && nt) {                 // Mesh::GetTextureIds (Mesh.h:58): kept until edx_mesh_set_textures passes its own
@@ -646,7 +716,7 @@ int edx_mesh_destroy(edx_context* c, edx_mesh* m)
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
     if (c && c->lastMesh == m) { c->lastMesh = nullptr; c->framePending = false; }
-    dev_free(m->pos4); dev_free(m->nrm4); dev_free(m->i0); dev_free(m->i1); dev_free(m->i2); dev_free(m->clusterBox);
+    dev_free(m->pos4); dev_free(m->nrm4); dev_free(m->i0); dev_free(m->i1); dev_free(m->i2); dev_free(m->clusterBox); dev_free(m->vclusterBox);
     dev_free(m->texDesc); dev_free(m->texels); dev_free(m->texIds);
     if (m->staging) cudaFree(m->staging);
     delete m;

@@ -57,6 +57,7 @@ typedef struct edx_stats {
     uint64_t clip_records;     /* fan triangles emitted by the clipper */
     uint32_t regrow_count;     /* times an internal queue was grown and the frame re-run */
     uint32_t tile_pairs;       /* (triangle, 64x64 bin) pairs that survived the bin-level culls: load of the tile path */
+    uint64_t mid_tris;         /* post-setup triangles rasterised one warp per triangle (the mid-size path) */
     float    stage_ms[8];      /* valid with profiling on: geom, clip, tile, total; rest 0 */
 } edx_stats;
 

@@ -39,10 +39,37 @@ def test_reduced_configs_bit_exact(name):
 @pytest.mark.parametrize("options,hier", [({"hiz": 0}, True), ({}, False), ({"small_max": 0}, True),
                                           ({"small_max": 2}, True), ({"small_max": 40}, True),
                                           ({"cluster_cull": 2, "pdl": 0}, True), ({"cluster_cull": 0, "small_max_clip": 0}, True),
-                                          ({"lean_resolve": 0, "clip_carveout": 2}, True), ({"lean_resolve": 2, "clip_carveout": 1}, True)])
+                                          ({"lean_resolve": 0, "clip_carveout": 2}, True), ({"lean_resolve": 2, "clip_carveout": 1}, True),
+                                          ({"mid_max": 0}, True), ({"mid_max": 0, "small_max": 32}, True), ({"mid_max": 16}, True),
+                                          ({"mid_max": 512, "small_max": 0, "small_max_clip": 0}, True), ({"mid_max": 200, "small_max": 3}, False)])
 def test_tuning_knobs_never_change_the_image(name, options, hier):
     # routing (direct vs tile path), hierarchical Z and the 8x8 block tests are pure optimisations
     assert_parity(REDUCED[name](), options=options, hierarchical=hier, stages=False)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4", "C4_yaw", "odd_bins"])
+@pytest.mark.parametrize("front_end,cull", [(1, 2), (2, 2), (2, 0), (1, 0)])
+def test_list_front_end_is_bit_identical(name, front_end, cull):
+    # front_end 1: device-side cluster cull into a work list + persistent geometry kernel; 2: plus the per-vertex
+    # stage (Renderer::VertexProcessing, Renderer.cpp:120-127) whose records the geometry kernel and the resolve gather.
+    # Large meshes select them automatically; forced here on the reduced configs, with and without cluster culling.
+    assert_parity(REDUCED[name](), options={"front_end": front_end, "cluster_cull": cull})
+
+
+@pytest.mark.parametrize("front_end", [1, 2])
+def test_list_front_end_with_msaa_textures_and_frames_in_sequence(front_end):
+    from edxraster_b200 import renderer as R
+    r = R.Renderer(0)
+    opts = {"front_end": front_end, "cluster_cull": 2}
+    sc = scenes.config4(width=640, height=360, quads_x=200, quads_z=160)
+    for msaa in (0, 2, 0):
+        ref = parity.render_oracle(sc, msaa=msaa)
+        got = parity.render_gpu(sc, msaa=msaa, stages=False, renderer=r, options=opts)
+        rep = parity.compare(ref, got)
+        assert parity.is_parity(rep), (msaa, rep)
+    r.close()
+    assert_parity(scenes.textured_plane(tex_filter=3), options=opts)
+    assert_parity(scenes.textured_sphere(tex_filter=2), options=opts, stages=False)
 
 
 @pytest.mark.parametrize("shader", [0, 1, 2, 3])
@@ -95,8 +122,44 @@ def test_full_size_c3():
 
 
 def test_full_size_c4():
-    _, got, _ = assert_parity(scenes.config4(), stages=False)
-    assert got["stats"]["clipped_tris"] > 1000
+    sc = scenes.config4()
+    ref = parity.render_oracle(sc)
+    for fe in (-1, 0, 1):                                  # auto (= 2 for this mesh), per-cluster CTAs, work list only
+        got = parity.render_gpu(sc, stages=False, options={"front_end": fe})
+        rep = parity.compare(ref, got)
+        assert parity.is_parity(rep), (fe, rep)
+        assert got["stats"]["clipped_tris"] > 1000
+
+
+def test_full_size_c5_views():
+    # BASELINE.json configs[4]: views of the 10M-triangle mesh at full size, through a FrameRing as the farm renders them
+    import copy
+    from edxraster_b200 import renderer as R
+    base = scenes.config4()
+    views = scenes.config5_views(base, 256)
+    pick = [5, 67, 130, 201, 255]
+    ring = R.FrameRing(0, depth=3)
+    ring.Initialize(base.width, base.height)
+    ring.SetPixelShader(base.shader)
+    mesh = ring.CreateMesh(base.vertices, base.indices)
+    for lane in ring.lanes:
+        lane.SetCaptureIds(True)
+    tickets = [ring.Submit(mesh, *views[v]) for v in pick[:3]]
+    got = {}
+    for n, v in enumerate(pick):
+        t = tickets[n]
+        lane = ring.lanes[t % 3]
+        got[v] = {"color": ring.GetBackBuffer(t).copy(), "depth": ring.GetDepthBuffer(t), "winner": lane.GetWinnerIds(), "derived": lane.DerivedState()}
+        if n + 3 < len(pick):
+            tickets.append(ring.Submit(mesh, *views[pick[n + 3]]))
+    for v in pick:
+        sc = copy.copy(base)
+        sc.mv, sc.proj, sc.raster = views[v]
+        rep = parity.compare(parity.render_oracle(sc), got[v])
+        assert parity.is_parity(rep), (v, rep)
+    assert len({g["depth"].tobytes() for g in got.values()}) == len(pick)
+    mesh.Release()
+    ring.close()
 
 
 def test_edge_cases():
@@ -172,8 +235,24 @@ def test_queue_regrow_path():
     flip = (a[:, 0] * b[:, 1] - b[:, 0] * a[:, 1]) < 0
     p[flip, 0], p[flip, 1] = p[flip, 1].copy(), p[flip, 0].copy()
     sc = raster_scene(p, 0.1 + 0.8 * rng.random((n, 3)), 1280, 720)
-    _, got, _ = assert_parity(sc, stages=False)
+    _, got, _ = assert_parity(sc, stages=False, options={"mid_max": 0, "small_max": 32})
     assert got["stats"]["binned_tris"] > 83000 and got["stats"]["regrow_count"] >= 1
+    # the same soup with the default routing: most of it is mid-size and overflows the warp-per-triangle queue instead
+    _, got, _ = assert_parity(sc, stages=False)
+    assert got["stats"]["mid_tris"] > 70000 and got["stats"]["regrow_count"] >= 1
+
+
+def test_clip_record_overflow_is_repaired():
+    # more fan triangles than the initial record capacity (65,536): the clipper must not leave keys that point at
+    # records it could not write (the resolve would read past the array); the frame is re-run with larger queues
+    rng = np.random.default_rng(9)
+    n = 260000
+    sc = scenes.config3(width=320, height=200, num_tris=n)
+    v = sc.vertices.copy()
+    v[:, 0:3] = (rng.random((n * 3, 3)) - 0.5) * np.array([6.0, 6.0, 1.2]) + np.array([0.0, 0.0, 0.3])
+    sc["vertices"] = v
+    _, got, _ = assert_parity(sc, stages=False)
+    assert got["stats"]["clip_records"] > 65536 and got["stats"]["regrow_count"] >= 1, got["stats"]
 
 
 def test_error_behaviour():
@@ -243,11 +322,11 @@ def test_tile_path_stress_many_candidates_per_bin(seed):
     p[flip, 0], p[flip, 1] = p[flip, 1].copy(), p[flip, 0].copy()
     sc = raster_scene(p, 0.05 + 0.9 * rng.random((n, 3)), 512, 384)
     ref = parity.render_oracle(sc)
-    for opts in ({}, {"hiz": 0}, {"small_max": 4}):
+    for opts in ({"mid_max": 0}, {"mid_max": 0, "hiz": 0}, {"mid_max": 0, "small_max": 4}, {}):
         got = parity.render_gpu(sc, options=opts, stages=False)
         rep = parity.compare(ref, got)
         assert parity.is_parity(rep), (opts, rep)
-        assert got["stats"]["binned_tris"] > 20000
+        assert got["stats"]["binned_tris"] > (20000 if "mid_max" in opts else 8000)
 
 
 def _fuzz_scene(seed):
@@ -270,7 +349,9 @@ def _fuzz_scene(seed):
     sc = scenes.Scene(name="fuzz%d" % seed, width=w, height=h, vertices=v,
                       indices=np.arange(n * 3, dtype=np.uint32).reshape(-1, 3), mv=c.view, proj=c.proj, raster=c.raster,
                       shader=int(rng.choice([0, 1, 2, 3])))
-    msaa = int(rng.choice([0, 0, 1, 2, 3]))
+    msaa = int(rng.choice([0, 0, 1, 2, 3, 4, 5]))
+    sc["front_end"] = int(rng.choice([0, 1, 2]))
+    sc["mid_max"] = int(rng.choice([0, 24, 64, 64, 300]))
     if sc.shader == 3 and rng.random() < 0.8:            # textured: random slots, sizes, filter, texcoord range
         v[:, 6:8] = (v[:, 6:8] - 0.5) * float(rng.choice([1.0, 4.0, 40.0]))
         tex = []
@@ -284,11 +365,11 @@ def _fuzz_scene(seed):
     return sc, msaa
 
 
-@pytest.mark.parametrize("seed", list(range(100, 116)))
+@pytest.mark.parametrize("seed", list(range(100, 124)))
 def test_fuzz_random_scenes(seed):
     sc, msaa = _fuzz_scene(seed)
     ref = parity.render_oracle(sc, msaa=msaa)
-    got = parity.render_gpu(sc, msaa=msaa, stages=(msaa == 0))
+    got = parity.render_gpu(sc, msaa=msaa, stages=(msaa == 0), options={"front_end": sc["front_end"], "cluster_cull": 2 * (seed & 1), "mid_max": sc["mid_max"]})
     rep = parity.compare(ref, got)
     assert parity.is_parity(rep), (seed, msaa, rep)
 
@@ -350,6 +431,7 @@ def test_overflow_in_an_unsynchronised_earlier_frame_is_reported():
     small = raster_scene(p[:50], 0.1 + 0.8 * rng.random((50, 3)), 1280, 720)
     r = R.Renderer(0)
     r.Initialize(1280, 720)
+    r.SetOption("mid_max", 0)                           # everything above the direct path's box goes to the tile-path queue
     r.SetPixelShader(big.shader)
     r.SetTransform(big.mv, big.proj, big.raster)
     mb, msm = r.CreateMesh(big.vertices, big.indices), r.CreateMesh(small.vertices, small.indices)
