@@ -648,6 +648,7 @@ def ours_arm(args):
     ms_total, t0, t1 = farm.timed_run(K, args.steps, n_warm)
     sampler.stop()
     launches_per_step = r.LastLaunchCount()
+    launch_list = r.LastLaunchList()
     ms_step = ms_total / args.steps
     value = world * nt / ms_step / 1e3        # Mtris/s, whole job
     ms_one = None
@@ -774,7 +775,7 @@ def ours_arm(args):
                 "resident_mesh_value": world * nt / e2e["resident"] / 1e3, "resident_mesh_ms_per_step": e2e["resident"],
                 "resident_mesh_what": "mesh uploaded once (the reference viewer's usage, Main.cpp:42,71-75); per step: transform in, render, frame read back to host"},
         "gpu_launches": launches_per_step * args.steps,
-        "kernels_per_step": {"geom_kernel": 1, "clip_kernel": 1, "tile_kernel": 1, "frame_end_kernel": 1},
+        "kernels_per_step": {k: launch_list.count(k) for k in dict.fromkeys(launch_list)},
         "roofline": {"bound": "hbm", "kernel": dom + "_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": ab, "kernel_ms": dom_ms,

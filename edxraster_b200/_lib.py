@@ -18,7 +18,7 @@ SYMBOLS = [
     "edx_mesh_destroy", "edx_render_mesh", "edx_get_back_buffer", "edx_synchronize", "edx_read_depth",
     "edx_set_capture_ids", "edx_read_winner_ids", "edx_read_sample", "edx_debug_clip_vertices", "edx_debug_raster_triangles",
     "edx_get_derived_state", "edx_device_color", "edx_device_depth", "edx_set_render_target", "edx_set_frame_sink", "edx_set_screen_partition", "edx_set_stream", "edx_timer_begin",
-    "edx_timer_end", "edx_set_profiling", "edx_get_stats", "edx_set_option", "edx_last_launch_count",
+    "edx_timer_end", "edx_set_profiling", "edx_get_stats", "edx_set_option", "edx_last_launch_count", "edx_last_launch_list",
     "edx_mesh_set_textures", "edx_mesh_read_texture_level", "edx_debug_tile_residency",
 ]
 
@@ -101,6 +101,8 @@ def load():
     lib.edx_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.edx_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     lib.edx_last_launch_count.argtypes = [vp]
+    lib.edx_last_launch_list.argtypes = [vp]
+    lib.edx_last_launch_list.restype = C.c_char_p
     lib.edx_mesh_set_textures.argtypes = [vp, vp, C.POINTER(TextureDesc), C.c_uint32, vp]
     lib.edx_debug_tile_residency.argtypes = [vp, C.POINTER(C.c_int)]
     lib.edx_mesh_read_texture_level.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, u32p, u32p]

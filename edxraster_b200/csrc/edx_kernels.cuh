@@ -1114,11 +1114,22 @@ __device__ __noinline__ float3 albedo_textured(const FrameParams& P, const TexQu
     return c;
 }
 
-// Stages a15-a17 for one pixel: re-derive the owning triangle from its prim id (visibility-buffer
-// style: nothing per-triangle was stored for small triangles), interpolate perspective-correctly
-// (Shader.h:142-170), shade (Shader.h:185-282) and pack (Renderer.cpp:295-301).
+// What interpolation and shading need of the (fan) triangle that owns a pixel: the coefficients of edges 1 and 2,
+// vertex 2, 1/det, the three 1/w, and the attributes of its three vertices.
+struct OwnerSetup {
+    uint32_t B1, C1, B2, C2;
+    int v2x, v2y;
+    float invDet, iw0, iw1, iw2;
+    float A[3][6];                     // position.xyz, normal.xyz of the three (fan) vertices
+    float TU[3], TV[3];                // their texture coordinates (only the textured shader reads them)
+    uint32_t ok;                       // 0: the owner's record is missing (overflowed frame, re-run by the host)
+};
+
+// Re-derive the owning triangle from its prim id (visibility-buffer style: nothing per-triangle was stored for
+// triangles that did not go through the clipper): indices -> vertices -> clip / per-vertex records -> setup, or the
+// ClipRec of a fan triangle with the attribute re-weighting of Clipper.h:139-147.
 template <bool TEX>
-__device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim, int px, int py)
+__device__ __forceinline__ void derive_owner(const FrameParams& P, uint32_t prim, OwnerSetup& o)
 {
     const uint32_t t = prim >> 3, fan = prim & 7u;
     const uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
@@ -1127,13 +1138,12 @@ __device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim
 
     int v1x, v1y, v2x, v2y, v0y, v0x;
     float invDet, iw0, iw1, iw2;
-    float A[3][6];                     // position.xyz, normal.xyz of the three (fan) vertices
-    float TU[3], TV[3];                // their texture coordinates (only the textured shader reads them)
     const bool textured = TEX;
     bool unclipped;
+    o.ok = 1u;
     if (P.vrec) {
         // front end 2: the owner's vertices were set up once per vertex this frame; gather the records instead of
-        // transforming, projecting, snapping and inverting w again for every pixel
+        // transforming, projecting, snapping and inverting w again
         const int4 r0 = load_vrec(P, i0), r1 = load_vrec(P, i1), r2 = load_vrec(P, i2);
         unclipped = (vrec_code(r0.w) | vrec_code(r1.w) | vrec_code(r2.w)) == 0u;
         if (unclipped) {
@@ -1154,13 +1164,18 @@ __device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim
         }
     }
     if (unclipped) {
-        A[0][0] = p0.x; A[0][1] = p0.y; A[0][2] = p0.z; A[0][3] = n0.x; A[0][4] = n0.y; A[0][5] = n0.z;
-        A[1][0] = p1.x; A[1][1] = p1.y; A[1][2] = p1.z; A[1][3] = n1.x; A[1][4] = n1.y; A[1][5] = n1.z;
-        A[2][0] = p2.x; A[2][1] = p2.y; A[2][2] = p2.z; A[2][3] = n2.x; A[2][4] = n2.y; A[2][5] = n2.z;
-        TU[0] = n0.w; TU[1] = n1.w; TU[2] = n2.w; TV[0] = p0.w; TV[1] = p1.w; TV[2] = p2.w;
+        o.A[0][0] = p0.x; o.A[0][1] = p0.y; o.A[0][2] = p0.z; o.A[0][3] = n0.x; o.A[0][4] = n0.y; o.A[0][5] = n0.z;
+        o.A[1][0] = p1.x; o.A[1][1] = p1.y; o.A[1][2] = p1.z; o.A[1][3] = n1.x; o.A[1][4] = n1.y; o.A[1][5] = n1.z;
+        o.A[2][0] = p2.x; o.A[2][1] = p2.y; o.A[2][2] = p2.z; o.A[2][3] = n2.x; o.A[2][4] = n2.y; o.A[2][5] = n2.z;
+        o.TU[0] = n0.w; o.TU[1] = n1.w; o.TU[2] = n2.w; o.TV[0] = p0.w; o.TV[1] = p1.w; o.TV[2] = p2.w;
     } else {
         const uint32_t recAt = __ldg(P.clipSlot + t) + fan;
-        if (recAt >= P.clipRecCap) return make_uchar4(0, 0, 0, 255);       // overflowed frame (re-run by finish_frame): never read past the records
+        if (recAt >= P.clipRecCap) {               // overflowed frame (re-run by finish_frame): never read past the records
+            o.ok = 0u; o.B1 = o.C1 = o.B2 = o.C2 = 0u; o.v2x = o.v2y = 0; o.invDet = o.iw0 = o.iw1 = o.iw2 = 0.0f;
+            #pragma unroll
+            for (int k = 0; k < 3; k++) { o.TU[k] = o.TV[k] = 0.0f; for (int m = 0; m < 6; m++) o.A[k][m] = 0.0f; }
+            return;
+        }
         const ClipRec* rp = P.clipRecs + recAt;
         const int4 w0 = __ldg(reinterpret_cast<const int4*>(rp));
         const int4 w1 = __ldg(reinterpret_cast<const int4*>(rp) + 1);
@@ -1181,32 +1196,42 @@ __device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim
             for (int m = 0; m < 6; m++) {
                 // Clipper.h:141-146: weight.x*a + weight.y*b + weight.z*c for new vertices
                 float blended = blend3(wt[k][0], wt[k][1], wt[k][2], O[0][m], O[1][m], O[2][m]);
-                A[k][m] = sk == 0 ? O[0][m] : (sk == 1 ? O[1][m] : (sk == 2 ? O[2][m] : blended));
+                o.A[k][m] = sk == 0 ? O[0][m] : (sk == 1 ? O[1][m] : (sk == 2 ? O[2][m] : blended));
             }
             if (textured) {
                 const float bu = blend3(wt[k][0], wt[k][1], wt[k][2], n0.w, n1.w, n2.w), bv = blend3(wt[k][0], wt[k][1], wt[k][2], p0.w, p1.w, p2.w);
-                TU[k] = sk == 0 ? n0.w : (sk == 1 ? n1.w : (sk == 2 ? n2.w : bu));
-                TV[k] = sk == 0 ? p0.w : (sk == 1 ? p1.w : (sk == 2 ? p2.w : bv));
+                o.TU[k] = sk == 0 ? n0.w : (sk == 1 ? n1.w : (sk == 2 ? n2.w : bu));
+                o.TV[k] = sk == 0 ? p0.w : (sk == 1 ? p1.w : (sk == 2 ? p2.w : bv));
             }
         }
     }
-    const uint32_t B1 = (uint32_t)v1y - (uint32_t)v2y, C1 = (uint32_t)v2x - (uint32_t)v1x;
-    const uint32_t B2 = (uint32_t)v2y - (uint32_t)v0y, C2 = (uint32_t)v0x - (uint32_t)v2x;
-    const uint32_t dx = (uint32_t)((px << 4) + 8 - v2x), dy = (uint32_t)((py << 4) + 8 - v2y);
+    if (!textured) { o.TU[0] = o.TU[1] = o.TU[2] = o.TV[0] = o.TV[1] = o.TV[2] = 0.0f; }
+    o.B1 = (uint32_t)v1y - (uint32_t)v2y; o.C1 = (uint32_t)v2x - (uint32_t)v1x;
+    o.B2 = (uint32_t)v2y - (uint32_t)v0y; o.C2 = (uint32_t)v0x - (uint32_t)v2x;
+    o.v2x = v2x; o.v2y = v2y; o.invDet = invDet; o.iw0 = iw0; o.iw1 = iw1; o.iw2 = iw2;
+}
+
+// Stages a15-a17 for one pixel of a known owner: perspective-correct interpolation (Shader.h:142-170), shading
+// (Shader.h:185-282) and packing (Renderer.cpp:295-301).
+template <bool TEX>
+__device__ __forceinline__ uchar4 shade_owned(const FrameParams& P, const OwnerSetup& o, uint32_t prim, int px, int py)
+{
+    if (!o.ok) return make_uchar4(0, 0, 0, 255);
+    const uint32_t dx = (uint32_t)((px << 4) + 8 - o.v2x), dy = (uint32_t)((py << 4) + 8 - o.v2y);
     float b0, b1;
-    barycentric((int)(B1 * dx + C1 * dy), (int)(B2 * dx + C2 * dy), invDet, b0, b1);
+    barycentric((int)(o.B1 * dx + o.C1 * dy), (int)(o.B2 * dx + o.C2 * dy), o.invDet, b0, b1);
     // Fragment::Interpolate, Shader.h:151-159
     float b2 = fsub(fsub(1.0f, b0), b1);
-    b0 = fmul(b0, iw0); b1 = fmul(b1, iw1); b2 = fmul(b2, iw2);
+    b0 = fmul(b0, o.iw0); b1 = fmul(b1, o.iw1); b2 = fmul(b2, o.iw2);
     const float invB = frcp(fadd(fadd(b0, b1), b2));
     b0 = fmul(b0, invB); b1 = fmul(b1, invB);
     b2 = fsub(fsub(1.0f, b0), b1);
-    const float posx = blend3(b0, b1, b2, A[0][0], A[1][0], A[2][0]);
-    const float posy = blend3(b0, b1, b2, A[0][1], A[1][1], A[2][1]);
-    const float posz = blend3(b0, b1, b2, A[0][2], A[1][2], A[2][2]);
-    float nx = blend3(b0, b1, b2, A[0][3], A[1][3], A[2][3]);
-    float ny = blend3(b0, b1, b2, A[0][4], A[1][4], A[2][4]);
-    float nz = blend3(b0, b1, b2, A[0][5], A[1][5], A[2][5]);
+    const float posx = blend3(b0, b1, b2, o.A[0][0], o.A[1][0], o.A[2][0]);
+    const float posy = blend3(b0, b1, b2, o.A[0][1], o.A[1][1], o.A[2][1]);
+    const float posz = blend3(b0, b1, b2, o.A[0][2], o.A[1][2], o.A[2][2]);
+    float nx = blend3(b0, b1, b2, o.A[0][3], o.A[1][3], o.A[2][3]);
+    float ny = blend3(b0, b1, b2, o.A[0][4], o.A[1][4], o.A[2][4]);
+    float nz = blend3(b0, b1, b2, o.A[0][5], o.A[1][5], o.A[2][5]);
     // Shader.h:256-264
     float w = rsqrt_exact(dot3(nx, ny, nz, nx, ny, nz));
     nx = fmul(nx, w); ny = fmul(ny, w); nz = fmul(nz, w);
@@ -1226,9 +1251,9 @@ __device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim
         cr = cg = cb = fadd(diffuse, spec);
     } else if (P.shader == SH_LAMBERT_ALBEDO) {
         float ar = P.albedo[0], ag = P.albedo[1], ab = P.albedo[2];
-        if (textured) {
-            const TexQuad q = { B1, C1, B2, C2, v2x, v2y, invDet, iw0, iw1, iw2, { TU[0], TU[1], TU[2] }, { TV[0], TV[1], TV[2] } };
-            const float3 c = albedo_textured(P, q, t, px, py, b0, b1, b2);
+        if (TEX) {
+            const TexQuad q = { o.B1, o.C1, o.B2, o.C2, o.v2x, o.v2y, o.invDet, o.iw0, o.iw1, o.iw2, { o.TU[0], o.TU[1], o.TU[2] }, { o.TV[0], o.TV[1], o.TV[2] } };
+            const float3 c = albedo_textured(P, q, prim >> 3, px, py, b0, b1, b2);
             ar = c.x; ag = c.y; ab = c.z;
         }
         cr = fmul(diffuse, ar); cg = fmul(diffuse, ag); cb = fmul(diffuse, ab);
@@ -1236,10 +1261,13 @@ __device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim
     return make_uchar4(to_u8(cr), to_u8(cg), to_u8(cb), 255);
 }
 
-// tile_kernel only ever shades untextured (inlined, as before): compiled next to the rasteriser, the textured
-// variant - even as a call - raised that kernel's register pressure and made C3 twice as slow. Textured frames
-// get their colour from textured_resolve_kernel (or msaa_resolve_kernel) instead.
-__device__ __forceinline__ uchar4 shade_pixel(const FrameParams& P, uint32_t prim, int px, int py) { return shade_impl<false>(P, prim, px, py); }
+template <bool TEX>
+__device__ __forceinline__ uchar4 shade_impl(const FrameParams& P, uint32_t prim, int px, int py)
+{
+    OwnerSetup o;
+    derive_owner<TEX>(P, prim, o);
+    return shade_owned<TEX>(P, o, prim, px, py);
+}
 
 __device__ __noinline__ uchar4 shade_pixel_textured(const FrameParams& P, uint32_t prim, int px, int py) { return shade_impl<true>(P, prim, px, py); }
 
@@ -1250,22 +1278,110 @@ __device__ __forceinline__ uchar4 shade_pixel_any(const FrameParams& P, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// tile_kernel: stages a7-a11 for large triangles + a13 resolve + a15-a17 for every pixel
+// shade_kernel: stages a15-a17 of a single-sample frame as a pass of its own over the visibility buffer. tile_kernel
+// has written depth and the owning prim id of every pixel. The reference shades every Z-passing fragment and lets
+// the last one win (Renderer.cpp:272-350); only the owner is shaded here.
+//
+// One CTA per 16 x 16 tile, one thread per pixel. Deriving an owner (indices, six vertex attributes, per-vertex or
+// clip records, setup) costs more than shading a pixel with it, and a tile usually has far fewer owners than pixels.
+// So the CTA first builds the set of distinct owners of its tile in a 64-slot table in shared memory (one lane per
+// group of equal ids in a warp inserts it), then thread s derives the owner in slot s - up to 64 DIFFERENT owners in
+// one pass of the code - and parks the result in shared memory, and every pixel shades from its owner's slot. A tile
+// whose pixels mostly have owners of their own (sub-pixel triangles) skips the table and derives per pixel.
 // ---------------------------------------------------------------------------------------------
-// Colour pass of a textured single-sample frame (LambertianAlbedoPixelShader with image textures, Shader.h:209-244):
-// tile_kernel has written depth and the owning prim id of every pixel and left colour alone; one thread per pixel
-// shades its owner here. 8x8-pixel blocks per 64 threads so that a warp's texture footprints stay close.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) textured_resolve_kernel(const __grid_constant__ FrameParams P)
+constexpr int SHADE_SLOTS = 64;
+
+template <bool TEX>
+__device__ __forceinline__ void owner_to_smem(const OwnerSetup& o, uint32_t* d)
 {
+    d[0] = o.B1; d[1] = o.C1; d[2] = o.B2; d[3] = o.C2; d[4] = (uint32_t)o.v2x; d[5] = (uint32_t)o.v2y;
+    d[6] = __float_as_uint(o.invDet); d[7] = __float_as_uint(o.iw0); d[8] = __float_as_uint(o.iw1); d[9] = __float_as_uint(o.iw2); d[10] = o.ok;
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        #pragma unroll
+        for (int m = 0; m < 6; m++) d[11 + 6 * k + m] = __float_as_uint(o.A[k][m]);
+        if (TEX) { d[29 + k] = __float_as_uint(o.TU[k]); d[32 + k] = __float_as_uint(o.TV[k]); }
+    }
+}
+
+template <bool TEX>
+__device__ __forceinline__ void owner_from_smem(OwnerSetup& o, const uint32_t* d)
+{
+    o.B1 = d[0]; o.C1 = d[1]; o.B2 = d[2]; o.C2 = d[3]; o.v2x = (int)d[4]; o.v2y = (int)d[5];
+    o.invDet = __uint_as_float(d[6]); o.iw0 = __uint_as_float(d[7]); o.iw1 = __uint_as_float(d[8]); o.iw2 = __uint_as_float(d[9]); o.ok = d[10];
+    #pragma unroll
+    for (int k = 0; k < 3; k++) {
+        #pragma unroll
+        for (int m = 0; m < 6; m++) o.A[k][m] = __uint_as_float(d[11 + 6 * k + m]);
+        if (TEX) { o.TU[k] = __uint_as_float(d[29 + k]); o.TV[k] = __uint_as_float(d[32 + k]); }
+        else { o.TU[k] = 0.0f; o.TV[k] = 0.0f; }
+    }
+}
+
+template <bool TEX>
+__global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ FrameParams P)
+{
+    constexpr int OWN_WORDS = TEX ? 37 : 31;                       // odd strides: distinct slots fall into distinct banks
+    __shared__ uint32_t sTab[SHADE_SLOTS];
+    __shared__ uint32_t sOwn[SHADE_SLOTS * OWN_WORDS];
+    __shared__ uint32_t sLeaders;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t tilesX = (uint32_t)(P.width + TILE_PX - 1) >> TILE_LOG2;
+    const int tx0 = (int)(blockIdx.x % tilesX) << TILE_LOG2, ty0 = (int)(blockIdx.x / tilesX) << TILE_LOG2;
+    const int px = tx0 + (int)(tid & 15u), py = ty0 + (int)(tid >> 4);      // a warp = two rows of the tile
+    if (tid < SHADE_SLOTS) sTab[tid] = 0xFFFFFFFFu;
+    if (tid == 0) sLeaders = 0;
     cudaGridDependencySynchronize();
-    const uint32_t blocksX = (uint32_t)(P.width + 7) >> 3;
-    const uint32_t blk = blockIdx.x * 4u + (threadIdx.x >> 6), in = threadIdx.x & 63u;
-    const int px = (int)((blk % blocksX) * 8u + (in & 7u)), py = (int)((blk / blocksX) * 8u + (in >> 3));
-    if (px >= P.width || py >= P.height || !owns_pixel(px, py, P.binsX, P.part, P.parts)) return;
-    const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);
-    const uint32_t prim = P.ids[at];
-    P.color[at] = prim != 0xFFFFFFFFu ? shade_pixel_textured(P, prim, px, py) : make_uchar4(0, 0, 0, 0);
+    if (!owns_pixel(tx0, ty0, P.binsX, P.part, P.parts)) return;           // (the whole CTA: a tile lies inside one bin)
+    const bool inside = px < P.width && py < P.height;
+    const size_t at = inside ? (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py) : 0;
+    const uint32_t prim = inside ? __ldg(P.ids + at) : 0xFFFFFFFFu;
+    const bool hit = prim != 0xFFFFFFFFu;
+    const uint32_t group = __match_any_sync(0xFFFFFFFFu, prim);
+    const int leader = __ffs(group) - 1;
+    const bool isLeader = hit && (int)lane == leader;
+    const uint32_t leaders = __ballot_sync(0xFFFFFFFFu, isLeader);
+    __syncthreads();
+    if (lane == 0 && leaders) atomicAdd(&sLeaders, (uint32_t)__popc(leaders));
+    __syncthreads();
+    const uint32_t nLeaders = sLeaders;
+    if (nLeaders == 0) {                                           // nothing drawn in this tile: cleared colour (FrameBuffer.cpp:91-95)
+        if (inside) P.color[at] = make_uchar4(0, 0, 0, 0);
+        return;
+    }
+    uint32_t sl = 0xFFu;
+    if (nLeaders <= 96u) {                                         // (at most 96 groups of equal ids in the 8 warps: the table pays)
+        if (isLeader) {
+            uint32_t h = (prim * 2654435761u) >> 26;
+            #pragma unroll 1
+            for (int probe = 0; probe < 8; probe++) {
+                const uint32_t old = atomicCAS(sTab + h, 0xFFFFFFFFu, prim);
+                if (old == 0xFFFFFFFFu || old == prim) { sl = h; break; }
+                h = (h + 1u) & (SHADE_SLOTS - 1);
+            }
+        }
+        sl = __shfl_sync(0xFFFFFFFFu, sl, leader);
+        if (!hit) sl = 0xFFu;
+        __syncthreads();
+        if (tid < SHADE_SLOTS) {
+            const uint32_t p = sTab[tid];
+            if (p != 0xFFFFFFFFu) {
+                OwnerSetup o;
+                derive_owner<TEX>(P, p, o);
+                owner_to_smem<TEX>(o, sOwn + tid * OWN_WORDS);
+            }
+        }
+        __syncthreads();
+    }
+    if (!inside) return;
+    uchar4 c = make_uchar4(0, 0, 0, 0);
+    if (hit) {
+        OwnerSetup o;
+        if (sl != 0xFFu) owner_from_smem<TEX>(o, sOwn + sl * OWN_WORDS);
+        else derive_owner<TEX>(P, prim, o);
+        c = shade_owned<TEX>(P, o, prim, px, py);
+    }
+    P.color[at] = c;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1276,7 +1392,35 @@ struct TileShared {
     uint32_t survCount, candCount;
     uint32_t binU;                             // order_f32 of the bin's depth upper bound
     uint32_t keyMax;                           // scratch: max ordered depth currently stored in the bin
+    unsigned long long keysReady;              // mbarrier: the bulk copy of the bin's keys has landed
 };
+
+// --- bulk asynchronous copy (TMA engine, no tensor map: the bin's key block is one contiguous 32 KB run) ---
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one thread: arm the barrier with the byte count, then hand the copy to the copy engine
+__device__ __forceinline__ void bulk_load(void* dstSmem, const void* srcGlobal, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "EDX_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra EDX_DONE;\n"
+        "bra EDX_WAIT;\n"
+        "EDX_DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 // pixel of key slot j (0..7) of this lane inside the warp's tile
 __device__ __forceinline__ void slot_pixel(int tx0, int ty0, int lane, int j, int& px, int& py)
@@ -1362,15 +1506,13 @@ __device__ __forceinline__ void load_big(const BigRec* src, BigRec& r)
     d4[0] = __ldg(s4); d4[1] = __ldg(s4 + 1); d4[2] = __ldg(s4 + 2); d4[3] = __ldg(s4 + 3);
 }
 
-// Output of one pixel: depth always, ids on request, colour unless depth-only (stages a13, a15-a17)
+// Output of one pixel: depth always, owner ids on request or when the frame is shaded (stage a13)
 __device__ __forceinline__ void resolve_pixel(const FrameParams& P, unsigned long long key, int px, int py)
 {
     const size_t at = (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py);   // bottom-up, FrameBuffer.cpp:41
     const bool hit = key != KEY_EMPTY;
     P.depth[at] = hit ? key_depth(key) : 1.0f;                                      // clear value, FrameBuffer.cpp:103
-    if (P.captureIds) P.ids[at] = hit ? key_prim(key) : 0xFFFFFFFFu;
-    if (P.shader != SH_DEPTH_ONLY)
-        P.color[at] = hit ? shade_pixel(P, key_prim(key), px, py) : make_uchar4(0, 0, 0, 0);
+    if (P.captureIds) P.ids[at] = hit ? key_prim(key) : 0xFFFFFFFFu;       // colour is shade_kernel's job (it reads these ids)
 }
 
 // End of frame: a one-thread kernel behind the frame's last kernel publishes the counters to pinned host memory
@@ -1491,36 +1633,43 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     const uint32_t bx = (uint32_t)(bin % P.binsX), by = (uint32_t)(bin / P.binsX);
     const int ox = (int)bx << BIN_LOG2, oy = (int)by << BIN_LOG2;
     const int tx0 = ox + (warp & 3) * TILE_PX, ty0 = oy + (warp >> 2) * TILE_PX;
+    if (tid == 0) mbar_init(&S.keysReady, 1);                 // (before the dependency wait: touches shared memory only)
+    __syncthreads();
     cudaGridDependencySynchronize();
     if (P.parts > 1 && (uint32_t)bin % (uint32_t)P.parts != (uint32_t)P.part) {   // sort-first: not this context's bin
         return;
     }
-    unsigned long long* gkeys = P.keys + (size_t)sId * P.keyStride + (size_t)bin * KEYS_PER_BIN + warp * 256;   // this warp's tile, [block][8x8]
+    unsigned long long* gbin = P.keys + (size_t)sId * P.keyStride + (size_t)bin * KEYS_PER_BIN;     // the bin's 4096 keys: one contiguous run
+    unsigned long long* gkeys = gbin + warp * 256;                                                   // this warp's tile, [block][8x8]
     if (ms && min(P.counters->nBig, P.bigCap) == 0) return;      // nothing on the tile path: the keys are already final
     if (!MS && P.leanResolve && min(P.counters->nBig, P.bigCap) == 0) return;   // lean_resolve_kernel has resolved the frame
-    // the tile's keys are wanted on every path: issue the loads (16 bytes per lane, linear key order) before
-    // the (dependent) counter read
+    // The bin's keys are wanted on every path. One thread hands the whole 32 KB block to the copy engine
+    // (cp.async.bulk, completion counted on an mbarrier) and the copy runs under the dependent counter read.
+    if (tid == 0) bulk_load(S.keys, gbin, KEYS_PER_BIN * (uint32_t)sizeof(unsigned long long), &S.keysReady);
     ulonglong2* gk2 = reinterpret_cast<ulonglong2*>(gkeys);
-    ulonglong2 kk[4];
-    #pragma unroll
-    for (int b4 = 0; b4 < 4; b4++) kk[b4] = gk2[b4 * 32 + lane];          // keys b4*64 + 2*lane, +1
     const uint32_t nBig = min(P.counters->nBig, P.bigCap);
     const ulonglong2 empty2 = make_ulonglong2(KEY_EMPTY, KEY_EMPTY);
+    mbar_wait(&S.keysReady, 0);
+    ulonglong2* sk2 = reinterpret_cast<ulonglong2*>(S.keys + warp * 256);
 
     if (nBig == 0) {
-        // Nothing on the tile path: resolve straight from the L2-resident keys, no staging (unless
-        // lean_resolve_kernel has already done exactly that for this frame).
-        if (!P.leanResolve) resolve_tile_direct<false>(P, gk2, kk, tx0, ty0, lane);
+        // Nothing on the tile path: resolve straight from the staged keys (unless lean_resolve_kernel has already
+        // done exactly that for this frame).
+        if (!P.leanResolve) {
+            ulonglong2 kk[4];
+            #pragma unroll
+            for (int b4 = 0; b4 < 4; b4++) kk[b4] = sk2[b4 * 32 + lane];          // keys b4*64 + 2*lane, +1
+            resolve_tile_direct<false>(P, gk2, kk, tx0, ty0, lane);
+        }
         return;
     }
 
-    // stage the bin's keys (what the small-triangle path left in L2) and reset them for the next frame
-    {
-        ulonglong2* sk2 = reinterpret_cast<ulonglong2*>(S.keys + warp * 256);
+    // reset the bin's keys in L2 for the next frame (what the small-triangle paths left there is now in shared memory)
+    if (!ms) {
         #pragma unroll
         for (int b4 = 0; b4 < 4; b4++) {
-            sk2[b4 * 32 + lane] = kk[b4];
-            if (!ms && (kk[b4].x != KEY_EMPTY || kk[b4].y != KEY_EMPTY)) gk2[b4 * 32 + lane] = empty2;
+            const ulonglong2 k2 = sk2[b4 * 32 + lane];
+            if (k2.x != KEY_EMPTY || k2.y != KEY_EMPTY) gk2[b4 * 32 + lane] = empty2;
         }
     }
     if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; }
@@ -1540,6 +1689,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             __syncthreads();
             if (!(cursor < nBig && have <= CAND_CAP - 4 * TILE_THREADS)) break;
             const uint32_t i = cursor + 4u * tid;
+            uint32_t hits = 0;
             if (i < nBig) {
                 uint32_t box[4];
                 if (i + 3 < nBig) {
@@ -1549,9 +1699,23 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                     #pragma unroll
                     for (int k = 0; k < 4; k++) box[k] = (i + k < nBig) ? __ldg(P.bigBox + i + k) : 0xFFu;   // x0=255 > x1=0: never matches
                 }
+                hits = (bin_in_box(box[0], bx, by) ? 1u : 0u) | (bin_in_box(box[1], bx, by) ? 2u : 0u) |
+                       (bin_in_box(box[2], bx, by) ? 4u : 0u) | (bin_in_box(box[3], bx, by) ? 8u : 0u);
+            }
+            {
+                // warp-aggregated append: one shared-memory atomic per warp instead of one per hit (a frame of
+                // screen-sized triangles made every thread of every bin hit the same counter: C3, 19 M bank conflicts)
+                const uint32_t cnt = (uint32_t)__popc(hits);
+                uint32_t incl = cnt;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                uint32_t base = 0;
+                if (lane == 31 && total) base = atomicAdd(&S.candCount, total);
+                base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
                 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (bin_in_box(box[k], bx, by)) S.cand[atomicAdd(&S.candCount, 1u)] = i + k;
+                    if (hits & (1u << k)) S.cand[base++] = i + k;
             }
             cursor += 4u * TILE_THREADS;
             __syncthreads();
@@ -1592,18 +1756,31 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                 __syncthreads();
             }
             const uint32_t j = base + tid;
-            if (j < nCand) {
-                BigRec r;
-                load_big(P.big + S.cand[j], r);
-                bool rej, full; float zl, zh;
+            BigRec r;
+            bool rej, full; float zl, zh;
+            {
+                // (threads past the end classify the last candidate again and drop the result: uniform control flow
+                // keeps the record in registers)
+                load_big(P.big + S.cand[min(j, nCand - 1u)], r);
                 // Single progressive pass (hierarchical Z): the bin's depth upper bound S.binU = nearest far side of any
                 // triangle seen so far that covers every pixel of the bin (a racy read of a bound that only shrinks is
                 // conservative); candidates behind it are dropped before their edge tests. Survivors admitted under an
                 // older, looser bound are re-checked against the final bounds tile by tile in raster_survivors.
                 classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, ms, hiz ? S.binU : 0xFFFFFFFFu, rej, full, zl, zh);
-                if (!rej && hiz && full && zh <= 1.0f) atomicMin(&S.binU, order_f32(zh));
+                rej = rej || j >= nCand;
+            }
+            {
+                // one shared-memory atomic per warp for the bound and one for the append (see the candidate scan)
+                if (hiz) {
+                    const uint32_t u = (!rej && full && zh <= 1.0f) ? order_f32(zh) : 0xFFFFFFFFu;
+                    const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, u);
+                    if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&S.binU, m);
+                }
+                const uint32_t keepMask = __ballot_sync(0xFFFFFFFFu, !rej);
+                uint32_t at = 0;
+                if (lane == 0 && keepMask) at = atomicAdd(&S.survCount, (uint32_t)__popc(keepMask));
+                at = __shfl_sync(0xFFFFFFFFu, at, 0) + (uint32_t)__popc(keepMask & ((1u << lane) - 1u));
                 if (!rej) {
-                    const uint32_t at = atomicAdd(&S.survCount, 1u);
                     int4* d2 = reinterpret_cast<int4*>(&S.surv[at]);
                     const int4* s2 = reinterpret_cast<const int4*>(&r);
                     d2[0] = s2[0]; d2[1] = s2[1]; d2[2] = s2[2]; d2[3] = s2[3];

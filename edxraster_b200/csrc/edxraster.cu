@@ -74,6 +74,7 @@ struct edx_context {
     const edx_mesh* lastMesh = nullptr;
     bool framePending = false;
     int launches = 0;
+    std::string launchList;                  // kernels of the last frame, in launch order
     edx_stats stats;
     cudaEvent_t evTimer[2] = { nullptr, nullptr };
     cudaEvent_t evStage[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -223,7 +224,10 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
-    auto launch = [&](auto kernel, dim3 grid, dim3 block, size_t smem) -> cudaError_t {
+    c->launchList.clear();
+    auto launch = [&](const char* name, auto kernel, dim3 grid, dim3 block, size_t smem) -> cudaError_t {
+        if (!c->launchList.empty()) c->launchList += ",";
+        c->launchList += name;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
         cfg.attrs = attr; cfg.numAttrs = 1;
@@ -232,42 +236,44 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     };
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[0], c->stream));
     if (m->nTris && fe == 0) {
-        EDX_CUDA(c, launch(geom_kernel, dim3((m->nTris + 255) / 256), dim3(256), 0));
+        EDX_CUDA(c, launch("geom_kernel", geom_kernel, dim3((m->nTris + 255) / 256), dim3(256), 0));
     } else if (m->nTris) {
         const uint32_t nTC = (m->nTris + 255) / 256, nVC = (m->nVerts + 255) / 256;
-        EDX_CUDA(c, launch(cull_kernel, dim3((nTC + (fe == 2 ? nVC : 0) + 255) / 256), dim3(256), 0));
-        if (fe == 2) EDX_CUDA(c, launch(vertex_kernel, dim3(std::min(nVC, 148u * 8u)), dim3(256), 0));
-        if (fe == 2) EDX_CUDA(c, launch(geom_list_kernel<true>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0));
-        else EDX_CUDA(c, launch(geom_list_kernel<false>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0));
+        EDX_CUDA(c, launch("cull_kernel", cull_kernel, dim3((nTC + (fe == 2 ? nVC : 0) + 255) / 256), dim3(256), 0));
+        if (fe == 2) EDX_CUDA(c, launch("vertex_kernel", vertex_kernel, dim3(std::min(nVC, 148u * 8u)), dim3(256), 0));
+        if (fe == 2) EDX_CUDA(c, launch("geom_list_kernel", geom_list_kernel<true>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0));
+        else EDX_CUDA(c, launch("geom_list_kernel", geom_list_kernel<false>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0));
     }
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[1], c->stream));
-    if (m->nTris) EDX_CUDA(c, launch(clip_kernel, dim3(148 * 4), dim3(128), 0));
-    if (m->nTris && c->midMax > 0) EDX_CUDA(c, launch(mid_kernel, dim3(148 * 4), dim3(128), 0));
+    if (m->nTris) EDX_CUDA(c, launch("clip_kernel", clip_kernel, dim3(148 * 4), dim3(128), 0));
+    if (m->nTris && c->midMax > 0) EDX_CUDA(c, launch("mid_kernel", mid_kernel, dim3(148 * 4), dim3(128), 0));
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[2], c->stream));
     const bool textured = c->shader == EDX_SHADER_LAMBERT_ALBEDO && m->nTex != 0;
     const bool lean = c->msaaLog2 == 0 && (c->leanResolve == 2 || (c->leanResolve == 1 && c->stats.binned_tris == 0));
     P.leanResolve = lean ? 1 : 0;
     const dim3 leanGrid((c->binsX * c->binsY * 16 + 7) / 8);
-    if (c->msaaLog2 == 0 && textured) {
-        // tile_kernel resolves depth + owner ids only; the colour pass is a kernel of its own (see its comment)
+    if (c->msaaLog2 == 0) {
+        // tile_kernel resolves depth (+ owner ids); a shaded frame's colour is a pass of its own over those ids
+        // (shade_kernel: it derives each distinct owner of an 8 x 4 pixel block once)
+        const bool shaded = c->shader != EDX_SHADER_DEPTH_ONLY;
         FrameParams T = P;
-        T.shader = EDX_SHADER_DEPTH_ONLY; T.captureIds = 1;
+        if (shaded) { T.shader = EDX_SHADER_DEPTH_ONLY; T.captureIds = 1; }
         std::swap(P, T);
-        if (lean) EDX_CUDA(c, launch(lean_resolve_kernel<false>, leanGrid, dim3(256), 0));      // (ids are captured: not the depth-only variant)
-        EDX_CUDA(c, launch(tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
+        if (lean && !shaded && !c->captureIds) EDX_CUDA(c, launch("lean_resolve_kernel", lean_resolve_kernel<true>, leanGrid, dim3(256), 0));
+        else if (lean) EDX_CUDA(c, launch("lean_resolve_kernel", lean_resolve_kernel<false>, leanGrid, dim3(256), 0));
+        EDX_CUDA(c, launch("tile_kernel", tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
         std::swap(P, T);
-        const uint32_t blocks = ((c->width + 7) / 8) * ((c->height + 7) / 8);
-        EDX_CUDA(c, launch(textured_resolve_kernel, dim3((blocks + 3) / 4), dim3(256), 0));
-    } else if (c->msaaLog2 == 0) {
-        if (lean && c->shader == EDX_SHADER_DEPTH_ONLY && !c->captureIds) EDX_CUDA(c, launch(lean_resolve_kernel<true>, leanGrid, dim3(256), 0));
-        else if (lean) EDX_CUDA(c, launch(lean_resolve_kernel<false>, leanGrid, dim3(256), 0));
-        EDX_CUDA(c, launch(tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
+        if (shaded) {
+            const uint32_t tiles = ((c->width + TILE_PX - 1) / TILE_PX) * ((c->height + TILE_PX - 1) / TILE_PX);   // one CTA each
+            if (textured) EDX_CUDA(c, launch("shade_kernel", shade_kernel<true>, dim3(tiles), dim3(256), 0));
+            else EDX_CUDA(c, launch("shade_kernel", shade_kernel<false>, dim3(tiles), dim3(256), 0));
+        }
     } else {
         // one CTA per (bin, sample), then the per-pixel resolve that also ends the frame
-        EDX_CUDA(c, launch(tile_kernel<true>, dim3(c->binsX * c->binsY, 1u << c->msaaLog2), dim3(TILE_THREADS), sizeof(TileShared)));
-        EDX_CUDA(c, launch(msaa_resolve_kernel, dim3((c->keyStride + 255) / 256), dim3(256), 0));
+        EDX_CUDA(c, launch("tile_kernel", tile_kernel<true>, dim3(c->binsX * c->binsY, 1u << c->msaaLog2), dim3(TILE_THREADS), sizeof(TileShared)));
+        EDX_CUDA(c, launch("msaa_resolve_kernel", msaa_resolve_kernel, dim3((c->keyStride + 255) / 256), dim3(256), 0));
     }
-    EDX_CUDA(c, launch(frame_end_kernel, dim3(1), dim3(32), 0));       // counters -> pinned host memory, reset for the next frame
+    EDX_CUDA(c, launch("frame_end_kernel", frame_end_kernel, dim3(1), dim3(32), 0));       // counters -> pinned host memory, reset for the next frame
     // frame sink (edx_set_frame_sink): the copy engine pushes the finished buffers, e.g. into the root GPU's memory over NVLink
     if (c->sinkColor && c->shader != EDX_SHADER_DEPTH_ONLY && c->msaaLog2 == 0)
         EDX_CUDA(c, cudaMemcpyAsync(c->sinkColor, P.color, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -934,6 +940,8 @@ int edx_get_stats(edx_context* c, edx_stats* out)
     *out = c->stats;
     return EDX_OK;
 }
+
+const char* edx_last_launch_list(const edx_context* c) { return c ? c->launchList.c_str() : ""; }
 
 int edx_last_launch_count(const edx_context* c) { return c ? c->launches : 0; }
 

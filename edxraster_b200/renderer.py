@@ -256,6 +256,11 @@ class Renderer:
     def LastLaunchCount(self):
         return int(self._lib.edx_last_launch_count(self._h))
 
+    def LastLaunchList(self):
+        """Names of the kernels the last RenderMesh launched, in order."""
+        s = self._lib.edx_last_launch_list(self._h)
+        return [k for k in (s.decode() if s else "").split(",") if k]
+
 
 class FrameRing:
     """Several frames in flight on one GPU. A frame is three dependent kernels of very different shapes (a

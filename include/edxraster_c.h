@@ -199,6 +199,8 @@ int edx_set_option(edx_context* ctx, const char* name, int value);
 int edx_debug_tile_residency(edx_context* ctx, int* ctas_per_sm);
 /* number of kernel launches issued by the last RenderMesh (for bench.py's gpu_launches) */
 int edx_last_launch_count(const edx_context* ctx);
+/* their names, comma-separated, in launch order (valid until the next RenderMesh) */
+const char* edx_last_launch_list(const edx_context* ctx);
 
 #ifdef __cplusplus
 }

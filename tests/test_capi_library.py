@@ -88,9 +88,10 @@ def test_null_handles_are_rejected_not_dereferenced():
     assert not lib.edx_get_back_buffer(None)
     assert not lib.edx_device_color(None) and not lib.edx_device_depth(None)
     assert lib.edx_last_launch_count(None) == 0
+    assert lib.edx_last_launch_list(None) == b""
     assert lib.edx_mesh_destroy(None, None) == 0          # destroying nothing is not an error
     lib.edx_destroy(None)
     lib.edx_last_error(None)
-    untested = set(_lib.SYMBOLS) - set(calls) - {"edx_get_back_buffer", "edx_device_color", "edx_device_depth", "edx_last_launch_count",
+    untested = set(_lib.SYMBOLS) - set(calls) - {"edx_get_back_buffer", "edx_device_color", "edx_device_depth", "edx_last_launch_count", "edx_last_launch_list",
                                                  "edx_mesh_destroy", "edx_destroy", "edx_last_error", "edx_version", "edx_create"}
     assert not untested, untested
