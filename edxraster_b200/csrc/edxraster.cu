@@ -75,6 +75,16 @@ struct edx_context {
     bool framePending = false;
     int launches = 0;
     std::string launchList;                  // kernels of the last frame, in launch order
+    // The frame's kernels as a CUDA graph (one per context, rebuilt when the launch sequence changes shape): a frame is
+    // five to eight launches, ~3.5 us of host time each - more than a small frame takes on the GPU. Replaying the
+    // captured sequence with fresh kernel parameters costs one launch.
+    struct LaunchDesc { const void* func; dim3 grid, block; uint32_t smem; int which; int stage; const char* name; };
+    std::vector<LaunchDesc> seq, graphSeq;
+    std::vector<cudaGraphNode_t> graphNodes;
+    std::vector<cudaKernelNodeParams> graphNodeParams;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t graphExec = nullptr;
+    int graphPdl = -1, graphCarveGen = -1;
+    int useGraphs = 1;                       // edx_set_option("graphs", 0 never | 1 small meshes (launch-bound frames) | 2 always)
     edx_stats stats;
     cudaEvent_t evTimer[2] = { nullptr, nullptr };
     cudaEvent_t evStage[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -82,6 +92,8 @@ struct edx_context {
 };
 
 namespace {
+
+int g_carveGeneration[64];       // bumped whenever clip_kernel's carve-out preference changes: captured graphs keep the old one
 
 int fail(edx_context* c, int code, const std::string& msg)
 {
@@ -218,62 +230,122 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     }
     if (c->shader != EDX_SHADER_DEPTH_ONLY) c->colorDirty = true;
 
-    c->launches = 0;
-    // Frame kernels are launched with programmatic stream serialization (PDL): each may be scheduled while
-    // its predecessor drains and blocks in cudaGridDependencySynchronize() until that one has completed.
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
-    c->launchList.clear();
-    auto launch = [&](const char* name, auto kernel, dim3 grid, dim3 block, size_t smem) -> cudaError_t {
-        if (!c->launchList.empty()) c->launchList += ",";
-        c->launchList += name;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        c->launches++;
-        return cudaLaunchKernelEx(&cfg, kernel, P);
+    // ---- the frame's launch sequence (stage: 0 geometry, 1 clip + mid, 2 tile / shade / end) ----
+    typedef edx_context::LaunchDesc LaunchDesc;
+    std::vector<LaunchDesc>& seq = c->seq;
+    seq.clear();
+    auto add = [&](const char* name, auto kernel, dim3 grid, dim3 block, size_t smem, int which, int stage) {
+        seq.push_back(LaunchDesc{ (const void*)kernel, grid, block, (uint32_t)smem, which, stage, name });
     };
-    if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[0], c->stream));
-    if (m->nTris && fe == 0) {
-        EDX_CUDA(c, launch("geom_kernel", geom_kernel, dim3((m->nTris + 255) / 256), dim3(256), 0));
-    } else if (m->nTris) {
-        const uint32_t nTC = (m->nTris + 255) / 256, nVC = (m->nVerts + 255) / 256;
-        EDX_CUDA(c, launch("cull_kernel", cull_kernel, dim3((nTC + (fe == 2 ? nVC : 0) + 255) / 256), dim3(256), 0));
-        if (fe == 2) EDX_CUDA(c, launch("vertex_kernel", vertex_kernel, dim3(std::min(nVC, 148u * 8u)), dim3(256), 0));
-        if (fe == 2) EDX_CUDA(c, launch("geom_list_kernel", geom_list_kernel<true>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0));
-        else EDX_CUDA(c, launch("geom_list_kernel", geom_list_kernel<false>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0));
-    }
-    if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[1], c->stream));
-    if (m->nTris) EDX_CUDA(c, launch("clip_kernel", clip_kernel, dim3(148 * 4), dim3(128), 0));
-    if (m->nTris && c->midMax > 0) EDX_CUDA(c, launch("mid_kernel", mid_kernel, dim3(148 * 4), dim3(128), 0));
-    if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[2], c->stream));
     const bool textured = c->shader == EDX_SHADER_LAMBERT_ALBEDO && m->nTex != 0;
     const bool lean = c->msaaLog2 == 0 && (c->leanResolve == 2 || (c->leanResolve == 1 && c->stats.binned_tris == 0));
     P.leanResolve = lean ? 1 : 0;
+    // tile_kernel resolves depth (+ owner ids); a shaded single-sample frame's colour is a pass of its own over those
+    // ids (shade_kernel), so the tile kernel sees the frame as depth-only with id capture (parameter block T)
+    const bool shaded = c->shader != EDX_SHADER_DEPTH_ONLY;
+    FrameParams T = P;
+    if (shaded && c->msaaLog2 == 0) { T.shader = EDX_SHADER_DEPTH_ONLY; T.captureIds = 1; }
+    if (m->nTris && fe == 0) {
+        add("geom_kernel", geom_kernel, dim3((m->nTris + 255) / 256), dim3(256), 0, 0, 0);
+    } else if (m->nTris) {
+        const uint32_t nTC = (m->nTris + 255) / 256, nVC = (m->nVerts + 255) / 256;
+        add("cull_kernel", cull_kernel, dim3((nTC + (fe == 2 ? nVC : 0) + 255) / 256), dim3(256), 0, 0, 0);
+        if (fe == 2) add("vertex_kernel", vertex_kernel, dim3(std::min(nVC, 148u * 8u)), dim3(256), 0, 0, 0);
+        if (fe == 2) add("geom_list_kernel", geom_list_kernel<true>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0, 0, 0);
+        else add("geom_list_kernel", geom_list_kernel<false>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0, 0, 0);
+    }
+    if (m->nTris) add("clip_kernel", clip_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
+    if (m->nTris && c->midMax > 0) add("mid_kernel", mid_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
     const dim3 leanGrid((c->binsX * c->binsY * 16 + 7) / 8);
     if (c->msaaLog2 == 0) {
-        // tile_kernel resolves depth (+ owner ids); a shaded frame's colour is a pass of its own over those ids
-        // (shade_kernel: it derives each distinct owner of an 8 x 4 pixel block once)
-        const bool shaded = c->shader != EDX_SHADER_DEPTH_ONLY;
-        FrameParams T = P;
-        if (shaded) { T.shader = EDX_SHADER_DEPTH_ONLY; T.captureIds = 1; }
-        std::swap(P, T);
-        if (lean && !shaded && !c->captureIds) EDX_CUDA(c, launch("lean_resolve_kernel", lean_resolve_kernel<true>, leanGrid, dim3(256), 0));
-        else if (lean) EDX_CUDA(c, launch("lean_resolve_kernel", lean_resolve_kernel<false>, leanGrid, dim3(256), 0));
-        EDX_CUDA(c, launch("tile_kernel", tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared)));
-        std::swap(P, T);
+        if (lean && !shaded && !c->captureIds) add("lean_resolve_kernel", lean_resolve_kernel<true>, leanGrid, dim3(256), 0, 1, 2);
+        else if (lean) add("lean_resolve_kernel", lean_resolve_kernel<false>, leanGrid, dim3(256), 0, 1, 2);
+        add("tile_kernel", tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared), 1, 2);
         if (shaded) {
             const uint32_t tiles = ((c->width + TILE_PX - 1) / TILE_PX) * ((c->height + TILE_PX - 1) / TILE_PX);   // one CTA each
-            if (textured) EDX_CUDA(c, launch("shade_kernel", shade_kernel<true>, dim3(tiles), dim3(256), 0));
-            else EDX_CUDA(c, launch("shade_kernel", shade_kernel<false>, dim3(tiles), dim3(256), 0));
+            if (textured) add("shade_kernel", shade_kernel<true>, dim3(tiles), dim3(256), 0, 0, 2);
+            else add("shade_kernel", shade_kernel<false>, dim3(tiles), dim3(256), 0, 0, 2);
         }
     } else {
         // one CTA per (bin, sample), then the per-pixel resolve that also ends the frame
-        EDX_CUDA(c, launch("tile_kernel", tile_kernel<true>, dim3(c->binsX * c->binsY, 1u << c->msaaLog2), dim3(TILE_THREADS), sizeof(TileShared)));
-        EDX_CUDA(c, launch("msaa_resolve_kernel", msaa_resolve_kernel, dim3((c->keyStride + 255) / 256), dim3(256), 0));
+        add("tile_kernel", tile_kernel<true>, dim3(c->binsX * c->binsY, 1u << c->msaaLog2), dim3(TILE_THREADS), sizeof(TileShared), 0, 2);
+        add("msaa_resolve_kernel", msaa_resolve_kernel, dim3((c->keyStride + 255) / 256), dim3(256), 0, 0, 2);
     }
-    EDX_CUDA(c, launch("frame_end_kernel", frame_end_kernel, dim3(1), dim3(32), 0));       // counters -> pinned host memory, reset for the next frame
+    add("frame_end_kernel", frame_end_kernel, dim3(1), dim3(32), 0, 0, 2);       // counters -> pinned host memory, reset for the next frame
+
+    c->launches = (int)seq.size();
+    c->launchList.clear();
+    for (const LaunchDesc& d : seq) { if (!c->launchList.empty()) c->launchList += ","; c->launchList += d.name; }
+    FrameParams* blocks[2] = { &P, &T };
+    // Frame kernels are launched with programmatic stream serialization (PDL): each may be scheduled while
+    // its predecessor drains and blocks in cudaGridDependencySynchronize() until that one has completed.
+    auto launch_one = [&](const LaunchDesc& d) -> cudaError_t {
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = c->pdl ? 1 : 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = d.grid; cfg.blockDim = d.block; cfg.dynamicSmemBytes = d.smem; cfg.stream = c->stream;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        void* args[1] = { blocks[d.which] };
+        return cudaLaunchKernelExC(&cfg, d.func, args);
+    };
+    // Measured on B200: replay saves ~8 us of host time per frame (C1 with three frames in flight: 25.5 -> 17.1 us)
+    // but a replayed frame takes 4-6 % longer on the GPU than the same kernels launched one by one (C2: 46.1 -> 48.5 us),
+    // so by default only meshes small enough to be launch-bound go through the graph.
+    bool viaGraph = (c->useGraphs == 2 || (c->useGraphs == 1 && m->nTris <= (1u << 18))) && !c->profiling && !dumpBuf;
+    if (viaGraph) {
+        bool same = c->graphExec && c->graphPdl == c->pdl && c->graphCarveGen == g_carveGeneration[c->device & 63] && c->graphSeq.size() == seq.size();
+        for (size_t i = 0; same && i < seq.size(); i++) {
+            const LaunchDesc& a = seq[i]; const LaunchDesc& b = c->graphSeq[i];
+            same = a.func == b.func && a.grid.x == b.grid.x && a.grid.y == b.grid.y && a.block.x == b.block.x && a.smem == b.smem && a.which == b.which;
+        }
+        if (!same) {
+            // (re)capture: the same launches, recorded instead of executed
+            if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }
+            if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+            c->graphNodes.clear(); c->graphNodeParams.clear();
+            bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            for (size_t i = 0; ok && i < seq.size(); i++) {
+                ok = launch_one(seq[i]) == cudaSuccess;
+                cudaStreamCaptureStatus st; const cudaGraphNode_t* deps = nullptr; const cudaGraphEdgeData* edges = nullptr; size_t nDeps = 0;
+                ok = ok && cudaStreamGetCaptureInfo_v3(c->stream, &st, nullptr, nullptr, &deps, &edges, &nDeps) == cudaSuccess && nDeps == 1;
+                if (ok) c->graphNodes.push_back(deps[0]);
+            }
+            cudaGraph_t g = nullptr;
+            const cudaError_t endErr = cudaStreamEndCapture(c->stream, &g);      // always end the capture, even after a failure
+            ok = ok && endErr == cudaSuccess && g;
+            if (ok) { c->graph = g; ok = cudaGraphInstantiate(&c->graphExec, c->graph, 0) == cudaSuccess; }
+            else if (g) cudaGraphDestroy(g);
+            for (size_t i = 0; ok && i < c->graphNodes.size(); i++) {
+                cudaKernelNodeParams np;
+                ok = cudaGraphKernelNodeGetParams(c->graphNodes[i], &np) == cudaSuccess;
+                c->graphNodeParams.push_back(np);
+            }
+            if (ok) { c->graphSeq = seq; c->graphPdl = c->pdl; c->graphCarveGen = g_carveGeneration[c->device & 63]; }
+            else {
+                cudaGetLastError();                       // graphs are an optimisation: fall back to plain launches for good
+                if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }
+                c->useGraphs = 0; viaGraph = false;
+            }
+        } else {
+            for (size_t i = 0; i < seq.size(); i++) {
+                cudaKernelNodeParams np = c->graphNodeParams[i];
+                void* args[1] = { blocks[seq[i].which] };
+                np.kernelParams = args; np.extra = nullptr;
+                EDX_CUDA(c, cudaGraphExecKernelNodeSetParams(c->graphExec, c->graphNodes[i], &np));
+            }
+        }
+        if (viaGraph) EDX_CUDA(c, cudaGraphLaunch(c->graphExec, c->stream));
+    }
+    if (!viaGraph) {
+        int stage = 0;
+        if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[0], c->stream));
+        for (const LaunchDesc& d : seq) {
+            while (c->profiling && stage < d.stage) EDX_CUDA(c, cudaEventRecord(c->evStage[++stage], c->stream));
+            EDX_CUDA(c, launch_one(d));
+        }
+        while (c->profiling && stage < 2) EDX_CUDA(c, cudaEventRecord(c->evStage[++stage], c->stream));
+    }
     // frame sink (edx_set_frame_sink): the copy engine pushes the finished buffers, e.g. into the root GPU's memory over NVLink
     if (c->sinkColor && c->shader != EDX_SHADER_DEPTH_ONLY && c->msaaLog2 == 0)
         EDX_CUDA(c, cudaMemcpyAsync(c->sinkColor, P.color, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -293,6 +365,7 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
 // seen in the last vetted frame. Purely a speed knob - results never depend on it.
 void tune_clip_carveout(edx_context* c, uint32_t tilePairs)
 {
+
     static int current[64];                                    // function attributes are per device (0 = not set yet)
     int want = c->clipCarveout == 0 ? (tilePairs > 100000u ? 2 : 1) : c->clipCarveout;
     int& cur = current[c->device & 63];
@@ -300,6 +373,7 @@ void tune_clip_carveout(edx_context* c, uint32_t tilePairs)
     cudaFuncSetAttribute(clip_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                          want == 2 ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
     cur = want;
+    g_carveGeneration[c->device & 63]++;
 }
 
 // Wait for the pending frame; if a queue overflowed, grow it and run the frame again. Frames submitted earlier
@@ -460,6 +534,8 @@ void edx_destroy(edx_context* c)
     release_frame_buffers(c);
     dev_free(c->big); dev_free(c->bigBox); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->clipSlot); dev_free(c->counters);
     dev_free(c->workList); dev_free(c->vcFlag); dev_free(c->vrec); dev_free(c->mid);
+    if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
+    if (c->graph) cudaGraphDestroy(c->graph);
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& e : c->evTimer) if (e) cudaEventDestroy(e);
     for (auto& e : c->evStage) if (e) cudaEventDestroy(e);
@@ -561,6 +637,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "small_max_clip")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max_clip in [0,64]"); c->smallMaxClip = value; return EDX_OK; }
     if (!strcmp(name, "cluster_cull")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "cluster_cull: 0 off, 1 auto, 2 always"); c->clusterCull = value; return EDX_OK; }
     if (!strcmp(name, "front_end")) { if (value < -1 || value > 2) return fail(c, EDX_ERR_INVALID, "front_end: -1 auto, 0 per-cluster CTAs, 1 cull + work list, 2 cull + per-vertex stage + work list"); c->frontEnd = value; return EDX_OK; }
+    if (!strcmp(name, "graphs")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "graphs: 0 never, 1 small meshes, 2 always"); c->useGraphs = value; return EDX_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }

@@ -40,7 +40,7 @@ def test_reduced_configs_bit_exact(name):
                                           ({"small_max": 2}, True), ({"small_max": 40}, True),
                                           ({"cluster_cull": 2, "pdl": 0}, True), ({"cluster_cull": 0, "small_max_clip": 0}, True),
                                           ({"lean_resolve": 0, "clip_carveout": 2}, True), ({"lean_resolve": 2, "clip_carveout": 1}, True),
-                                          ({"mid_max": 0}, True), ({"mid_max": 0, "small_max": 32}, True), ({"mid_max": 16}, True),
+                                          ({"graphs": 0}, True), ({"graphs": 2, "pdl": 0}, True), ({"mid_max": 0}, True), ({"mid_max": 0, "small_max": 32}, True), ({"mid_max": 16}, True),
                                           ({"mid_max": 512, "small_max": 0, "small_max_clip": 0}, True), ({"mid_max": 200, "small_max": 3}, False)])
 def test_tuning_knobs_never_change_the_image(name, options, hier):
     # routing (direct vs tile path), hierarchical Z and the 8x8 block tests are pure optimisations
