@@ -123,6 +123,12 @@ __global__ void __launch_bounds__(256) vertex_cluster_bounds_kernel(const float4
     }
 }
 
+__global__ void __launch_bounds__(256) fill_f32_kernel(float* __restrict__ p, size_t n, float v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 __global__ void __launch_bounds__(256) fill_keys_kernel(ulonglong2* __restrict__ keys, size_t nPairs)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1388,7 +1394,7 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
 struct TileShared {
     unsigned long long keys[KEYS_PER_BIN];     // 32 KB: [tile 4x4][block 2x2][8x8]
     BigRec surv[SURV_CAP];                     // 48 KB
-    uint32_t cand[CAND_CAP];                   // 8 KB
+    uint32_t cand[CAND_CAP];                   // 16 KB
     uint32_t survCount, candCount;
     uint32_t binU;                             // order_f32 of the bin's depth upper bound
     uint32_t keyMax;                           // scratch: max ordered depth currently stored in the bin

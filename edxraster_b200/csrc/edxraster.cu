@@ -71,6 +71,13 @@ struct edx_context {
 
     uint32_t* clipSlot = nullptr; uint32_t clipSlotCap = 0;   // per triangle: first ClipRec of its fan (this frame)
     uint32_t seenOverFrames = 0;             // Counters::overFrames already accounted for
+    // What the pending frame was submitted with. A caller may change transform, shader, targets ... before the next
+    // synchronising call; if that call has to re-run the frame (queue overflow) it must be the frame as submitted.
+    struct Submitted {
+        edx_host::Mat4 mvp, raster; float eye[3], light[3], albedo[3];
+        int shader, texFilter, hierarchical, captureIds, part, parts;
+        uchar4* extColor; float* extDepth; void* sinkColor; void* sinkDepth;
+    } submitted;
     const edx_mesh* lastMesh = nullptr;
     bool framePending = false;
     int launches = 0;
@@ -141,6 +148,12 @@ int allocate_frame_buffers(edx_context* c, uint32_t w, uint32_t h)
     EDX_CUDA(c, cudaGetLastError());
     EDX_CUDA(c, cudaMemsetAsync(c->color, 0, nPix * sizeof(uchar4), c->stream));     // FrameBuffer.cpp:91-95
     EDX_CUDA(c, cudaMemsetAsync(c->ids, 0xFF, nPix * S * sizeof(uint32_t), c->stream));
+    {
+        // depth reads before the first frame see the reference's clear value 1.0 (FrameBuffer::Init / Clear, FrameBuffer.cpp:103)
+        const size_t n = nPix * S;
+        fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->depth, n, 1.0f);
+        EDX_CUDA(c, cudaGetLastError());
+    }
     c->colorDirty = false;
     return EDX_OK;
 }
@@ -380,6 +393,24 @@ void tune_clip_carveout(edx_context* c, uint32_t tilePairs)
 // without a synchronising call in between cannot be run again (their transform and target are gone): if the
 // device counted more overflowed frames than the ones repaired here, the queues are grown to the largest demand
 // seen and the call reports EDX_ERR_OVERFLOW once, so the caller knows those frames are incomplete.
+void save_submitted(edx_context* c, edx_context::Submitted& s)
+{
+    s.mvp = c->mvp; s.raster = c->raster;
+    memcpy(s.eye, c->eye, 12); memcpy(s.light, c->light, 12); memcpy(s.albedo, c->albedo, 12);
+    s.shader = c->shader; s.texFilter = c->texFilter; s.hierarchical = c->hierarchical; s.captureIds = c->captureIds;
+    s.part = c->part; s.parts = c->parts;
+    s.extColor = c->extColor; s.extDepth = c->extDepth; s.sinkColor = c->sinkColor; s.sinkDepth = c->sinkDepth;
+}
+
+void load_submitted(edx_context* c, const edx_context::Submitted& s)
+{
+    c->mvp = s.mvp; c->raster = s.raster;
+    memcpy(c->eye, s.eye, 12); memcpy(c->light, s.light, 12); memcpy(c->albedo, s.albedo, 12);
+    c->shader = s.shader; c->texFilter = s.texFilter; c->hierarchical = s.hierarchical; c->captureIds = s.captureIds;
+    c->part = s.part; c->parts = s.parts;
+    c->extColor = s.extColor; c->extDepth = s.extDepth; c->sinkColor = s.sinkColor; c->sinkDepth = s.sinkDepth;
+}
+
 int finish_frame(edx_context* c)
 {
     EDX_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -456,7 +487,15 @@ int finish_frame(edx_context* c)
         if (int r = grow(c, c->clipQueue, c->clipQueueCap, k.nClipQueue)) return r;
         if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(k.nClipRecs, 7ull * std::min<uint64_t>(k.nClipQueue, c->clipQueueCap)))) return r;
         c->stats.regrow_count++;
-        if (int r = enqueue_frame(c, c->lastMesh, nullptr, 0)) return r;
+        {
+            // re-run the frame AS SUBMITTED: the caller may have set another transform / shader / target since
+            edx_context::Submitted now;
+            save_submitted(c, now);
+            load_submitted(c, c->submitted);
+            const int r = enqueue_frame(c, c->lastMesh, nullptr, 0);
+            load_submitted(c, now);
+            if (r) return r;
+        }
         EDX_CUDA(c, cudaStreamSynchronize(c->stream));
     }
     return fail(c, EDX_ERR_OVERFLOW, "internal queues still overflow after 8 regrow attempts");
@@ -642,7 +681,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "lean_resolve")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "lean_resolve: 0 never, 1 auto, 2 always"); c->leanResolve = value; return EDX_OK; }
-    if (!strcmp(name, "clip_carveout")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "clip_carveout: 0 auto, 1 L1, 2 shared"); c->clipCarveout = value; tune_clip_carveout(c, c->stats.tile_pairs); return EDX_OK; }
+    if (!strcmp(name, "clip_carveout")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "clip_carveout: 0 auto, 1 L1, 2 shared"); c->clipCarveout = value; if (int r = bind(c)) return r; tune_clip_carveout(c, c->stats.tile_pairs); return EDX_OK; }
     return fail(c, EDX_ERR_INVALID, std::string("unknown option ") + name);
 }
 
@@ -814,6 +853,7 @@ int edx_render_mesh(edx_context* c, const edx_mesh* m)
     if (int r = bind(c)) return r;
     c->lastMesh = m;
     c->stats.submitted_tris = m->nTris;
+    save_submitted(c, c->submitted);
     if (int r = enqueue_frame(c, m, nullptr, 0)) return r;
     c->framePending = true;
     return EDX_OK;
@@ -933,6 +973,7 @@ int edx_debug_raster_triangles(edx_context* c, const edx_mesh* m, uint64_t capac
         }
     }
     cudaFree(d);
+    c->seenOverFrames = c->hostCounters->overFrames;     // attempts that overflowed were repeated right here: nothing was lost
     c->framePending = true;              // a regular frame was rendered alongside; let finish_frame vet its queues
     if (!rc) rc = finish_frame(c);
     return rc;
@@ -1029,8 +1070,8 @@ int edx_debug_tile_residency(edx_context* c, int* ctas_per_sm)
     uint32_t* d = nullptr;
     EDX_CUDA(c, cudaMalloc(&d, 1024 * 4));
     EDX_CUDA(c, cudaMemsetAsync(d, 0, 1024 * 4, c->stream));
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(residency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)); attr = true; }
+    static bool attr[64];                                       // function attributes are per device
+    if (!attr[c->device & 63]) { cudaFuncSetAttribute(residency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)); attr[c->device & 63] = true; }
     residency_kernel<<<2048, TILE_THREADS, sizeof(TileShared), c->stream>>>(d);
     uint32_t h[1024];
     cudaError_t e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
