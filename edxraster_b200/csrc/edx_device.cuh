@@ -21,7 +21,7 @@ constexpr int BLOCK_PX = 8;              // ... tested as four 8x8 blocks, then 
 constexpr int TILES_PER_BIN = (BIN / TILE_PX) * (BIN / TILE_PX);   // 16
 constexpr int KEYS_PER_BIN = BIN * BIN;                            // 4096
 constexpr int TILE_THREADS = TILES_PER_BIN * 32;                   // 512
-constexpr int SURV_CAP = 768;            // per-bin survivor list held in shared memory
+constexpr int SURV_CAP = 640;            // per-bin survivor list held in shared memory (flushed to the rasteriser when it passes SURV_CAP - 512)
 constexpr int CAND_CAP = 4096;           // per-bin candidate indices (bin-box filter hits) held in shared memory
 constexpr int HIZ_MIN_CAND = 48;         // below this many candidates a bin skips hierarchical Z
 
@@ -79,7 +79,8 @@ struct Counters {
     uint32_t overFrames;
     uint32_t maxBig, maxClipQueue, maxClipRecs;
     uint32_t tilePairs;      // (triangle, bin) pairs that survived the bin-level culls this frame: the tile path's load
-    uint32_t maxMid, padMid;
+    uint32_t maxMid;
+    uint32_t nClipMulti;     // straddlers of several planes (back half of the clip queue; nClipQueue counts the single-plane front half)
     uint32_t nWork;          // list front end: triangle clusters that survived cull_kernel this frame
     uint32_t ticket;         // list front end: work items handed out beyond the first gridDim.x
     unsigned long long dbg[8];   // EDX_DEBUG_STATS builds: summed per-CTA cycle counts of the tile kernel's phases

@@ -333,6 +333,19 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
 // ---------------------------------------------------------------------------------------------
 __device__ void clip_single_plane(const FrameParams& P, uint32_t t, const V4& c0, const V4& c1, const V4& c2, uint32_t planes);
 
+// hand a straddler to clip_kernel: single-plane ones to the front half of the queue, the others to the back half
+__device__ __forceinline__ void queue_straddler(const FrameParams& P, uint32_t t, const V4& c0, const V4& c1, const V4& c2, uint32_t planes)
+{
+    const uint32_t half = P.clipQueueCap / 2u;
+    const bool single = __popc(planes) == 1;
+    uint32_t at;
+    if (single) { at = warp_append(&P.counters->nClipQueue); if (at >= half) return; }
+    else { at = warp_append(&P.counters->nClipMulti); if (at >= P.clipQueueCap - half) return; at += half; }
+    float4* q = reinterpret_cast<float4*>(P.clipQueue + at);
+    q[0] = make_float4(c0.x, c0.y, c0.z, c0.w); q[1] = make_float4(c1.x, c1.y, c1.z, c1.w);
+    q[2] = make_float4(c2.x, c2.y, c2.z, c2.w); q[3] = make_float4(__uint_as_float(t), __uint_as_float(planes), 0.0f, 0.0f);
+}
+
 // Stages a1, a2, a5, a6 for one submitted triangle with its vertex work done per corner (front end 0 / 1), then routing.
 __device__ __forceinline__ void geom_triangle(const FrameParams& P, uint32_t t)
 {
@@ -349,12 +362,7 @@ __device__ __forceinline__ void geom_triangle(const FrameParams& P, uint32_t t)
             if (P.fuseClip && __popc(planes) == 1) {
                 clip_single_plane(P, t, c0, c1, c2, planes);     // one plane: clip right here, no queue round trip
             } else {
-                uint32_t at = warp_append(&P.counters->nClipQueue);
-                if (at < P.clipQueueCap) {
-                    float4* q = reinterpret_cast<float4*>(P.clipQueue + at);
-                    q[0] = make_float4(c0.x, c0.y, c0.z, c0.w); q[1] = make_float4(c1.x, c1.y, c1.z, c1.w);
-                    q[2] = make_float4(c2.x, c2.y, c2.z, c2.w); q[3] = make_float4(__uint_as_float(t), 0.0f, 0.0f, 0.0f);
-                }
+                queue_straddler(P, t, c0, c1, c2, planes);
             }
         }
         return;
@@ -514,13 +522,9 @@ __device__ __forceinline__ void geom_triangle_vrec(const FrameParams& P, uint32_
         // cluster only reports ONE plane bit per vertex, so the reject test is repeated with the exact codes.
         const float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
         const V4 c0 = to_clip(P.mvp, p0.x, p0.y, p0.z), c1 = to_clip(P.mvp, p1.x, p1.y, p1.z), c2 = to_clip(P.mvp, p2.x, p2.y, p2.z);
-        if (clip_code(c0) & clip_code(c1) & clip_code(c2)) return;
-        const uint32_t at = warp_append(&P.counters->nClipQueue);
-        if (at < P.clipQueueCap) {
-            float4* q = reinterpret_cast<float4*>(P.clipQueue + at);
-            q[0] = make_float4(c0.x, c0.y, c0.z, c0.w); q[1] = make_float4(c1.x, c1.y, c1.z, c1.w);
-            q[2] = make_float4(c2.x, c2.y, c2.z, c2.w); q[3] = make_float4(__uint_as_float(t), 0.0f, 0.0f, 0.0f);
-        }
+        const uint32_t e0 = clip_code(c0), e1 = clip_code(c1), e2 = clip_code(c2);
+        if (e0 & e1 & e2) return;
+        queue_straddler(P, t, c0, c1, c2, (e0 ^ e1) | (e1 ^ e2) | (e2 ^ e0));
         return;
     }
     SetupTri s;
@@ -679,18 +683,59 @@ __device__ __noinline__ void emit_fan(const FrameParams& P, uint32_t t, int fan,
 
 __device__ __forceinline__ V4 pick3(const V4* c, uint32_t i) { return i == 0 ? c[0] : (i == 1 ? c[1] : c[2]); }
 
+// One clip plane as data instead of control flow, so that straddlers of DIFFERENT planes run the same instructions
+// side by side in a warp. Clipper.h:237-278 per plane: inside test, t = d0 / (d0 - d1), snap.
+//   LEFT / BOTTOM   inside c >= -w   d(v) = c + w   ((w + c) in the reference: commutative)     snap c = -w
+//   RIGHT / TOP / FAR  inside c <= w   d(v) = c - w   ((-w + c) in the reference: the same sum)   snap c = w
+//   NEAR            inside z >= 0    d(v) = z                                                     snap z = 0
+struct PlaneSel {
+    int comp;        // 0 x, 1 y, 2 z
+    bool plus;       // LEFT / BOTTOM
+    bool nearp;
+    __device__ __forceinline__ explicit PlaneSel(uint32_t plane)
+    {
+        comp = (plane & (LEFT_BIT | RIGHT_BIT)) ? 0 : ((plane & (BOTTOM_BIT | TOP_BIT)) ? 1 : 2);
+        plus = (plane & (LEFT_BIT | BOTTOM_BIT)) != 0;
+        nearp = plane == NEAR_BIT;
+    }
+    __device__ __forceinline__ float coord(const V4& v) const { return comp == 0 ? v.x : (comp == 1 ? v.y : v.z); }
+    __device__ __forceinline__ bool inside(const V4& v) const
+    {
+        const float c = coord(v);
+        return nearp ? c >= 0.0f : (plus ? c >= -v.w : c <= v.w);
+    }
+    __device__ __forceinline__ float dist(const V4& v) const
+    {
+        const float c = coord(v);
+        return nearp ? c : fadd(c, plus ? v.w : -v.w);
+    }
+    // one new vertex where edge a->b crosses the plane (Clipper.h:210-214): position, snap, clip weights
+    __device__ __forceinline__ void cut(const V4& a, const V4& b, const float* wa, const float* wb, V4& r, float* rw) const
+    {
+        const float da = dist(a), db = dist(b);
+        const float t = fdiv(da, fsub(da, db));
+        const float s = fsub(1.0f, t);
+        r.x = fadd(fmul(a.x, s), fmul(b.x, t));
+        r.y = fadd(fmul(a.y, s), fmul(b.y, t));
+        r.z = fadd(fmul(a.z, s), fmul(b.z, t));
+        r.w = fadd(fmul(a.w, s), fmul(b.w, t));
+        const float snap = nearp ? 0.0f : (plus ? -r.w : r.w);
+        r.x = comp == 0 ? snap : r.x; r.y = comp == 1 ? snap : r.y; r.z = comp == 2 ? snap : r.z;
+        #pragma unroll
+        for (int k = 0; k < 3; k++) rw[k] = fadd(fmul(wa[k], s), fmul(wb[k], t));
+    }
+};
+
 // One straddler that crosses exactly ONE clip plane (the common case at screen edges): the polygon has 3 or
 // 4 vertices in an order fixed by which vertices are inside (Clipper.h:196-229), so it is built with static
-// indices and lives in registers. Not inlined: it is shared by clip_kernel and (optionally) geom_kernel,
-// where it must not raise the hot path's register count.
+// indices and lives in registers. Plane and inside pattern only enter through selects: a warp full of such
+// straddlers - whatever their planes - executes one instruction stream. Not inlined: it is shared by clip_kernel and
+// (optionally) geom_kernel, where it must not raise the hot path's register count.
 __device__ __noinline__ void clip_single_plane(const FrameParams& P, uint32_t t, const V4& c0, const V4& c1, const V4& c2, uint32_t planes)
 {
     const V4 c[3] = { c0, c1, c2 };
-    // Fast path: exactly one plane is crossed (the common case at screen edges). The polygon has
-    // 3 or 4 vertices in an order fixed by which vertices are inside (Clipper.h:196-229), so it is
-    // built with static indices and lives in registers.
-    const int plane = (int)planes;
-    const uint32_t in = (plane_inside(plane, c[0]) ? 1u : 0u) | (plane_inside(plane, c[1]) ? 2u : 0u) | (plane_inside(plane, c[2]) ? 4u : 0u);
+    const PlaneSel pl(planes);
+    const uint32_t in = (pl.inside(c[0]) ? 1u : 0u) | (pl.inside(c[1]) ? 2u : 0u) | (pl.inside(c[2]) ? 4u : 0u);
     // Exactly two edges cross the plane. In the order Clipper.h:196-229 visits them they are
     //   in = 1:(0>1),(2>0)  2:(0>1),(1>2)  4:(1>2),(2>0)  6:(0>1),(2>0)  5:(0>1),(1>2)  3:(1>2),(2>0)
     const bool firstIs01 = (in != 4u && in != 3u), secondIs20 = (in == 1u || in == 4u || in == 6u || in == 3u);
@@ -700,27 +745,19 @@ __device__ __noinline__ void clip_single_plane(const FrameParams& P, uint32_t t,
     {
         const float ua[3] = { ai == 0u ? 1.0f : 0.0f, ai == 1u ? 1.0f : 0.0f, 0.0f };
         const float uaj[3] = { 0.0f, aj == 1u ? 1.0f : 0.0f, aj == 2u ? 1.0f : 0.0f };
-        cut_vertex(plane, pick3(c, ai), pick3(c, aj), ua, uaj, cutA, wA);
+        pl.cut(pick3(c, ai), pick3(c, aj), ua, uaj, cutA, wA);
         const float ub[3] = { 0.0f, bi == 1u ? 1.0f : 0.0f, bi == 2u ? 1.0f : 0.0f };
         const float ubj[3] = { bj == 0u ? 1.0f : 0.0f, 0.0f, bj == 2u ? 1.0f : 0.0f };
-        cut_vertex(plane, pick3(c, bi), pick3(c, bj), ub, ubj, cutB, wB);
+        pl.cut(pick3(c, bi), pick3(c, bj), ub, ubj, cutB, wB);
     }
-    // assemble the polygon: slot pattern per inside-mask (C = cut, digits = original vertex)
-    //   1:[A,B,0]  2:[A,1,B]  4:[A,2,B]  6:[A,1,2,B]  5:[A,B,2,0]  3:[1,A,B,0]
+    // assemble the polygon: slot pattern per inside-mask (3 = cut A, 4 = cut B, digits = original vertex), three bits
+    // per slot:   1:[A,B,0]  2:[A,1,B]  4:[A,2,B]  6:[A,1,2,B]  5:[A,B,2,0]  3:[1,A,B,0]
+    const uint32_t pattern = in == 1u ? 00043u : (in == 2u ? 04413u : (in == 4u ? 04423u : (in == 6u ? 04213u : (in == 5u ? 00243u : 00431u))));
     V4 v[4]; float w[4][3]; int nv = (in == 1u || in == 2u || in == 4u) ? 3 : 4;
     if (in == 0u || in == 7u) nv = 0;
-    int kind[4];           // 0..2 original vertex, 3 = cutA, 4 = cutB
-    switch (in) {
-    case 1: kind[0] = 3; kind[1] = 4; kind[2] = 0; kind[3] = 0; break;
-    case 2: kind[0] = 3; kind[1] = 1; kind[2] = 4; kind[3] = 4; break;
-    case 4: kind[0] = 3; kind[1] = 2; kind[2] = 4; kind[3] = 4; break;
-    case 6: kind[0] = 3; kind[1] = 1; kind[2] = 2; kind[3] = 4; break;
-    case 5: kind[0] = 3; kind[1] = 4; kind[2] = 2; kind[3] = 0; break;
-    default: kind[0] = 1; kind[1] = 3; kind[2] = 4; kind[3] = 0; break;
-    }
     #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const int kd = kind[k];
+        const int kd = (int)((pattern >> (3 * k)) & 7u);
         v[k] = kd == 3 ? cutA : (kd == 4 ? cutB : pick3(c, (uint32_t)kd));
         #pragma unroll
         for (int m = 0; m < 3; m++) w[k][m] = kd == 3 ? wA[m] : (kd == 4 ? wB[m] : (kd == m ? 1.0f : 0.0f));
@@ -745,14 +782,26 @@ __device__ __noinline__ void clip_single_plane(const FrameParams& P, uint32_t t,
 __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ FrameParams P)
 {
     cudaGridDependencySynchronize();
-    const uint32_t n = min(P.counters->nClipQueue, P.clipQueueCap);
-    // Work item q goes to lane q / W of warp q % W (W = warps in the grid): a short queue is spread one
-    // triangle per warp over the whole chip instead of packing 32 divergent clippers into each of a
-    // few warps; a long queue still fills every lane.
+    // The queue has two halves. Front: straddlers of exactly one plane - one instruction stream whatever the plane,
+    // so they are packed 32 to a warp. Back: straddlers of several planes - long, data-dependent loops over
+    // local-memory polygons - spread one per warp first so a short queue costs one item's latency, not 32.
+    const uint32_t half = P.clipQueueCap / 2u;
+    const uint32_t n1 = min(P.counters->nClipQueue, half), nN = min(P.counters->nClipMulti, P.clipQueueCap - half);
+    const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, nThreads = gridDim.x * blockDim.x;
+    for (uint32_t q = gtid; q < n1; q += nThreads) {
+        const float4* item = reinterpret_cast<const float4*>(P.clipQueue + q);
+        const float4 q0 = __ldg(item), q1 = __ldg(item + 1), q2 = __ldg(item + 2), q3 = __ldg(item + 3);
+        V4 c0, c1, c2;
+        c0.x = q0.x; c0.y = q0.y; c0.z = q0.z; c0.w = q0.w;
+        c1.x = q1.x; c1.y = q1.y; c1.z = q1.z; c1.w = q1.w;
+        c2.x = q2.x; c2.y = q2.y; c2.z = q2.z; c2.w = q2.w;
+        clip_single_plane(P, __float_as_uint(q3.x), c0, c1, c2, __float_as_uint(q3.y));
+    }
+    // Work item q goes to lane q / W of warp q % W (W = warps in the grid)
     const uint32_t W = gridDim.x * (blockDim.x >> 5);
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    for (uint32_t q = (threadIdx.x & 31u) * W + gw; q < n; q += 32u * W) {
-        const float4* item = reinterpret_cast<const float4*>(P.clipQueue + q);
+    for (uint32_t q = (threadIdx.x & 31u) * W + gw; q < nN; q += 32u * W) {
+        const float4* item = reinterpret_cast<const float4*>(P.clipQueue + half + q);
         const float4 q0 = __ldg(item), q1 = __ldg(item + 1), q2 = __ldg(item + 2), q3 = __ldg(item + 3);
         const uint32_t t = __float_as_uint(q3.x);
         V4 c[3];
@@ -761,8 +810,6 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
         c[2].x = q2.x; c[2].y = q2.y; c[2].z = q2.z; c[2].w = q2.w;
         const uint32_t k0 = clip_code(c[0]), k1 = clip_code(c[1]), k2 = clip_code(c[2]);
         const uint32_t planes = (k0 ^ k1) | (k1 ^ k2) | (k2 ^ k0);           // Clipper.h:119
-
-        if (__popc(planes) == 1) { clip_single_plane(P, t, c[0], c[1], c[2], planes); continue; }
 
         // General path: several planes, up to 9 vertices, polygon in local memory.
         Poly a, b;
@@ -1393,11 +1440,13 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
 // ---------------------------------------------------------------------------------------------
 struct TileShared {
     unsigned long long keys[KEYS_PER_BIN];     // 32 KB: [tile 4x4][block 2x2][8x8]
-    BigRec surv[SURV_CAP];                     // 48 KB
-    uint32_t cand[CAND_CAP];                   // 16 KB
+    BigRec surv[SURV_CAP];                     // 40 KB
+    uint32_t cand[CAND_CAP];                   // 16 KB: candidate indices of the current chunk of the tile-path list ...
+    uint32_t candZ[CAND_CAP];                  // 16 KB: ... and their ordered near depth (0xFFFFFFFF = rejected)
     uint32_t survCount, candCount;
     uint32_t binU;                             // order_f32 of the bin's depth upper bound
     uint32_t keyMax;                           // scratch: max ordered depth currently stored in the bin
+    uint32_t admitCount, admitNear;            // scratch: candidates the bin's bound admits, the nearest of them
     unsigned long long keysReady;              // mbarrier: the bulk copy of the bin's keys has landed
 };
 
@@ -1469,6 +1518,23 @@ __device__ __forceinline__ void raster_survivors(const FrameParams& P, TileShare
     #pragma unroll
     for (int j = 0; j < 8; j++) k[j] = tkeys[j * 32 + lane];
     uint32_t U = order_f32(1.0f);
+    if (hiz) {
+        // Bound pass: the tile's depth upper bound is a pure minimum - the nearest far side of any survivor that
+        // covers the whole tile (and what the tile already holds) - so it is taken over the WHOLE list before anything
+        // is rasterised. A bound that only tightens as the list is walked makes the work depend on the order the
+        // clipper happened to append the triangles in (C3: 550K or 670K surviving pairs, a 3x swing in time).
+        U = min(U, tile_key_max(k, tx0, ty0, P.width, P.height));
+        uint32_t zhiAll = 0xFFFFFFFFu;
+        for (int b = 0; b < n; b += 32) {
+            const int j = b + lane;
+            if (j < n) {
+                bool rej, full; float zl, zh;
+                classify_rect(S.surv[j], tx0, ty0, TILE_PX, P.width, P.height, true, ms, min(U, S.binU), rej, full, zl, zh);
+                if (!rej && full && zh <= 1.0f) zhiAll = min(zhiAll, order_f32(zh));
+            }
+        }
+        U = min(U, __reduce_min_sync(0xFFFFFFFFu, zhiAll));
+    }
     for (int b = 0; b < n; b += 32) {
         if (hiz) U = min(U, tile_key_max(k, tx0, ty0, P.width, P.height));
         const int j = b + lane;
@@ -1532,14 +1598,17 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     // every load first (nine independent L2 reads in flight), then the stores from registers; no fence: the host
     // reads the pinned copy only after the stream has completed this kernel
     volatile Counters* d = P.counters;
-    const uint32_t nBig = d->nBig, nClipQueue = d->nClipQueue, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid;
+    const uint32_t nBig = d->nBig, nClip1 = d->nClipQueue, nClipN = d->nClipMulti, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid;
+    // the clip queue is split in two halves (clip_kernel): publish a demand that exceeds the capacity exactly when a half overflowed
+    const uint32_t halfQ = P.clipQueueCap / 2u;
+    const uint32_t nClipQueue = (nClip1 > halfQ || nClipN > P.clipQueueCap - halfQ) ? 2u * max(nClip1, nClipN) + 2u : nClip1 + nClipN;
     uint32_t overFrames = d->overFrames;
     const uint32_t maxBig = max(d->maxBig, nBig), maxClipQueue = max(d->maxClipQueue, nClipQueue), maxClipRecs = max(d->maxClipRecs, nClipRecs), maxMid = max(d->maxMid, nMid);
 #ifdef EDX_DEBUG_STATS
     for (int i = 0; i < 8; i++) { P.hostCounters->dbg[i] = P.counters->dbg[i]; P.counters->dbg[i] = 0; }
 #endif
     if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap || nMid > P.midCap) overFrames++;
-    d->nBig = 0; d->nClipQueue = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0;
+    d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0;
     d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs; d->maxMid = maxMid;
     volatile Counters* h = P.hostCounters;
     h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid;
@@ -1678,7 +1747,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             if (k2.x != KEY_EMPTY || k2.y != KEY_EMPTY) gk2[b4 * 32 + lane] = empty2;
         }
     }
-    if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; }
+    if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; S.admitCount = 0; S.admitNear = 0xFFFFFFFFu; }
     __syncthreads();
 #ifdef EDX_DEBUG_STATS
     long long tMark = clock64(), tCand = 0, tSweep = 0, tFlush = 0, nFlush = 0, nSurvTot = 0;
@@ -1731,68 +1800,101 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
 #endif
         const uint32_t nCand = S.candCount;
         const bool hiz = hizOn && nCand >= HIZ_MIN_CAND;
-        // 3. exact reject + depth cull against the bin; survivors go to shared memory and are rasterised
-        //    whenever the list fills up
+        // 3a. classify every candidate against the bin: exact reject, and (hierarchical Z) its conservative near depth;
+        //     a candidate that covers the whole bin lowers the bin's depth upper bound S.binU to its far side. The bound
+        //     is a pure minimum over the candidates, so it is complete before anything is admitted (3b): which
+        //     triangles survive does not depend on the order the list was appended in.
         for (uint32_t base = 0; base < nCand; base += TILE_THREADS) {
-            const uint32_t haveSurv = S.survCount;               // same rule: read, barrier, then decide
-            __syncthreads();
-            if (haveSurv > SURV_CAP - TILE_THREADS) {
-                if (tid == 0) atomicAdd(&P.counters->tilePairs, haveSurv);
-#ifdef EDX_DEBUG_STATS
-                long long tF = clock64(); nFlush++; nSurvTot += haveSurv;
-#endif
-                raster_survivors<MS>(P, S, ox, oy, hiz, offX, offY);
-                __syncthreads();
-#ifdef EDX_DEBUG_STATS
-                tFlush += clock64() - tF;
-#endif
-                if (hiz) {
-                    // what is now stored in the bin bounds everything still to come
-                    if (tx0 < P.width && ty0 < P.height) {
-                        unsigned long long kk[8];
-                        #pragma unroll
-                        for (int j = 0; j < 8; j++) kk[j] = S.keys[warp * 256 + j * 32 + lane];
-                        const uint32_t m = tile_key_max(kk, tx0, ty0, P.width, P.height);
-                        if (lane == 0) atomicMax(&S.keyMax, m);
-                    }
-                    __syncthreads();
-                    if (tid == 0) { S.binU = min(S.binU, S.keyMax); S.keyMax = 0; }
-                }
-                if (tid == 0) S.survCount = 0;
-                __syncthreads();
-            }
             const uint32_t j = base + tid;
             BigRec r;
             bool rej, full; float zl, zh;
-            {
-                // (threads past the end classify the last candidate again and drop the result: uniform control flow
-                // keeps the record in registers)
-                load_big(P.big + S.cand[min(j, nCand - 1u)], r);
-                // Single progressive pass (hierarchical Z): the bin's depth upper bound S.binU = nearest far side of any
-                // triangle seen so far that covers every pixel of the bin (a racy read of a bound that only shrinks is
-                // conservative); candidates behind it are dropped before their edge tests. Survivors admitted under an
-                // older, looser bound are re-checked against the final bounds tile by tile in raster_survivors.
-                classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, ms, hiz ? S.binU : 0xFFFFFFFFu, rej, full, zl, zh);
-                rej = rej || j >= nCand;
+            // (threads past the end classify the last candidate again and drop the result: uniform control flow
+            // keeps the record in registers)
+            load_big(P.big + S.cand[min(j, nCand - 1u)], r);
+            classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, ms, hiz ? S.binU : 0xFFFFFFFFu, rej, full, zl, zh);
+            rej = rej || j >= nCand;
+            if (hiz) {
+                const uint32_t u = (!rej && full && zh <= 1.0f) ? order_f32(zh) : 0xFFFFFFFFu;
+                const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, u);
+                if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&S.binU, m);      // one shared-memory atomic per warp
             }
-            {
-                // one shared-memory atomic per warp for the bound and one for the append (see the candidate scan)
-                if (hiz) {
-                    const uint32_t u = (!rej && full && zh <= 1.0f) ? order_f32(zh) : 0xFFFFFFFFu;
-                    const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, u);
-                    if (lane == 0 && m != 0xFFFFFFFFu) atomicMin(&S.binU, m);
-                }
-                const uint32_t keepMask = __ballot_sync(0xFFFFFFFFu, !rej);
-                uint32_t at = 0;
-                if (lane == 0 && keepMask) at = atomicAdd(&S.survCount, (uint32_t)__popc(keepMask));
-                at = __shfl_sync(0xFFFFFFFFu, at, 0) + (uint32_t)__popc(keepMask & ((1u << lane) - 1u));
-                if (!rej) {
-                    int4* d2 = reinterpret_cast<int4*>(&S.surv[at]);
-                    const int4* s2 = reinterpret_cast<const int4*>(&r);
-                    d2[0] = s2[0]; d2[1] = s2[1]; d2[2] = s2[2]; d2[3] = s2[3];
-                }
-            }
+            if (j < nCand) S.candZ[j] = rej ? 0xFFFFFFFFu : (hiz ? min(order_f32(zl), 0xFFFFFFFEu) : 0u);
+        }
+        __syncthreads();
+        // 3b. admit what can still be visible; survivors go to shared memory and are rasterised whenever the list fills
+        //     up. A bin that no candidate covers completely (the diagonal of a screen-sized quad's two fan triangles)
+        //     gets no bound from 3a; what bounds it is the depth already drawn. So a long admission list is walked
+        //     NEAREST FIRST, in eight slabs of near depth with a raster flush after each: once the near triangles are
+        //     drawn, the bin's (and in raster_survivors each tile's) stored depth culls the slabs behind them - again
+        //     whatever order the list was appended in.
+        auto flush = [&](uint32_t haveSurv) {
+            if (tid == 0) atomicAdd(&P.counters->tilePairs, haveSurv);
+#ifdef EDX_DEBUG_STATS
+            long long tF = clock64(); nFlush++; nSurvTot += haveSurv;
+#endif
+            raster_survivors<MS>(P, S, ox, oy, hiz, offX, offY);
             __syncthreads();
+#ifdef EDX_DEBUG_STATS
+            tFlush += clock64() - tF;
+#endif
+            if (hiz) {
+                // what is now stored in the bin bounds everything still to come
+                if (tx0 < P.width && ty0 < P.height) {
+                    unsigned long long kk[8];
+                    #pragma unroll
+                    for (int j = 0; j < 8; j++) kk[j] = S.keys[warp * 256 + j * 32 + lane];
+                    const uint32_t m = tile_key_max(kk, tx0, ty0, P.width, P.height);
+                    if (lane == 0) atomicMax(&S.keyMax, m);
+                }
+                __syncthreads();
+                if (tid == 0) { S.binU = min(S.binU, S.keyMax); S.keyMax = 0; }
+            }
+            if (tid == 0) S.survCount = 0;
+            __syncthreads();
+        };
+        uint32_t nSlabs = 1, zNear = 0, zFar = 0xFFFFFFFEu;
+        if (hiz) {
+            const uint32_t U0 = S.binU;
+            uint32_t cnt = 0, zmin = 0xFFFFFFFFu;
+            for (uint32_t j = tid; j < nCand; j += TILE_THREADS) {
+                const uint32_t z = S.candZ[j];
+                if (z <= U0) { cnt++; zmin = min(zmin, z); }
+            }
+            cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+            zmin = __reduce_min_sync(0xFFFFFFFFu, zmin);
+            if (lane == 0 && cnt) { atomicAdd(&S.admitCount, cnt); atomicMin(&S.admitNear, zmin); }
+            __syncthreads();
+            if (S.admitCount > (uint32_t)(SURV_CAP - TILE_THREADS)) { nSlabs = 8; zNear = S.admitNear; zFar = U0; }
+            __syncthreads();
+            if (tid == 0) { S.admitCount = 0; S.admitNear = 0xFFFFFFFFu; }
+        }
+        for (uint32_t slab = 0; slab < nSlabs; slab++) {
+            const uint32_t span = zFar - zNear;
+            const uint32_t lo = slab == 0 ? 0u : zNear + (uint32_t)(((unsigned long long)span * slab) / nSlabs) + 1u;
+            const uint32_t hi = slab + 1 == nSlabs ? 0xFFFFFFFEu : zNear + (uint32_t)(((unsigned long long)span * (slab + 1)) / nSlabs);
+            for (uint32_t base = 0; base < nCand; base += TILE_THREADS) {
+                const uint32_t haveSurv = S.survCount;               // same rule: read, barrier, then decide
+                __syncthreads();
+                if (haveSurv > SURV_CAP - TILE_THREADS) flush(haveSurv);
+                const uint32_t j = base + tid;
+                const uint32_t z = j < nCand ? S.candZ[j] : 0xFFFFFFFFu;
+                const bool keep = z >= lo && z <= hi && z <= (hiz ? S.binU : 0xFFFFFFFEu);
+                const uint32_t keepMask = __ballot_sync(0xFFFFFFFFu, keep);
+                uint32_t at = 0;
+                if (lane == 0 && keepMask) at = atomicAdd(&S.survCount, (uint32_t)__popc(keepMask));     // one shared-memory atomic per warp
+                at = __shfl_sync(0xFFFFFFFFu, at, 0) + (uint32_t)__popc(keepMask & ((1u << lane) - 1u));
+                if (keep) {
+                    const int4* s2 = reinterpret_cast<const int4*>(P.big + S.cand[j]);
+                    int4* d2 = reinterpret_cast<int4*>(&S.surv[at]);
+                    d2[0] = __ldg(s2); d2[1] = __ldg(s2 + 1); d2[2] = __ldg(s2 + 2); d2[3] = __ldg(s2 + 3);
+                }
+                __syncthreads();
+            }
+            if (nSlabs > 1 && slab + 1 < nSlabs) {
+                const uint32_t haveSurv = S.survCount;
+                __syncthreads();
+                if (haveSurv) flush(haveSurv);
+            }
         }
         if (tid == 0) S.candCount = 0;
         __syncthreads();

@@ -52,7 +52,7 @@ struct edx_context {
     uint32_t* vcFlag = nullptr; uint32_t vcFlagCap = 0;
     int4* vrec = nullptr; uint32_t vrecCap = 0;
     int leanResolve = 0;                     // 0 never (default: measured slower with frames in flight), 1 when the last vetted frame had an empty tile path, 2 always
-    int clipCarveout = 0;                    // 0 auto (follow the tile path's load), 1 prefer L1, 2 prefer shared memory
+    int clipCarveout = 1;                    // 1 default carve-out (large L1; the clipper's polygons live in local memory), 2 prefer shared memory
     bool colorDirty = false;
 
     unsigned long long* keys = nullptr;
@@ -369,18 +369,18 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     return EDX_OK;
 }
 
-// Which shared-memory carve-out clip_kernel asks for. Measured on B200 ("carve-out"): when the
-// clipper runs with the default (large L1) configuration, the tile kernel that follows it takes up to 2x longer on
-// frames dominated by the tile path (C3: 0.80 -> 1.65 ms in a process that uses no other CUDA module); when it asks
-// for the max-shared configuration the tile kernel always runs at full speed (0.70 ms) but the clipper itself, whose
-// polygons live in local memory, slows down (C2 +12 us, C4 +16 us per frame). The mechanism is not understood (CTA
-// residency, clocks and per-CTA cycle counts are identical in both states). So: follow the load of the tile path
-// seen in the last vetted frame. Purely a speed knob - results never depend on it.
-void tune_clip_carveout(edx_context* c, uint32_t tilePairs)
+// Which shared-memory carve-out clip_kernel asks for (`edx_set_option("clip_carveout", 1 | 2)`, an experiment knob).
+// Round 1 found that C3 ran 0.8 or 1.65 ms per frame depending on this preference and followed the tile path's load
+// with a heuristic. The cause is now known: the preference changes how fast the clipper runs -
+// its polygons live in local memory, so it is 2.4x faster with the large L1 - and thereby the ORDER in which it
+// appends the large triangles; the tile kernel's hierarchical Z used to cull progressively, in list order, and on
+// the bins that no single triangle covers a bad order left thousands of survivors. The bound is now complete before
+// anything is admitted and long lists are walked nearest first, so the order no longer matters and the clipper
+// simply keeps the default (large L1) configuration.
+void tune_clip_carveout(edx_context* c, uint32_t)
 {
-
     static int current[64];                                    // function attributes are per device (0 = not set yet)
-    int want = c->clipCarveout == 0 ? (tilePairs > 100000u ? 2 : 1) : c->clipCarveout;
+    const int want = c->clipCarveout == 2 ? 2 : 1;
     int& cur = current[c->device & 63];
     if (want == cur) return;
     cudaFuncSetAttribute(clip_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -556,7 +556,9 @@ int edx_create(int device, edx_context** out)
               cudaHostGetDevicePointer((void**)&c->hostCountersDev, c->hostCounters, 0) == cudaSuccess &&
               cudaMemset(c->counters, 0, sizeof(Counters)) == cudaSuccess &&
               cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
-              cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess;
+              cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileShared)) == cudaSuccess &&
+              cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+              cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) == cudaSuccess;
     for (int i = 0; ok && i < 2; i++) ok = cudaEventCreate(&c->evTimer[i]) == cudaSuccess;
     for (int i = 0; ok && i < 4; i++) ok = cudaEventCreate(&c->evStage[i]) == cudaSuccess;
     if (!ok) { edx_destroy(c); return EDX_ERR_CUDA; }
@@ -681,7 +683,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "hiz")) { c->hiz = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "lean_resolve")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "lean_resolve: 0 never, 1 auto, 2 always"); c->leanResolve = value; return EDX_OK; }
-    if (!strcmp(name, "clip_carveout")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "clip_carveout: 0 auto, 1 L1, 2 shared"); c->clipCarveout = value; if (int r = bind(c)) return r; tune_clip_carveout(c, c->stats.tile_pairs); return EDX_OK; }
+    if (!strcmp(name, "clip_carveout")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "clip_carveout: 1 L1 (default), 2 shared"); if (value == 0) value = 1; c->clipCarveout = value; if (int r = bind(c)) return r; tune_clip_carveout(c, c->stats.tile_pairs); return EDX_OK; }
     return fail(c, EDX_ERR_INVALID, std::string("unknown option ") + name);
 }
 
