@@ -23,6 +23,7 @@ constexpr int KEYS_PER_BIN = BIN * BIN;                            // 4096
 constexpr int TILE_THREADS = TILES_PER_BIN * 32;                   // 512
 constexpr int SURV_CAP = 640;            // per-bin survivor list held in shared memory (flushed to the rasteriser when it passes SURV_CAP - 512)
 constexpr int CAND_CAP = 4096;           // per-bin candidate indices (bin-box filter hits) held in shared memory
+constexpr int SORT_MIN = 1024, SORT_MAX = 65536;   // tile-path lists of this length are put in nearest-first order (sort_big_kernel)
 constexpr int HIZ_MIN_CAND = 48;         // below this many candidates a bin skips hierarchical Z
 
 constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
@@ -80,6 +81,7 @@ struct Counters {
     uint32_t maxBig, maxClipQueue, maxClipRecs;
     uint32_t tilePairs;      // (triangle, bin) pairs that survived the bin-level culls this frame: the tile path's load
     uint32_t maxMid;
+    uint32_t bigSorted;      // this frame's tile-path list has a nearest-first order (sort_big_kernel)
     uint32_t nClipMulti;     // straddlers of several planes (back half of the clip queue; nClipQueue counts the single-plane front half)
     uint32_t nWork;          // list front end: triangle clusters that survived cull_kernel this frame
     uint32_t ticket;         // list front end: work items handed out beyond the first gridDim.x
@@ -135,6 +137,9 @@ struct FrameParams {
     MidRec* mid; uint32_t midCap;
     BigRec* big; uint32_t bigCap;
     uint32_t* bigBox;                    // per tile-path triangle: its bin bounding box, 4 x u8 (x0, x1, y0, y1)
+    // nearest-first view of the tile-path list (sort_big_kernel): position -> record index, bin box, and a lower bound of
+    // the depth any triangle at or after the position can produce (bigKey: scratch, keys in list order)
+    uint32_t* bigOrder; uint32_t* bigKey; uint32_t* bigBoxSorted; uint32_t* bigBound;
     ClipItem* clipQueue; uint32_t clipQueueCap;
     ClipRec* clipRecs; uint32_t clipRecCap;
     uint32_t* clipSlot;                  // per submitted triangle: first ClipRec of its polygon

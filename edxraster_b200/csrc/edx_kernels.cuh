@@ -1438,6 +1438,80 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
 }
 
 // ---------------------------------------------------------------------------------------------
+// sort_big_kernel: puts the frame's tile-path list in nearest-first order (one CTA; lists shorter than SORT_MIN or
+// longer than SORT_MAX stay as appended). key = ordered( min vertex depth - the slack classify_rect allows itself ):
+// a lower bound of the near depth classify_rect computes for ANY rect. A counting sort over 1024 depth buckets is
+// enough: what tile_kernel needs at position p is a lower bound of the keys of ALL later entries - the lower edge of
+// p's bucket - so that a bin whose depth bound is below it can stop reading the list there. Screen-sized triangles
+// made every bin classify the whole list (C3: 4000 candidates per bin, two thirds of the tile kernel's time) although
+// the nearest few settle it.
+// ---------------------------------------------------------------------------------------------
+constexpr int SORT_BUCKETS = 1024;
+
+__device__ __forceinline__ uint32_t big_sort_key(const BigRec* r)
+{
+    const float4 a = __ldg(reinterpret_cast<const float4*>(r) + 1);      // v2x v2y z0 z1
+    const float z2 = __ldg(reinterpret_cast<const float*>(r) + 8);
+    const float vlo = fminf(a.z, fminf(a.w, z2)), vhi = fmaxf(a.z, fmaxf(a.w, z2));
+    if (!(vlo == vlo) || !(vhi == vhi)) return 0u;                        // NaN depths: never used to stop a bin
+    const float Ed = 1e-5f * fmaxf(fabsf(vlo), fabsf(vhi)) + 1e-30f;     // as classify_rect
+    return min(order_f32(vlo - 2.0f * Ed), 0xFFFFFFFEu);
+}
+
+__global__ void __launch_bounds__(1024) sort_big_kernel(const __grid_constant__ FrameParams P)
+{
+    __shared__ uint32_t sCount[SORT_BUCKETS];
+    __shared__ uint32_t sMin, sMax;
+    const uint32_t tid = threadIdx.x;
+    sCount[tid] = 0;
+    if (tid == 0) { sMin = 0xFFFFFFFFu; sMax = 0u; }
+    cudaGridDependencySynchronize();
+    const uint32_t n = min(P.counters->nBig, P.bigCap);
+    if (n < (uint32_t)SORT_MIN || n > (uint32_t)SORT_MAX) { if (tid == 0) P.counters->bigSorted = 0; return; }
+    __syncthreads();
+    // keys (parked in bigKey), their range
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (uint32_t i = tid; i < n; i += 1024u) { const uint32_t k = big_sort_key(P.big + i); P.bigKey[i] = k; lo = min(lo, k); hi = max(hi, k); }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if ((tid & 31u) == 0) { atomicMin(&sMin, lo); atomicMax(&sMax, hi); }
+    __syncthreads();
+    const uint32_t kmin = sMin;
+    const unsigned long long range = (unsigned long long)(sMax - kmin) + 1ull;
+    // histogram -> exclusive scan -> scatter
+    for (uint32_t i = tid; i < n; i += 1024u)
+        atomicAdd(&sCount[(uint32_t)(((unsigned long long)(P.bigKey[i] - kmin) * SORT_BUCKETS) / range)], 1u);
+    __syncthreads();
+    {
+        const uint32_t c = sCount[tid];
+        uint32_t incl = c;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((tid & 31u) >= (uint32_t)o) incl += v; }
+        __shared__ uint32_t sWarp[32];
+        if ((tid & 31u) == 31u) sWarp[tid >> 5] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t w = sWarp[tid];
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, w, o); if (tid >= (uint32_t)o) w += v; }
+            sWarp[tid] = w;
+        }
+        __syncthreads();
+        sCount[tid] = incl - c + ((tid >> 5) ? sWarp[(tid >> 5) - 1] : 0u);       // first position of bucket tid
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += 1024u) {
+        const uint32_t k = P.bigKey[i];
+        const uint32_t b = (uint32_t)(((unsigned long long)(k - kmin) * SORT_BUCKETS) / range);
+        const uint32_t at = atomicAdd(&sCount[b], 1u);
+        P.bigOrder[at] = i;
+        P.bigBoxSorted[at] = __ldg(P.bigBox + i);
+        // every key of bucket b and of the buckets after it is >= this
+        P.bigBound[at] = kmin + (uint32_t)(((unsigned long long)b * range) / SORT_BUCKETS);
+    }
+    if (tid == 0) P.counters->bigSorted = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 struct TileShared {
     unsigned long long keys[KEYS_PER_BIN];     // 32 KB: [tile 4x4][block 2x2][8x8]
     BigRec surv[SURV_CAP];                     // 40 KB
@@ -1754,25 +1828,67 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
 #endif
 
     const bool hizOn = P.hiz && P.hierarchical;
+    auto flush_bin = [&](uint32_t haveSurv, bool hiz) {
+        if (tid == 0) atomicAdd(&P.counters->tilePairs, haveSurv);
+#ifdef EDX_DEBUG_STATS
+        long long tF = clock64(); nFlush++; nSurvTot += haveSurv;
+#endif
+        raster_survivors<MS>(P, S, ox, oy, hiz, offX, offY);
+        __syncthreads();
+#ifdef EDX_DEBUG_STATS
+        tFlush += clock64() - tF;
+#endif
+        if (hiz) {
+            // what is now stored in the bin bounds everything still to come
+            if (tx0 < P.width && ty0 < P.height) {
+                unsigned long long kk[8];
+                #pragma unroll
+                for (int j = 0; j < 8; j++) kk[j] = S.keys[warp * 256 + j * 32 + lane];
+                const uint32_t m = tile_key_max(kk, tx0, ty0, P.width, P.height);
+                if (lane == 0) atomicMax(&S.keyMax, m);
+            }
+            __syncthreads();
+            if (tid == 0) { S.binU = min(S.binU, S.keyMax); S.keyMax = 0; }
+        }
+        if (tid == 0) S.survCount = 0;
+        __syncthreads();
+    };
+    // Nearest-first view of the list (sort_big_kernel): the bin reads it 512 entries at a time and stops at the first
+    // position whose key - a lower bound of every later triangle's depth - is behind the bin's depth bound.
+    const bool sorted = hizOn && P.counters->bigSorted != 0;
+    const uint32_t* boxes = sorted ? P.bigBoxSorted : P.bigBox;
+    const uint32_t chunk = sorted ? 512u : 4u * TILE_THREADS;
     uint32_t cursor = 0;                                       // next entry of the tile-path list (uniform)
     while (cursor < nBig) {
+        if (sorted && cursor) {
+            // (uniform: every thread reads the same words after the barrier that closed the previous chunk)
+            const uint32_t bound = __ldg(P.bigBound + cursor);       // no later triangle is nearer than this
+            bool behind = bound > S.binU;
+            if (!behind) {
+                // not behind the bound yet: the bin may still get bounded by what the admitted triangles draw
+                const uint32_t haveSurv = S.survCount;
+                __syncthreads();
+                if (haveSurv) { flush_bin(haveSurv, true); behind = bound > S.binU; }
+            }
+            if (behind) break;
+        }
         // 1. candidates: a 4-byte bin box per triangle filters the list before any record is loaded
         for (;;) {
             // The loop decision must be the same for every thread: read the count, then a barrier, so no
             // thread can start appending (and change the count) before all threads have read it.
             const uint32_t have = S.candCount;
             __syncthreads();
-            if (!(cursor < nBig && have <= CAND_CAP - 4 * TILE_THREADS)) break;
+            if (!(cursor < nBig && have <= (sorted ? 0u : (uint32_t)(CAND_CAP - 4 * TILE_THREADS)))) break;
             const uint32_t i = cursor + 4u * tid;
             uint32_t hits = 0;
-            if (i < nBig) {
+            if (4u * tid < chunk && i < nBig) {
                 uint32_t box[4];
                 if (i + 3 < nBig) {
-                    const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(P.bigBox + i));
+                    const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(boxes + i));
                     box[0] = b4.x; box[1] = b4.y; box[2] = b4.z; box[3] = b4.w;
                 } else {
                     #pragma unroll
-                    for (int k = 0; k < 4; k++) box[k] = (i + k < nBig) ? __ldg(P.bigBox + i + k) : 0xFFu;   // x0=255 > x1=0: never matches
+                    for (int k = 0; k < 4; k++) box[k] = (i + k < nBig) ? __ldg(boxes + i + k) : 0xFFu;   // x0=255 > x1=0: never matches
                 }
                 hits = (bin_in_box(box[0], bx, by) ? 1u : 0u) | (bin_in_box(box[1], bx, by) ? 2u : 0u) |
                        (bin_in_box(box[2], bx, by) ? 4u : 0u) | (bin_in_box(box[3], bx, by) ? 8u : 0u);
@@ -1792,7 +1908,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                 for (int k = 0; k < 4; k++)
                     if (hits & (1u << k)) S.cand[base++] = i + k;
             }
-            cursor += 4u * TILE_THREADS;
+            cursor += chunk;
             __syncthreads();
         }
 #ifdef EDX_DEBUG_STATS
@@ -1810,7 +1926,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             bool rej, full; float zl, zh;
             // (threads past the end classify the last candidate again and drop the result: uniform control flow
             // keeps the record in registers)
-            load_big(P.big + S.cand[min(j, nCand - 1u)], r);
+            { const uint32_t pos = S.cand[min(j, nCand - 1u)]; load_big(P.big + (sorted ? __ldg(P.bigOrder + pos) : pos), r); }
             classify_rect(r, ox, oy, BIN, P.width, P.height, hiz, ms, hiz ? S.binU : 0xFFFFFFFFu, rej, full, zl, zh);
             rej = rej || j >= nCand;
             if (hiz) {
@@ -1827,31 +1943,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         //     NEAREST FIRST, in eight slabs of near depth with a raster flush after each: once the near triangles are
         //     drawn, the bin's (and in raster_survivors each tile's) stored depth culls the slabs behind them - again
         //     whatever order the list was appended in.
-        auto flush = [&](uint32_t haveSurv) {
-            if (tid == 0) atomicAdd(&P.counters->tilePairs, haveSurv);
-#ifdef EDX_DEBUG_STATS
-            long long tF = clock64(); nFlush++; nSurvTot += haveSurv;
-#endif
-            raster_survivors<MS>(P, S, ox, oy, hiz, offX, offY);
-            __syncthreads();
-#ifdef EDX_DEBUG_STATS
-            tFlush += clock64() - tF;
-#endif
-            if (hiz) {
-                // what is now stored in the bin bounds everything still to come
-                if (tx0 < P.width && ty0 < P.height) {
-                    unsigned long long kk[8];
-                    #pragma unroll
-                    for (int j = 0; j < 8; j++) kk[j] = S.keys[warp * 256 + j * 32 + lane];
-                    const uint32_t m = tile_key_max(kk, tx0, ty0, P.width, P.height);
-                    if (lane == 0) atomicMax(&S.keyMax, m);
-                }
-                __syncthreads();
-                if (tid == 0) { S.binU = min(S.binU, S.keyMax); S.keyMax = 0; }
-            }
-            if (tid == 0) S.survCount = 0;
-            __syncthreads();
-        };
+        auto flush = [&](uint32_t haveSurv) { flush_bin(haveSurv, hiz); };
         uint32_t nSlabs = 1, zNear = 0, zFar = 0xFFFFFFFEu;
         if (hiz) {
             const uint32_t U0 = S.binU;
@@ -1884,7 +1976,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                 if (lane == 0 && keepMask) at = atomicAdd(&S.survCount, (uint32_t)__popc(keepMask));     // one shared-memory atomic per warp
                 at = __shfl_sync(0xFFFFFFFFu, at, 0) + (uint32_t)__popc(keepMask & ((1u << lane) - 1u));
                 if (keep) {
-                    const int4* s2 = reinterpret_cast<const int4*>(P.big + S.cand[j]);
+                    const uint32_t pos = S.cand[j];
+                    const int4* s2 = reinterpret_cast<const int4*>(P.big + (sorted ? __ldg(P.bigOrder + pos) : pos));
                     int4* d2 = reinterpret_cast<int4*>(&S.surv[at]);
                     d2[0] = __ldg(s2); d2[1] = __ldg(s2 + 1); d2[2] = __ldg(s2 + 2); d2[3] = __ldg(s2 + 3);
                 }

@@ -61,6 +61,8 @@ struct edx_context {
     void* sinkColor = nullptr; void* sinkDepth = nullptr;       // edx_set_frame_sink: where the copy engine pushes each finished frame
     BigRec* big = nullptr; uint32_t bigCap = 0;
     uint32_t* bigBox = nullptr; uint32_t bigBoxCap = 0;
+    uint32_t* bigOrder = nullptr; uint32_t* bigKey = nullptr; uint32_t* bigBoxSorted = nullptr; uint32_t* bigBound = nullptr; uint32_t bigSortCap = 0;   // nearest-first view (sort_big_kernel)
+    int sortBig = 1;                         // edx_set_option("sort_big", 0 | 1)
     ClipItem* clipQueue = nullptr; uint32_t clipQueueCap = 0;
     ClipRec* clipRecs = nullptr; uint32_t clipRecCap = 0;
     Counters* counters = nullptr;
@@ -190,6 +192,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.tex = m->texDesc; P.texels = m->texels; P.texIds = m->texIds; P.nTex = m->nTex; P.texFilter = c->texFilter;
     P.keys = c->keys;
     P.big = c->big; P.bigCap = c->bigCap; P.bigBox = c->bigBox;
+    P.bigOrder = c->bigOrder; P.bigKey = c->bigKey; P.bigBoxSorted = c->bigBoxSorted; P.bigBound = c->bigBound;
     P.clipQueue = c->clipQueue; P.clipQueueCap = c->clipQueueCap;
     P.clipRecs = c->clipRecs; P.clipRecCap = c->clipRecCap;
     P.clipSlot = c->clipSlot;
@@ -203,6 +206,14 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     // initial queue sizes; grown on demand after a frame reports it needed more
     if (int r = grow(c, c->big, c->bigCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
     if (int r = grow(c, c->bigBox, c->bigBoxCap, c->bigCap)) return r;
+    if (!c->bigOrder) {                      // the sorted view never holds more than SORT_MAX entries
+        uint32_t cap = 0;
+        if (int r = grow(c, c->bigOrder, cap, SORT_MAX)) return r;
+        cap = 0; if (int r = grow(c, c->bigKey, cap, SORT_MAX)) return r;
+        cap = 0; if (int r = grow(c, c->bigBoxSorted, cap, SORT_MAX)) return r;
+        cap = 0; if (int r = grow(c, c->bigBound, cap, SORT_MAX)) return r;
+        c->bigSortCap = cap;
+    }
     if (int r = grow(c, c->mid, c->midCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
     if (int r = grow(c, c->clipQueue, c->clipQueueCap, std::max<uint64_t>(1u << 14, m->nTris / 32))) return r;
     if (int r = grow(c, c->clipRecs, c->clipRecCap, std::max<uint64_t>(1u << 16, m->nTris / 8))) return r;
@@ -269,6 +280,7 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     }
     if (m->nTris) add("clip_kernel", clip_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
     if (m->nTris && c->midMax > 0) add("mid_kernel", mid_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
+    if (m->nTris && c->sortBig && c->hiz && c->hierarchical) add("sort_big_kernel", sort_big_kernel, dim3(1), dim3(1024), 0, 0, 1);
     const dim3 leanGrid((c->binsX * c->binsY * 16 + 7) / 8);
     if (c->msaaLog2 == 0) {
         if (lean && !shaded && !c->captureIds) add("lean_resolve_kernel", lean_resolve_kernel<true>, leanGrid, dim3(256), 0, 1, 2);
@@ -573,7 +585,7 @@ void edx_destroy(edx_context* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     release_frame_buffers(c);
-    dev_free(c->big); dev_free(c->bigBox); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->clipSlot); dev_free(c->counters);
+    dev_free(c->big); dev_free(c->bigBox); dev_free(c->bigOrder); dev_free(c->bigKey); dev_free(c->bigBoxSorted); dev_free(c->bigBound); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->clipSlot); dev_free(c->counters);
     dev_free(c->workList); dev_free(c->vcFlag); dev_free(c->vrec); dev_free(c->mid);
     if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
     if (c->graph) cudaGraphDestroy(c->graph);
@@ -678,6 +690,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "small_max_clip")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max_clip in [0,64]"); c->smallMaxClip = value; return EDX_OK; }
     if (!strcmp(name, "cluster_cull")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "cluster_cull: 0 off, 1 auto, 2 always"); c->clusterCull = value; return EDX_OK; }
     if (!strcmp(name, "front_end")) { if (value < -1 || value > 2) return fail(c, EDX_ERR_INVALID, "front_end: -1 auto, 0 per-cluster CTAs, 1 cull + work list, 2 cull + per-vertex stage + work list"); c->frontEnd = value; return EDX_OK; }
+    if (!strcmp(name, "sort_big")) { c->sortBig = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "graphs")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "graphs: 0 never, 1 small meshes, 2 always"); c->useGraphs = value; return EDX_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
