@@ -43,6 +43,7 @@ WORKLOADS = {
     "C3": "C3: 2,000 screen-covering triangles, 3840x2160, Blinn-Phong, perspective-correct interpolation",
     "C4": "C4: 10,000,000-triangle displaced grid, 1920x1080, near/side-plane clipping, Blinn-Phong",
     "C5": "C5: 256 camera views of the C4 mesh (10,000,000 triangles), 1920x1080, view i on GPU i mod N, frames gathered to rank 0",
+    "M1": "M1 (stress, not a BASELINE config): 1,000,000 mid-size triangles (vertices over 32..128 px boxes), 1920x1080, depth only",
 }
 
 

@@ -1006,6 +1006,56 @@ int edx_get_derived_state(const edx_context* c, float mvp[16], float eye[3], flo
 void* edx_device_color(edx_context* c) { return c ? (c->extColor ? c->extColor : c->color) : nullptr; }
 void* edx_device_depth(edx_context* c) { return c ? (c->extDepth ? c->extDepth : c->depth) : nullptr; }
 
+int edx_device_count(void)
+{
+    int n = 0, ok = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ok++;
+    }
+    return ok;
+}
+
+int edx_enable_peer_access(edx_context* c, int peer)
+{
+    if (!c) return EDX_ERR_INVALID;
+    if (peer == c->device) return EDX_OK;
+    if (int r = bind(c)) return r;
+    int can = 0;
+    EDX_CUDA(c, cudaDeviceCanAccessPeer(&can, c->device, peer));
+    if (!can) return fail(c, EDX_ERR_UNSUPPORTED, "no peer access between the two devices");
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return EDX_OK; }
+    EDX_CUDA(c, e);
+    return EDX_OK;
+}
+
+int edx_device_alloc(edx_context* c, size_t bytes, void** out)
+{
+    if (!c || !out || !bytes) return fail(c, EDX_ERR_INVALID, "bad argument");
+    if (int r = bind(c)) return r;
+    EDX_CUDA(c, cudaMalloc(out, bytes));
+    return EDX_OK;
+}
+
+int edx_device_free(edx_context* c, void* p)
+{
+    if (!c) return EDX_ERR_INVALID;
+    if (int r = bind(c)) return r;
+    EDX_CUDA(c, cudaFree(p));
+    return EDX_OK;
+}
+
+int edx_read_device(edx_context* c, void* dst, const void* src, size_t bytes)
+{
+    if (!c || !dst || !src) return fail(c, EDX_ERR_INVALID, "bad argument");
+    if (int r = bind(c)) return r;
+    EDX_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    return EDX_OK;
+}
+
 int edx_set_frame_sink(edx_context* c, void* color, void* depth)
 {
     if (!c) return EDX_ERR_INVALID;

@@ -64,10 +64,11 @@ def config1(width=1280, height=720, slices=100, stacks=100):
 # ---------------------------------------------------------------------------------------------
 # C2: random small triangles, depth only, fixed order
 # ---------------------------------------------------------------------------------------------
-def config2(width=1920, height=1080, num_tris=1_000_000, max_px=4.0, seed=0xEDD5A57E2):
+def config2(width=1920, height=1080, num_tris=1_000_000, max_px=4.0, seed=0xEDD5A57E2, min_px=None, name="C2_small_tris"):
     rng = np.random.default_rng(seed)
     centre = rng.random((num_tris, 1, 2)) * np.array([width, height])
-    off = (rng.random((num_tris, 3, 2)) - 0.5) * max_px
+    size = max_px if min_px is None else min_px + (max_px - min_px) * rng.random((num_tris, 1, 1))
+    off = (rng.random((num_tris, 3, 2)) - 0.5) * size
     xy = centre + off                                   # raster-space pixels, y down
     z = 0.1 + 0.8 * rng.random((num_tris, 3))
     # force the orientation the reference keeps (det > 0, RasterTriangle.h:49-51)
@@ -84,9 +85,16 @@ def config2(width=1920, height=1080, num_tris=1_000_000, max_px=4.0, seed=0xEDD5
     nrm = np.tile(np.array([0.0, 0.0, -1.0]), (pos.shape[0], 1))
     uv = rng.random((pos.shape[0], 2))
     idx = np.arange(num_tris * 3, dtype=np.uint32).reshape(-1, 3)
-    return Scene(name="C2_small_tris", width=width, height=height, vertices=_pack(pos, nrm, uv), indices=idx,
+    return Scene(name=name, width=width, height=height, vertices=_pack(pos, nrm, uv), indices=idx,
                  mv=cam.identity(), proj=cam.identity(), raster=cam.raster_matrix(width, height),
                  shader=SHADER_DEPTH_ONLY)
+
+
+def stress_m1(width=1920, height=1080, num_tris=1_000_000, seed=0x111):
+    """M1 - not a BASELINE config: a stress case for the routing of MID-SIZE triangles. One million
+    triangles whose vertices scatter over boxes of 32..128 px, depth only: too large for the per-thread path, and with
+    round 1's routing all of them landed on the tile path, where every 64x64 bin swept the whole list."""
+    return config2(width, height, num_tris, max_px=128.0, seed=seed, min_px=32.0, name="M1_mid_tris")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -207,6 +215,8 @@ def by_name(name, scale=1.0):
     if name == "C4":
         s = math.sqrt(scale)
         return config4(quads_x=max(2, int(2500 * s)), quads_z=max(2, int(2000 * s)))
+    if name == "M1":
+        return stress_m1(num_tris=max(1, int(1_000_000 * scale)))
     raise ValueError(name)
 
 

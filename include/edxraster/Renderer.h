@@ -558,11 +558,82 @@ public:
     const _byte* GetBackBuffer(size_t ticket) { return InRing(ticket) ? Lane(ticket).GetBackBuffer() : nullptr; }
     bool GetDepthBuffer(size_t ticket, float* out) { return InRing(ticket) && Lane(ticket).GetDepthBuffer(out); }
     Renderer& Lane(size_t ticket) { return *mLanes[ticket % mLanes.size()]; }
+    Renderer& NextLane() { return *mLanes[mNext % mLanes.size()]; }      // the lane the next Submit renders on
     size_t Depth() const { return mLanes.size(); }
     int LastStatus() const { for (auto& r : mLanes) if (r->LastStatus() != EDX_OK) return r->LastStatus(); return EDX_OK; }
 private:
     std::vector<std::unique_ptr<Renderer>> mLanes;
     size_t mNext = 0;
+};
+
+// Frame-parallel rendering on the GPUs of one box (BASELINE config 5): the C++ counterpart of
+// RealtimeViewer's per-frame loop (Main.cpp:71-75) run once per GPU. One FrameRing per GPU, view i on GPU i mod N;
+// every finished colour buffer is pushed by the copy engine straight into the root GPU's frame store over NVLink
+// (edx_set_frame_sink) - no collective, no host copy per frame. One Mesh per GPU (a Mesh owns one device copy).
+struct ViewTransform { Matrix modelView, proj, toRaster; };
+
+class FrameFarm {
+public:
+    explicit FrameFarm(int gpus = 0, int depth = 3)
+    {
+        const int have = edx_device_count();
+        mGpus = gpus <= 0 || gpus > have ? have : gpus;
+        for (int g = 0; g < mGpus; g++) mRings.emplace_back(new FrameRing(depth, g));
+        for (int g = 0; g < mGpus; g++) mMeshes.emplace_back(new Mesh);
+    }
+    ~FrameFarm() { ReleaseStore(); }
+    int Gpus() const { return mGpus; }
+    void Initialize(uint w, uint h)
+    {
+        mW = w; mH = h;
+        for (auto& r : mRings) r->Initialize(w, h);
+        // every GPU may write the root's memory
+        for (int g = 1; g < mGpus; g++)
+            for (size_t l = 0; l < mRings[g]->Depth(); l++)
+                if (edx_enable_peer_access(mRings[g]->Lane(l).Handle(), 0) != EDX_OK) mStatus = EDX_ERR_UNSUPPORTED;
+    }
+    void SetPixelShader(PixelShaderKind k) { for (auto& r : mRings) r->SetPixelShader(k); }
+    void SetTextureFilter(TextureFilter f) { for (auto& r : mRings) r->SetTextureFilter(f); }
+    // build(mesh) fills the Mesh of one GPU; called once per GPU
+    template <class Build> void LoadMeshes(Build build) { for (auto& m : mMeshes) build(*m); }
+    // Renders every view; returns false on error. Frames stay in the root GPU's store until the next Render.
+    bool Render(const std::vector<ViewTransform>& views)
+    {
+        if (mGpus == 0 || mStatus != EDX_OK) return false;
+        const size_t frameBytes = (size_t)mW * mH * 4;
+        if (views.size() > mStoreFrames) {
+            ReleaseStore();
+            if (edx_device_alloc(Root(), views.size() * frameBytes, &mStore) != EDX_OK) return false;
+            mStoreFrames = views.size();
+        }
+        for (size_t i = 0; i < views.size(); i++) {
+            FrameRing& ring = *mRings[i % mGpus];
+            Renderer& lane = ring.NextLane();
+            lane.SetFrameSink((_byte*)mStore + i * frameBytes, nullptr);
+            ring.Submit(*mMeshes[i % mGpus], views[i].modelView, views[i].proj, views[i].toRaster);
+        }
+        for (auto& r : mRings) { r->Synchronize(); if (r->LastStatus() != EDX_OK) return false; }
+        mFrames = views.size();
+        return true;
+    }
+    // frame `view` of the last Render, copied from the root GPU to `out` (w*h*4 bytes, RGBA8 bottom-up)
+    bool GetFrame(size_t view, _byte* out) const
+    {
+        if (view >= mFrames) return false;
+        const size_t frameBytes = (size_t)mW * mH * 4;
+        return edx_read_device(Root(), out, (const _byte*)mStore + view * frameBytes, frameBytes) == EDX_OK;
+    }
+    FrameRing& Ring(int gpu) { return *mRings[gpu]; }
+    Mesh& MeshOf(int gpu) { return *mMeshes[gpu]; }
+private:
+    edx_context* Root() const { return mRings[0]->Lane(0).Handle(); }
+    void ReleaseStore() { if (mStore) { edx_device_free(Root(), mStore); mStore = nullptr; mStoreFrames = 0; } }
+    int mGpus = 0, mStatus = EDX_OK;
+    uint mW = 0, mH = 0;
+    std::vector<std::unique_ptr<FrameRing>> mRings;
+    std::vector<std::unique_ptr<Mesh>> mMeshes;
+    void* mStore = nullptr;
+    size_t mStoreFrames = 0, mFrames = 0;
 };
 
 inline void Mesh::ReleaseDevice() const

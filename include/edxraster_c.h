@@ -173,6 +173,13 @@ int edx_set_render_target(edx_context* ctx, void* device_color, void* device_dep
  * symmetric-memory mapping) - typically this rank's slot of the root GPU's frame store. NULL, NULL switches it off.
  * Single-sample only. The caller owns the protocol that tells the root a slot has landed. */
 int edx_set_frame_sink(edx_context* ctx, void* remote_color, void* remote_depth);
+/* Helpers for a frame farm inside ONE process (one context per GPU; include/edxraster/Renderer.h FrameFarm). They
+ * only wrap what a caller without the CUDA runtime needs around edx_set_frame_sink: */
+int edx_device_count(void);                                            /* B200 devices visible to the process */
+int edx_enable_peer_access(edx_context* ctx, int peer_device);         /* ctx's GPU may write peer_device's memory (NVLink) */
+int edx_device_alloc(edx_context* ctx, size_t bytes, void** out);      /* device memory on ctx's GPU, e.g. the root's frame store */
+int edx_device_free(edx_context* ctx, void* p);
+int edx_read_device(edx_context* ctx, void* host_dst, const void* device_src, size_t bytes);   /* stream-ordered D2H on ctx's stream, then synchronise */
 /* Sort-first split of ONE frame over several contexts / GPUs: this context rasterises, resolves
  * and writes only the 64x64-pixel bins b (row-major) with b % parts == part; the rest of its frame buffer is left
  * untouched. Every context still runs the geometry stages on the whole mesh. parts = 1 restores the full frame. */

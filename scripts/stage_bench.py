@@ -26,6 +26,8 @@ for w in a.workloads.split(","):
             r.SetOption(k, int(v))
         m = r.CreateMesh(sc.vertices, sc.indices)
         frames = 30 if sc.num_tris < 5_000_000 else 10
+        r.RenderMesh(m)
+        r.Synchronize()                  # the first frame sizes the internal queues (grow + re-run if it overflowed)
         for _ in range(3):
             r.RenderMesh(m)
         r.Synchronize()
@@ -50,6 +52,10 @@ for w in a.workloads.split(","):
             ring.SetOption(k, int(v))
         xf = R.PackedTransform(sc.mv, sc.proj, sc.raster)
         n = frames * 4
+        for lane in ring.lanes:          # size each lane's queues before frames pile up unsynchronised
+            lane.SetTransform(xf)
+            lane.RenderMesh(m)
+            lane.Synchronize()
         for rep in range(2):
             ring.Synchronize()
             t = time.perf_counter()

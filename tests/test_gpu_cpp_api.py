@@ -200,3 +200,15 @@ def test_obj_materials_become_texture_slots(tmp_path):
     pix = np.frombuffer(data, np.uint8, w * h * 3, off).reshape(h, w, 3)[..., ::-1]
     assert np.abs(pix.astype(np.int32) - ref[..., :3].astype(np.int32)).max() <= 1
     assert len(np.unique(pix.reshape(-1, 3), axis=0)) > 500
+
+
+def test_frame_farm_through_the_cpp_api():
+    # examples/farm_viewer: views dealt over every GPU of the box (one on a single-GPU box), three frames in flight per
+    # GPU, each finished frame pushed into GPU 0's store by the copy engine (edx_set_frame_sink); the program compares
+    # every farmed frame with the single-Renderer frame of the same view and exits 0 iff all are identical
+    exe = os.path.join(ROOT, "examples", "farm_viewer")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "examples")])
+    out = subprocess.run([exe, "13", "0", "120"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "0 of 13 farmed frames differ" in out.stdout

@@ -668,3 +668,15 @@ def test_streamed_meshes_on_three_contexts_match_the_oracle():
     for _, r, mesh in lanes:
         mesh.Release()
         r.close()
+
+
+def test_m1_mid_size_stress_every_routing():
+    # M1 (bench.py --workload M1, reduced): triangles of 32..128 px. Default routing sends most to the warp-per-triangle
+    # path; mid_max = 0 is round 1's routing (everything on the tile path, every bin sweeps the whole list).
+    sc = scenes.stress_m1(width=1280, height=720, num_tris=60000)
+    ref = parity.render_oracle(sc)
+    for opts in ({}, {"mid_max": 0, "small_max": 32}, {"mid_max": 128}, {"sort_big": 0}):
+        got = parity.render_gpu(sc, options=opts, stages=False)
+        rep = parity.compare(ref, got)
+        assert parity.is_parity(rep), (opts, rep)
+    assert got["stats"]["mid_tris"] + got["stats"]["binned_tris"] > 50000
