@@ -7,6 +7,9 @@ def kname(n):
     n = re.sub(r"^void\s+", "", n).split("(")[0]
     return n.replace("<0>", "").replace("<(bool)0>", "").replace("<1>", "_msaa").replace("<(bool)1>", "_msaa")
 
+FRAME_KERNELS = ("geom_kernel", "cull_kernel", "vertex_kernel", "geom_list_kernel", "clip_kernel", "mid_kernel", "sort_big_kernel",
+                 "tile_kernel", "shade_kernel", "msaa_resolve_kernel", "frame_end_kernel")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 out = os.path.join(ROOT, "profiles")
@@ -25,7 +28,7 @@ for w in ("C1", "C2", "C3", "C4"):
     per = {}
     for r in rows[1:]:
         per.setdefault(kname(r[ki]), []).append(float(r[vi].replace(",", "")))
-    frame = {k: sum(v[-3:]) / len(v[-3:]) for k, v in per.items() if k in ("geom_kernel", "clip_kernel", "tile_kernel", "frame_end_kernel")}
+    frame = {k: sum(v[-3:]) / len(v[-3:]) for k, v in per.items() if k.split("_msaa")[0] in FRAME_KERNELS}
     tot = sum(frame.values()) or 1
     lines += ["## %s launch list (ns per launch, mean of last 3 frames)" % w, "", "| kernel | ns | share of frame |", "|---|---|---|"]
     for k, v in frame.items():
