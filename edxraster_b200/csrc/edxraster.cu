@@ -45,6 +45,7 @@ struct edx_context {
     int msaaLog2 = 0, texFilter = 2, hierarchical = 1, captureIds = 0, profiling = 0;
     int smallMax = 8, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1, part = 0, parts = 1;
     MidRec* mid = nullptr; uint32_t midCap = 0;
+    int midCtasPerSm = 16;
     int midMax = 64;                         // boxes from smallMax up to this go to mid_kernel (one warp per triangle); 0 = none
     int frontEnd = -1;                       // -1 auto, 0 geom_kernel, 1 cull + list, 2 cull + per-vertex stage + list (FrameParams::frontEnd)
     int frontEndUsed = 0;
@@ -279,7 +280,9 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
         else add("geom_list_kernel", geom_list_kernel<false>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0, 0, 0);
     }
     if (m->nTris) add("clip_kernel", clip_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
-    if (m->nTris && c->midMax > 0) add("mid_kernel", mid_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
+    // one warp per mid-size triangle: as many warps as the chip holds (148 SMs x 16 CTAs x 4 warps) so that a queue of
+    // tens of thousands is a couple of triangles per warp, not a serial walk whose every step waits on a record load
+    if (m->nTris && c->midMax > 0) add("mid_kernel", mid_kernel, dim3(148 * (unsigned)c->midCtasPerSm), dim3(128), 0, 0, 1);
     if (m->nTris && c->sortBig && c->hiz && c->hierarchical) add("sort_big_kernel", sort_big_kernel, dim3(1), dim3(1024), 0, 0, 1);
     const dim3 leanGrid((c->binsX * c->binsY * 16 + 7) / 8);
     if (c->msaaLog2 == 0) {
@@ -686,6 +689,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
 {
     if (!c || !name) return EDX_ERR_INVALID;
     if (!strcmp(name, "small_max")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max in [0,64]"); c->smallMax = value; return EDX_OK; }
+    if (!strcmp(name, "mid_ctas")) { if (value < 1 || value > 32) return fail(c, EDX_ERR_INVALID, "mid_ctas in [1,32]"); c->midCtasPerSm = value; return EDX_OK; }
     if (!strcmp(name, "mid_max")) { if (value < 0 || value > 1024) return fail(c, EDX_ERR_INVALID, "mid_max in [0,1024]"); c->midMax = value; return EDX_OK; }
     if (!strcmp(name, "small_max_clip")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max_clip in [0,64]"); c->smallMaxClip = value; return EDX_OK; }
     if (!strcmp(name, "cluster_cull")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "cluster_cull: 0 off, 1 auto, 2 always"); c->clusterCull = value; return EDX_OK; }
