@@ -292,6 +292,7 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+OPTIONS = []
 NVLINK_INGRESS_GBS = 733.0      # one B200's NVLink receive rate as measured in round 1 (7 senders, copy engine); nominal 900
 
 
@@ -335,6 +336,9 @@ class Farm:
             lr.Initialize(W, H)
             lr.SetTransform(sc.mv, sc.proj, sc.raster)
             lr.SetPixelShader(sc.shader)
+            for kv in OPTIONS:                    # --opt name=value: tuning knobs for experiments (none changes a pixel)
+                k, v = kv.split("=")
+                lr.SetOption(k, int(v))
             self.lanes.append((ls, lr))
         self.r = self.lanes[0][1]
         views = sc.get("views")
@@ -811,9 +815,11 @@ def main():
     ap.add_argument("--gather", default="ce", choices=["nccl", "ce", "stores", "none"], help="how finished frames reach rank 0 at N > 1")
     ap.add_argument("--in-flight", type=int, default=3, help="independent frames in flight per GPU (1 = one frame at a time)")
     ap.add_argument("--scale", type=float, default=1.0, help="triangle-count scale (debug only; 1.0 = BASELINE size)")
+    ap.add_argument("--opt", action="append", default=[], help="experiment: edx_set_option name=value on every context of the headline run")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary C1/C3/C4 measurements")
     ap.add_argument("--peer-stores", action="store_true", help="N > 1: let every rank's resolve kernel store its pixels straight into rank 0's (symmetric) memory over NVLink instead of the NCCL gather; measured slower (32-byte row segments): 88 vs 73 us/step at N = 4")
     args = ap.parse_args()
+    OPTIONS.extend(args.opt)
     if args.impl == "reference":
         return reference_arm(args)
     if args.gpus > 1 and "RANK" not in os.environ:

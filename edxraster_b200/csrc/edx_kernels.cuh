@@ -292,7 +292,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                 r0 += sC0; r1 += sC1; r2 += sC2;
             }
         }
-    } else if (x1 - x0 < P.midMax && y1 - y0 < P.midMax) {
+    } else if (P.midLaunched && x1 - x0 < P.midMax && y1 - y0 < P.midMax) {
         // Mid-size triangle: a lone thread would serialise hundreds of pixel tests (and stall its warp), a whole-bin
         // sweep is too heavy a machine for it. mid_kernel gives it one warp.
         const uint32_t at = warp_append(&P.counters->nMid);
@@ -303,6 +303,7 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
             dst[2] = make_int4(__float_as_int(z2), __float_as_int(s.invDet), (int)prim, 0);
         }
     } else {
+        if (!P.midLaunched && x1 - x0 < P.midMax && y1 - y0 < P.midMax) atomicAdd(&P.counters->nMidDiverted, 1u);   // tells the host to launch mid_kernel again
         const uint32_t at = warp_append(&P.counters->nBig);
         if (at < P.bigCap) {
             // Depth plane over pixel centres (sub-pixel 16*p + 8), fitted in fp32 together with a bound of
@@ -1672,7 +1673,7 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     // every load first (nine independent L2 reads in flight), then the stores from registers; no fence: the host
     // reads the pinned copy only after the stream has completed this kernel
     volatile Counters* d = P.counters;
-    const uint32_t nBig = d->nBig, nClip1 = d->nClipQueue, nClipN = d->nClipMulti, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid;
+    const uint32_t nBig = d->nBig, nClip1 = d->nClipQueue, nClipN = d->nClipMulti, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid, nMidDiverted = d->nMidDiverted, serial = d->frameSerial + 1u;
     // the clip queue is split in two halves (clip_kernel): publish a demand that exceeds the capacity exactly when a half overflowed
     const uint32_t halfQ = P.clipQueueCap / 2u;
     const uint32_t nClipQueue = (nClip1 > halfQ || nClipN > P.clipQueueCap - halfQ) ? 2u * max(nClip1, nClipN) + 2u : nClip1 + nClipN;
@@ -1682,10 +1683,10 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     for (int i = 0; i < 8; i++) { P.hostCounters->dbg[i] = P.counters->dbg[i]; P.counters->dbg[i] = 0; }
 #endif
     if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap || nMid > P.midCap) overFrames++;
-    d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0;
+    d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0; d->nMidDiverted = 0; d->bigSorted = 0; d->frameSerial = serial;
     d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs; d->maxMid = maxMid;
     volatile Counters* h = P.hostCounters;
-    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid;
+    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid; h->nMidDiverted = nMidDiverted; h->frameSerial = serial;
     h->overFrames = overFrames; h->maxBig = maxBig; h->maxClipQueue = maxClipQueue; h->maxClipRecs = maxClipRecs;
 }
 

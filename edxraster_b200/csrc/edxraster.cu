@@ -46,6 +46,8 @@ struct edx_context {
     int smallMax = 8, smallMaxClip = 8, hiz = 1, fuseClip = 0, pdl = 1, clusterCull = 1, part = 0, parts = 1;
     MidRec* mid = nullptr; uint32_t midCap = 0;
     int midCtasPerSm = 16;
+    uint32_t hintTris = 0, hintVerts = 0;    // size of the previously enqueued mesh: the counters its frame published hint what a frame of an equal-sized mesh needs
+    int skipIdle = 1;                        // edx_set_option("skip_idle", 0 | 1): leave out kernels the previous frame of the same mesh had no work for
     int midMax = 64;                         // boxes from smallMax up to this go to mid_kernel (one warp per triangle); 0 = none
     int frontEnd = -1;                       // -1 auto, 0 geom_kernel, 1 cull + list, 2 cull + per-vertex stage + list (FrameParams::frontEnd)
     int frontEndUsed = 0;
@@ -279,11 +281,27 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
         if (fe == 2) add("geom_list_kernel", geom_list_kernel<true>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0, 0, 0);
         else add("geom_list_kernel", geom_list_kernel<false>, dim3(std::min(nTC, 148u * 5u)), dim3(256), 0, 0, 0);
     }
+    // Two kernels of the chain are often idle: mid_kernel (no mid-size triangles: C2) and sort_big_kernel (short or
+    // empty tile-path list: C1, C2). An idle kernel still costs its launch and a grid of CTAs that read one counter and
+    // exit - 2.5 us per C2 frame. The counters the previous frame of this context published (pinned host memory; no
+    // synchronisation, a stale value is as good) say whether a mesh of the same size had work for them; if not they are left out.
+    // That is always safe: without mid_kernel a mid-size triangle takes the tile path (and counts itself, so the next
+    // frame has the kernel again), without the sort the tile kernel reads the list as appended.
+    bool launchMid = c->midMax > 0, launchSort = c->sortBig && c->hiz && c->hierarchical;
+    if (c->skipIdle && c->hintTris == m->nTris && c->hintVerts == m->nVerts && !dumpBuf) {
+        const volatile Counters* h = c->hostCounters;
+        if (h->frameSerial != 0) {
+            launchMid = launchMid && (h->nMid != 0 || h->nMidDiverted != 0);
+            launchSort = launchSort && h->nBig >= (uint32_t)SORT_MIN;
+        }
+    }
+    c->hintTris = m->nTris; c->hintVerts = m->nVerts;
+    P.midLaunched = launchMid ? 1 : 0; T.midLaunched = P.midLaunched;
     if (m->nTris) add("clip_kernel", clip_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
     // one warp per mid-size triangle: as many warps as the chip holds (148 SMs x 16 CTAs x 4 warps) so that a queue of
     // tens of thousands is a couple of triangles per warp, not a serial walk whose every step waits on a record load
-    if (m->nTris && c->midMax > 0) add("mid_kernel", mid_kernel, dim3(148 * (unsigned)c->midCtasPerSm), dim3(128), 0, 0, 1);
-    if (m->nTris && c->sortBig && c->hiz && c->hierarchical) add("sort_big_kernel", sort_big_kernel, dim3(1), dim3(1024), 0, 0, 1);
+    if (m->nTris && launchMid) add("mid_kernel", mid_kernel, dim3(148 * (unsigned)c->midCtasPerSm), dim3(128), 0, 0, 1);
+    if (m->nTris && launchSort) add("sort_big_kernel", sort_big_kernel, dim3(1), dim3(1024), 0, 0, 1);
     const dim3 leanGrid((c->binsX * c->binsY * 16 + 7) / 8);
     if (c->msaaLog2 == 0) {
         if (lean && !shaded && !c->captureIds) add("lean_resolve_kernel", lean_resolve_kernel<true>, leanGrid, dim3(256), 0, 1, 2);
@@ -694,6 +712,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "small_max_clip")) { if (value < 0 || value > 64) return fail(c, EDX_ERR_INVALID, "small_max_clip in [0,64]"); c->smallMaxClip = value; return EDX_OK; }
     if (!strcmp(name, "cluster_cull")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "cluster_cull: 0 off, 1 auto, 2 always"); c->clusterCull = value; return EDX_OK; }
     if (!strcmp(name, "front_end")) { if (value < -1 || value > 2) return fail(c, EDX_ERR_INVALID, "front_end: -1 auto, 0 per-cluster CTAs, 1 cull + work list, 2 cull + per-vertex stage + work list"); c->frontEnd = value; return EDX_OK; }
+    if (!strcmp(name, "skip_idle")) { c->skipIdle = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "sort_big")) { c->sortBig = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "graphs")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "graphs: 0 never, 1 small meshes, 2 always"); c->useGraphs = value; return EDX_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }

@@ -680,3 +680,31 @@ def test_m1_mid_size_stress_every_routing():
         rep = parity.compare(ref, got)
         assert parity.is_parity(rep), (opts, rep)
     assert got["stats"]["mid_tris"] + got["stats"]["binned_tris"] > 50000
+
+
+def test_idle_kernels_are_left_out_safely():
+    # mid_kernel / sort_big_kernel are left out of a frame when the previous frame of the same mesh had no work for them
+    # (skip_idle). Same mesh, three views: far away (every triangle tiny), close up (mid-size and large triangles appear in
+    # a frame that has no mid_kernel: they must take the tile path), close up again (mid_kernel is back). All three exact.
+    import copy
+    from edxraster_b200 import camera as cam, renderer as R
+    base = scenes.config1(width=640, height=360, slices=80, stacks=80)
+    r = R.Renderer(0)
+    r.Initialize(base.width, base.height)
+    r.SetCaptureIds(True)
+    r.SetPixelShader(1)
+    m = r.CreateMesh(base.vertices, base.indices)
+    launches = []
+    for eye_z in (-60.0, -60.0, -1.6, -1.6, -1.6):
+        c = cam.Camera((0.0, 0.0, eye_z), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), base.width, base.height, 65.0, 0.01, 100.0)
+        sc = copy.copy(base)
+        sc.mv, sc.proj, sc.raster = c.view, c.proj, c.raster
+        r.SetTransform(sc.mv, sc.proj, sc.raster)
+        r.RenderMesh(m)
+        got = {"color": r.GetBackBuffer().copy(), "depth": r.GetDepthBuffer(), "winner": r.GetWinnerIds(), "derived": r.DerivedState()}
+        launches.append(r.LastLaunchList())
+        rep = parity.compare(parity.render_oracle(sc), got)
+        assert parity.is_parity(rep), (eye_z, rep)
+    assert "mid_kernel" in launches[0] and "mid_kernel" not in launches[1]       # frame 0 had no mid-size triangle
+    assert "mid_kernel" not in launches[2] and "mid_kernel" in launches[3]       # frame 2 diverted some: back in frame 3
+    r.close()
