@@ -42,7 +42,7 @@ class TextureDesc(C.Structure):         # edx_texture_desc
 class Stats(C.Structure):
     _fields_ = [("submitted_tris", C.c_uint64), ("clipped_tris", C.c_uint64), ("binned_tris", C.c_uint64),
                 ("clip_records", C.c_uint64), ("regrow_count", C.c_uint32), ("tile_pairs", C.c_uint32),
-                ("mid_tris", C.c_uint64), ("stage_ms", C.c_float * 8)]
+                ("mid_tris", C.c_uint64), ("bin_pairs", C.c_uint64), ("stage_ms", C.c_float * 8)]
 
 
 _lib = None

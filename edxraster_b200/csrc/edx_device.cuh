@@ -24,6 +24,7 @@ constexpr int TILE_THREADS = TILES_PER_BIN * 32;                   // 512
 constexpr int SURV_CAP = 640;            // per-bin survivor list held in shared memory (flushed to the rasteriser when it passes SURV_CAP - 512)
 constexpr int CAND_CAP = 4096;           // per-bin candidate indices (bin-box filter hits) held in shared memory
 constexpr int SORT_MIN = 1024, SORT_MAX = 65536;   // tile-path lists of this length are put in nearest-first order (sort_big_kernel)
+constexpr int BIN_LEVELS = 16;           // depth levels a bin's list is ordered by (nearest first), uniform over the frame's key range
 constexpr int HIZ_MIN_CAND = 48;         // below this many candidates a bin skips hierarchical Z
 
 constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
@@ -87,6 +88,9 @@ struct Counters {
     uint32_t nClipMulti;     // straddlers of several planes (back half of the clip queue; nClipQueue counts the single-plane front half)
     uint32_t nWork;          // list front end: triangle clusters that survived cull_kernel this frame
     uint32_t ticket;         // list front end: work items handed out beyond the first gridDim.x
+    // per-bin lists of the tile path (bin_*_kernel): valid this frame, range of the depth keys, (triangle, bin) pairs wanted
+    uint32_t binned, binKeyMin, binKeyMax, nBinPairs;      // (binKeyMin is kept complemented: zero is its identity)
+    unsigned long long binPairs64;
     unsigned long long dbg[8];   // EDX_DEBUG_STATS builds: summed per-CTA cycle counts of the tile kernel's phases
 };
 
@@ -143,6 +147,12 @@ struct FrameParams {
     // nearest-first view of the tile-path list (sort_big_kernel): position -> record index, bin box, and a lower bound of
     // the depth any triangle at or after the position can produce (bigKey: scratch, keys in list order)
     uint32_t* bigOrder; uint32_t* bigKey; uint32_t* bigBoxSorted; uint32_t* bigBound;
+    // Per-bin lists of the tile path for LONG lists (a7: Renderer.cpp:162-229 bins every triangle into the tiles its box
+    // overlaps): count -> exclusive scan -> scatter over (bin, depth level); binCursor[bin * BIN_LEVELS + level] is the END
+    // of that run of binList after the scatter (= the start of the next run), binKey the depth key of every list entry.
+    uint32_t* binCursor; uint32_t* binList; uint32_t* binKey; uint32_t binListCap;
+    int binMin;                          // lists at least this long are binned (0 = never)
+    int binForce;                        // tests: bin even where the shared list would be read as cheaply
     ClipItem* clipQueue; uint32_t clipQueueCap;
     ClipRec* clipRecs; uint32_t clipRecCap;
     uint32_t* clipSlot;                  // per submitted triangle: first ClipRec of its polygon

@@ -1513,6 +1513,110 @@ __global__ void __launch_bounds__(1024) sort_big_kernel(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-bin lists for LONG tile-path lists (stage a7: Renderer::TiledRasterization bins every triangle into the tiles
+// its bounding box overlaps, Renderer.cpp:162-229). tile_kernel's bins otherwise all read the whole list (a 4-byte box
+// per entry): fine for a few thousand large triangles, quadratic for hundreds of thousands. Four small kernels,
+// launched only when the previous frame of an equal-sized mesh had such a list and doing nothing unless this frame's
+// is at least P.binMin long:
+//   bin_keys_kernel     depth key of every entry (as sort_big_kernel's), their range; zeroes the counters
+//   bin_fill_kernel<0>  count per (bin, depth level): level = position of the key in the frame's key range, 16 levels
+//   bin_scan_kernel     exclusive scan of the counts -> first slot of every (bin, level) run; decides `binned`
+//   bin_fill_kernel<1>  scatter: list entry i goes to the run of every bin of its box, at its level
+// A bin's list is then the concatenation of its 16 runs, NEAREST LEVEL FIRST, so what sort_big_kernel's order gives
+// short lists holds here too: tile_kernel reads the bin's list a few thousand entries at a time and stops at the first
+// level that lies behind the bin's depth bound. Order inside a run is whatever the atomics made it - the frame does
+// not depend on it (the visibility key does the ordering), only on the set.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool bin_wanted(const FrameParams& P, uint32_t n) { return P.binMin > 0 && n >= (uint32_t)P.binMin; }
+__device__ __forceinline__ uint32_t bin_level(uint32_t k, uint32_t kmin, unsigned long long range)
+{
+    return (uint32_t)(((unsigned long long)(k - kmin) * BIN_LEVELS) / range);
+}
+
+__global__ void __launch_bounds__(256) bin_keys_kernel(const __grid_constant__ FrameParams P)
+{
+    cudaGridDependencySynchronize();
+    const uint32_t n = min(P.counters->nBig, P.bigCap);
+    if (!bin_wanted(P, n)) return;
+    const uint32_t stride = gridDim.x * 256u, g = blockIdx.x * 256u + threadIdx.x;
+    const uint32_t nRuns = (uint32_t)(P.binsX * P.binsY) * BIN_LEVELS;
+    for (uint32_t i = g; i < nRuns; i += stride) P.binCursor[i] = 0;
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    for (uint32_t i = g; i < n; i += stride) { const uint32_t k = big_sort_key(P.big + i); P.binKey[i] = k; lo = min(lo, k); hi = max(hi, k); }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo); hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    // (the minimum is kept complemented so that the counters' zero state is its identity)
+    if ((threadIdx.x & 31u) == 0 && lo <= hi) { atomicMax(&P.counters->binKeyMin, ~lo); atomicMax(&P.counters->binKeyMax, hi); }
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ FrameParams P)
+{
+    cudaGridDependencySynchronize();
+    const uint32_t n = min(P.counters->nBig, P.bigCap);
+    if (!bin_wanted(P, n)) return;
+    if (SCATTER && P.counters->binned == 0) return;
+    const uint32_t kmin = ~P.counters->binKeyMin;
+    const unsigned long long range = (unsigned long long)(P.counters->binKeyMax - kmin) + 1ull;
+    const uint32_t stride = gridDim.x * 256u;
+    unsigned long long pairs = 0;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += stride) {
+        const uint32_t box = __ldg(P.bigBox + i);
+        const uint32_t lvl = bin_level(P.binKey[i], kmin, range);
+        const uint32_t x0 = box & 255u, x1 = min((box >> 8) & 255u, (uint32_t)P.binsX - 1u), y0 = (box >> 16) & 255u, y1 = min(box >> 24, (uint32_t)P.binsY - 1u);
+        if (x0 > x1 || y0 > y1) continue;
+        pairs += (unsigned long long)(x1 - x0 + 1u) * (y1 - y0 + 1u);
+        for (uint32_t y = y0; y <= y1; y++)
+            for (uint32_t x = x0; x <= x1; x++) {
+                uint32_t* run = P.binCursor + (y * (uint32_t)P.binsX + x) * BIN_LEVELS + lvl;
+                if (SCATTER) P.binList[atomicAdd(run, 1u)] = i;
+                else atomicAdd(run, 1u);
+            }
+    }
+    if (!SCATTER) {
+        // the pair total in 64 bits (the 32-bit counts of a frame of a million screen-sized triangles would wrap)
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
+        if ((threadIdx.x & 31u) == 0 && pairs) atomicAdd(&P.counters->binPairs64, pairs);
+    }
+}
+
+__global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ FrameParams P)
+{
+    __shared__ uint32_t sWarp[32];
+    cudaGridDependencySynchronize();
+    const uint32_t n = min(P.counters->nBig, P.bigCap);
+    if (!bin_wanted(P, n)) return;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nBins = (uint32_t)(P.binsX * P.binsY), nRuns = nBins * BIN_LEVELS;
+    const uint32_t per = (nRuns + 1023u) / 1024u, first = min(tid * per, nRuns), last = min(first + per, nRuns);
+    uint32_t sum = 0;
+    for (uint32_t i = first; i < last; i++) sum += P.binCursor[i];
+    uint32_t incl = sum;
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((tid & 31u) >= (uint32_t)o) incl += v; }
+    if ((tid & 31u) == 31u) sWarp[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t w = sWarp[tid];
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, w, o); if (tid >= (uint32_t)o) w += v; }
+        sWarp[tid] = w;
+    }
+    __syncthreads();
+    uint32_t at = incl - sum + ((tid >> 5) ? sWarp[(tid >> 5) - 1] : 0u);
+    for (uint32_t i = first; i < last; i++) { const uint32_t c = P.binCursor[i]; P.binCursor[i] = at; at += c; }
+    if (tid == 0) {
+        // Lists pay when a bin's list is much shorter than the whole list; a frame of screen-sized triangles (every
+        // triangle in most bins) keeps the shared list, and so does a frame whose pairs do not fit this frame's
+        // allocation (the host sees the demand and the next frame has the room).
+        const unsigned long long total = P.counters->binPairs64;
+        const bool pays = P.binForce || 4ull * total <= (unsigned long long)n * nBins;
+        P.counters->nBinPairs = pays ? (uint32_t)min(total, 0xFFFFFFFFull) : 0u;
+        P.counters->binned = (pays && total <= (unsigned long long)P.binListCap) ? 1u : 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 struct TileShared {
     unsigned long long keys[KEYS_PER_BIN];     // 32 KB: [tile 4x4][block 2x2][8x8]
     BigRec surv[SURV_CAP];                     // 40 KB
@@ -1673,7 +1777,7 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     // every load first (nine independent L2 reads in flight), then the stores from registers; no fence: the host
     // reads the pinned copy only after the stream has completed this kernel
     volatile Counters* d = P.counters;
-    const uint32_t nBig = d->nBig, nClip1 = d->nClipQueue, nClipN = d->nClipMulti, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid, nMidDiverted = d->nMidDiverted, serial = d->frameSerial + 1u;
+    const uint32_t nBig = d->nBig, nClip1 = d->nClipQueue, nClipN = d->nClipMulti, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid, nMidDiverted = d->nMidDiverted, serial = d->frameSerial + 1u, nBinPairs = d->nBinPairs, binned = d->binned;
     // the clip queue is split in two halves (clip_kernel): publish a demand that exceeds the capacity exactly when a half overflowed
     const uint32_t halfQ = P.clipQueueCap / 2u;
     const uint32_t nClipQueue = (nClip1 > halfQ || nClipN > P.clipQueueCap - halfQ) ? 2u * max(nClip1, nClipN) + 2u : nClip1 + nClipN;
@@ -1684,9 +1788,10 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
 #endif
     if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap || nMid > P.midCap) overFrames++;
     d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0; d->nMidDiverted = 0; d->bigSorted = 0; d->frameSerial = serial;
+    d->binned = 0; d->binKeyMin = 0; d->binKeyMax = 0; d->nBinPairs = 0; d->binPairs64 = 0;
     d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs; d->maxMid = maxMid;
     volatile Counters* h = P.hostCounters;
-    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid; h->nMidDiverted = nMidDiverted; h->frameSerial = serial;
+    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid; h->nMidDiverted = nMidDiverted; h->frameSerial = serial; h->nBinPairs = nBinPairs; h->binned = binned;
     h->overFrames = overFrames; h->maxBig = maxBig; h->maxClipQueue = maxClipQueue; h->maxClipRecs = maxClipRecs;
 }
 
@@ -1856,14 +1961,27 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
     };
     // Nearest-first view of the list (sort_big_kernel): the bin reads it 512 entries at a time and stops at the first
     // position whose key - a lower bound of every later triangle's depth - is behind the bin's depth bound.
-    const bool sorted = hizOn && P.counters->bigSorted != 0;
+    // Long lists come binned (bin_*_kernel): the bin reads its own list, nearest depth level first, instead of
+    // filtering the whole list by bin box.
+    const bool binned = P.counters->binned != 0;
+    const bool sorted = !binned && hizOn && P.counters->bigSorted != 0;
     const uint32_t* boxes = sorted ? P.bigBoxSorted : P.bigBox;
     const uint32_t chunk = sorted ? 512u : 4u * TILE_THREADS;
-    uint32_t cursor = 0;                                       // next entry of the tile-path list (uniform)
-    while (cursor < nBig) {
-        if (sorted && cursor) {
+    const uint32_t* runEnd = P.binCursor + (size_t)bin * BIN_LEVELS;          // binned: end of each of the bin's runs in binList
+    const uint32_t listLo = (binned && bin) ? runEnd[-1] : 0u;
+    const uint32_t listN = binned ? runEnd[BIN_LEVELS - 1] - listLo : nBig;
+    uint32_t cursor = 0;                                       // next entry of the (bin's) tile-path list (uniform)
+    while (cursor < listN) {
+        if ((sorted || (binned && hizOn)) && cursor) {
             // (uniform: every thread reads the same words after the barrier that closed the previous chunk)
-            const uint32_t bound = __ldg(P.bigBound + cursor);       // no later triangle is nearer than this
+            uint32_t bound;                                          // no later triangle is nearer than this
+            if (sorted) bound = __ldg(P.bigBound + cursor);
+            else {
+                uint32_t l = 0;                                      // depth level of the next unread entry: all later ones are at or behind it
+                while (l < (uint32_t)BIN_LEVELS - 1u && runEnd[l] <= listLo + cursor) l++;
+                const uint32_t kmin = ~P.counters->binKeyMin;
+                bound = kmin + (uint32_t)((((unsigned long long)(P.counters->binKeyMax - kmin) + 1ull) * l) / BIN_LEVELS);
+            }
             bool behind = bound > S.binU;
             if (!behind) {
                 // not behind the bound yet: the bin may still get bounded by what the admitted triangles draw
@@ -1879,11 +1997,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             // thread can start appending (and change the count) before all threads have read it.
             const uint32_t have = S.candCount;
             __syncthreads();
-            if (!(cursor < nBig && have <= (sorted ? 0u : (uint32_t)(CAND_CAP - 4 * TILE_THREADS)))) break;
+            if (!(cursor < listN && have <= (sorted ? 0u : (uint32_t)(CAND_CAP - 4 * TILE_THREADS)))) break;
             const uint32_t i = cursor + 4u * tid;
             uint32_t hits = 0;
-            if (4u * tid < chunk && i < nBig) {
-                uint32_t box[4];
+            uint32_t box[4];                                         // binned: the four list entries themselves
+            if (binned) {
+                #pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (i + k < listN) { box[k] = P.binList[listLo + i + k]; hits |= 1u << k; }
+            } else if (4u * tid < chunk && i < nBig) {
                 if (i + 3 < nBig) {
                     const uint4 b4 = __ldg(reinterpret_cast<const uint4*>(boxes + i));
                     box[0] = b4.x; box[1] = b4.y; box[2] = b4.z; box[3] = b4.w;
@@ -1907,7 +2029,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                 base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
                 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (hits & (1u << k)) S.cand[base++] = i + k;
+                    if (hits & (1u << k)) S.cand[base++] = binned ? box[k] : i + k;
             }
             cursor += chunk;
             __syncthreads();

@@ -66,6 +66,8 @@ struct edx_context {
     uint32_t* bigBox = nullptr; uint32_t bigBoxCap = 0;
     uint32_t* bigOrder = nullptr; uint32_t* bigKey = nullptr; uint32_t* bigBoxSorted = nullptr; uint32_t* bigBound = nullptr; uint32_t bigSortCap = 0;   // nearest-first view (sort_big_kernel)
     int sortBig = 1;                         // edx_set_option("sort_big", 0 | 1)
+    int binMin = 16384;                      // edx_set_option("bin_min", n): tile-path lists at least this long get per-bin lists (0 = never)
+    uint32_t* binCursor = nullptr; uint32_t* binList = nullptr; uint32_t* binKey = nullptr; uint32_t binCursorCap = 0, binListCap = 0, binKeyCap = 0;
     ClipItem* clipQueue = nullptr; uint32_t clipQueueCap = 0;
     ClipRec* clipRecs = nullptr; uint32_t clipRecCap = 0;
     Counters* counters = nullptr;
@@ -196,6 +198,7 @@ void fill_params(const edx_context* c, const edx_mesh* m, FrameParams& P)
     P.keys = c->keys;
     P.big = c->big; P.bigCap = c->bigCap; P.bigBox = c->bigBox;
     P.bigOrder = c->bigOrder; P.bigKey = c->bigKey; P.bigBoxSorted = c->bigBoxSorted; P.bigBound = c->bigBound;
+    P.binCursor = c->binCursor; P.binList = c->binList; P.binKey = c->binKey; P.binListCap = c->binListCap; P.binMin = c->binMin < 0 ? -c->binMin : c->binMin; P.binForce = c->binMin < 0 ? 1 : 0;
     P.clipQueue = c->clipQueue; P.clipQueueCap = c->clipQueueCap;
     P.clipRecs = c->clipRecs; P.clipRecCap = c->clipRecCap;
     P.clipSlot = c->clipSlot;
@@ -243,6 +246,24 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
         if (fe == 2) if (int r = grow(c, c->vrec, c->vrecCap, m->nVerts)) return r;
     }
     c->frontEndUsed = fe;
+
+    // Per-bin lists for a long tile-path list (bin_*_kernel): launched when the previous frame of an equal-sized mesh had
+    // such a list (or nothing is known yet and the mesh could produce one); the kernels themselves look at this frame's
+    // list and do nothing if it is short. Room for the (triangle, bin) pairs follows the demand the last frame published;
+    // a frame that finds too little keeps the shared list and the next one has the room.
+    const uint32_t binMin = (uint32_t)(c->binMin < 0 ? -c->binMin : c->binMin);      // (negative: tests force lists that would not pay)
+    bool launchBin = binMin > 0 && m->nTris >= binMin && !dumpBuf;
+    if (launchBin && c->skipIdle && c->hintTris == m->nTris && c->hintVerts == m->nVerts) {
+        const volatile Counters* h = c->hostCounters;
+        if (h->frameSerial != 0) launchBin = h->nBig >= binMin;
+    }
+    if (launchBin) {
+        const volatile Counters* h = c->hostCounters;
+        const uint64_t pairs = std::max<uint64_t>({ 1u << 20, (uint64_t)h->nBinPairs, 8ull * std::min<uint64_t>(h->nBig, c->bigCap) });
+        if (int r = grow(c, c->binList, c->binListCap, std::min<uint64_t>(pairs, 1ull << 30))) return r;
+        if (int r = grow(c, c->binCursor, c->binCursorCap, (uint64_t)c->binsX * c->binsY * BIN_LEVELS)) return r;
+        if (int r = grow(c, c->binKey, c->binKeyCap, c->bigCap)) return r;
+    }
 
     FrameParams P;
     fill_params(c, m, P);
@@ -302,6 +323,12 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     // tens of thousands is a couple of triangles per warp, not a serial walk whose every step waits on a record load
     if (m->nTris && launchMid) add("mid_kernel", mid_kernel, dim3(148 * (unsigned)c->midCtasPerSm), dim3(128), 0, 0, 1);
     if (m->nTris && launchSort) add("sort_big_kernel", sort_big_kernel, dim3(1), dim3(1024), 0, 0, 1);
+    if (launchBin) {
+        add("bin_keys_kernel", bin_keys_kernel, dim3(148 * 4), dim3(256), 0, 0, 1);
+        add("bin_fill_kernel", bin_fill_kernel<false>, dim3(148 * 8), dim3(256), 0, 0, 1);
+        add("bin_scan_kernel", bin_scan_kernel, dim3(1), dim3(1024), 0, 0, 1);
+        add("bin_fill_kernel", bin_fill_kernel<true>, dim3(148 * 8), dim3(256), 0, 0, 1);
+    }
     const dim3 leanGrid((c->binsX * c->binsY * 16 + 7) / 8);
     if (c->msaaLog2 == 0) {
         if (lean && !shaded && !c->captureIds) add("lean_resolve_kernel", lean_resolve_kernel<true>, leanGrid, dim3(256), 0, 1, 2);
@@ -453,7 +480,7 @@ int finish_frame(edx_context* c)
         const Counters k = *c->hostCounters;
         const bool over = k.nBig > c->bigCap || k.nClipQueue > c->clipQueueCap || k.nClipRecs > c->clipRecCap || k.nMid > c->midCap;
         c->stats.binned_tris = k.nBig; c->stats.clipped_tris = k.nClipQueue; c->stats.clip_records = k.nClipRecs;
-        c->stats.tile_pairs = k.tilePairs; c->stats.mid_tris = k.nMid;
+        c->stats.tile_pairs = k.tilePairs; c->stats.mid_tris = k.nMid; c->stats.bin_pairs = k.binned ? k.nBinPairs : 0;
 #ifdef EDX_DEBUG_STATS
         if (getenv("EDX_DEBUG_PRINT")) {
             uint32_t h[512];
@@ -606,7 +633,7 @@ void edx_destroy(edx_context* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     release_frame_buffers(c);
-    dev_free(c->big); dev_free(c->bigBox); dev_free(c->bigOrder); dev_free(c->bigKey); dev_free(c->bigBoxSorted); dev_free(c->bigBound); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->clipSlot); dev_free(c->counters);
+    dev_free(c->big); dev_free(c->bigBox); dev_free(c->bigOrder); dev_free(c->bigKey); dev_free(c->bigBoxSorted); dev_free(c->bigBound); dev_free(c->binCursor); dev_free(c->binList); dev_free(c->binKey); dev_free(c->clipQueue); dev_free(c->clipRecs); dev_free(c->clipSlot); dev_free(c->counters);
     dev_free(c->workList); dev_free(c->vcFlag); dev_free(c->vrec); dev_free(c->mid);
     if (c->graphExec) cudaGraphExecDestroy(c->graphExec);
     if (c->graph) cudaGraphDestroy(c->graph);
@@ -714,6 +741,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "front_end")) { if (value < -1 || value > 2) return fail(c, EDX_ERR_INVALID, "front_end: -1 auto, 0 per-cluster CTAs, 1 cull + work list, 2 cull + per-vertex stage + work list"); c->frontEnd = value; return EDX_OK; }
     if (!strcmp(name, "skip_idle")) { c->skipIdle = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "sort_big")) { c->sortBig = value ? 1 : 0; return EDX_OK; }
+    if (!strcmp(name, "bin_min")) { c->binMin = value; return EDX_OK; }
     if (!strcmp(name, "graphs")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "graphs: 0 never, 1 small meshes, 2 always"); c->useGraphs = value; return EDX_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }

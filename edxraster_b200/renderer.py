@@ -242,7 +242,7 @@ class Renderer:
         s = _lib.Stats()
         self._check(self._lib.edx_get_stats(self._h, C.byref(s)))
         return {"submitted_tris": s.submitted_tris, "clipped_tris": s.clipped_tris, "binned_tris": s.binned_tris,
-                "clip_records": s.clip_records, "regrow_count": s.regrow_count, "tile_pairs": s.tile_pairs, "mid_tris": s.mid_tris,
+                "clip_records": s.clip_records, "regrow_count": s.regrow_count, "tile_pairs": s.tile_pairs, "mid_tris": s.mid_tris, "bin_pairs": s.bin_pairs,
                 "stage_ms": {"geom": s.stage_ms[0], "clip": s.stage_ms[1], "tile": s.stage_ms[2], "total": s.stage_ms[3]}}
 
     def SetOption(self, name, value):

@@ -58,6 +58,7 @@ typedef struct edx_stats {
     uint32_t regrow_count;     /* times an internal queue was grown and the frame re-run */
     uint32_t tile_pairs;       /* (triangle, 64x64 bin) pairs that survived the bin-level culls: load of the tile path */
     uint64_t mid_tris;         /* post-setup triangles rasterised one warp per triangle (the mid-size path) */
+    uint64_t bin_pairs;        /* (triangle, bin) entries of the per-bin lists built for a long tile-path list; 0 = shared list */
     float    stage_ms[8];      /* valid with profiling on: geom, clip, tile, total; rest 0 */
 } edx_stats;
 

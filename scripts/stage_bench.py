@@ -64,7 +64,7 @@ for w in a.workloads.split(","):
             ring.Synchronize()
             ms3 = (time.perf_counter() - t) * 1e3 / n
         ring.close()
-        print("%s [%s] frame %.1f us | 3 in flight %.1f us | geom %.1f clip %.1f tile %.1f | mid %d big %d clipped %d pairs %d"
-              % (w, var, ms * 1e3, ms3 * 1e3, st["geom"] * 1e3, st["clip"] * 1e3, st["tile"] * 1e3, s["mid_tris"], s["binned_tris"], s["clipped_tris"], s["tile_pairs"]), flush=True)
+        print("%s [%s] frame %.1f us | 3 in flight %.1f us | geom %.1f clip %.1f tile %.1f | mid %d big %d clipped %d pairs %d listpairs %d"
+              % (w, var, ms * 1e3, ms3 * 1e3, st["geom"] * 1e3, st["clip"] * 1e3, st["tile"] * 1e3, s["mid_tris"], s["binned_tris"], s["clipped_tris"], s["tile_pairs"], s["bin_pairs"]), flush=True)
         m.Release()
         r.close()

@@ -41,6 +41,7 @@ def test_reduced_configs_bit_exact(name):
                                           ({"cluster_cull": 2, "pdl": 0}, True), ({"cluster_cull": 0, "small_max_clip": 0}, True),
                                           ({"lean_resolve": 0, "clip_carveout": 2}, True), ({"lean_resolve": 2, "clip_carveout": 1}, True),
                                           ({"graphs": 0}, True), ({"graphs": 2, "pdl": 0}, True), ({"mid_max": 0}, True), ({"mid_max": 0, "small_max": 32}, True), ({"mid_max": 16}, True),
+                                          ({"bin_min": -1}, True), ({"bin_min": -1, "mid_max": 0, "small_max": 2}, True), ({"bin_min": -1, "hiz": 0, "mid_max": 0}, False),
                                           ({"mid_max": 512, "small_max": 0, "small_max_clip": 0}, True), ({"mid_max": 200, "small_max": 3}, False)])
 def test_tuning_knobs_never_change_the_image(name, options, hier):
     # routing (direct vs tile path), hierarchical Z and the 8x8 block tests are pure optimisations
@@ -322,11 +323,15 @@ def test_tile_path_stress_many_candidates_per_bin(seed):
     p[flip, 0], p[flip, 1] = p[flip, 1].copy(), p[flip, 0].copy()
     sc = raster_scene(p, 0.05 + 0.9 * rng.random((n, 3)), 512, 384)
     ref = parity.render_oracle(sc)
-    for opts in ({"mid_max": 0}, {"mid_max": 0, "hiz": 0}, {"mid_max": 0, "small_max": 4}, {}):
+    for opts in ({"mid_max": 0}, {"mid_max": 0, "hiz": 0}, {"mid_max": 0, "small_max": 4}, {}, {"bin_min": 0}, {"bin_min": -1, "mid_max": 0},
+                 {"bin_min": 100, "mid_max": 0, "hiz": 0}):
         got = parity.render_gpu(sc, options=opts, stages=False)
         rep = parity.compare(ref, got)
         assert parity.is_parity(rep), (opts, rep)
         assert got["stats"]["binned_tris"] > (20000 if "mid_max" in opts else 8000)
+        # per-bin lists (stage a7) are built for long tile-path lists, and only for them
+        if opts.get("bin_min", 1) <= 0:
+            assert (got["stats"]["bin_pairs"] > got["stats"]["binned_tris"]) == (opts["bin_min"] < 0), (opts, got["stats"])
 
 
 def _fuzz_scene(seed):
@@ -675,10 +680,12 @@ def test_m1_mid_size_stress_every_routing():
     # path; mid_max = 0 is round 1's routing (everything on the tile path, every bin sweeps the whole list).
     sc = scenes.stress_m1(width=1280, height=720, num_tris=60000)
     ref = parity.render_oracle(sc)
-    for opts in ({}, {"mid_max": 0, "small_max": 32}, {"mid_max": 128}, {"sort_big": 0}):
+    for opts in ({}, {"mid_max": 0, "small_max": 32}, {"mid_max": 128}, {"sort_big": 0}, {"bin_min": 0}, {"bin_min": 0, "mid_max": 0}, {"bin_min": 1000, "mid_max": 0}):
         got = parity.render_gpu(sc, options=opts, stages=False)
         rep = parity.compare(ref, got)
         assert parity.is_parity(rep), (opts, rep)
+        if "bin_min" in opts:           # long tile-path lists are binned (stage a7) unless switched off
+            assert (got["stats"]["bin_pairs"] > 0) == (opts["bin_min"] > 0 and got["stats"]["binned_tris"] >= opts["bin_min"]), (opts, got["stats"])
     assert got["stats"]["mid_tris"] + got["stats"]["binned_tris"] > 50000
 
 
