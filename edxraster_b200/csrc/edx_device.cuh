@@ -91,6 +91,7 @@ struct Counters {
     // per-bin lists of the tile path (bin_*_kernel): valid this frame, range of the depth keys, (triangle, bin) pairs wanted
     uint32_t binned, binKeyMin, binKeyMax, nBinPairs;      // (binKeyMin is kept complemented: zero is its identity)
     unsigned long long binPairs64;
+    unsigned long long midArea;  // pixels spanned by the boxes of the triangles mid_kernel rasterised this frame
     unsigned long long dbg[8];   // EDX_DEBUG_STATS builds: summed per-CTA cycle counts of the tile kernel's phases
 };
 

@@ -860,6 +860,7 @@ __global__ void __launch_bounds__(128) mid_kernel(const __grid_constant__ FrameP
     const uint32_t lane = threadIdx.x & 31u, nWarps = gridDim.x * (blockDim.x >> 5), gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const bool ms = P.samples > 1;
     const int lx = (int)(lane & 7u), ly = (int)(lane >> 3);
+    unsigned long long boxArea = 0;          // pixels this warp's triangles' boxes span: the fragment load of a path that has no occlusion culling
     for (uint32_t q = gw; q < n; q += nWarps) {
         const int4* rp = reinterpret_cast<const int4*>(P.mid + q);
         const int4 a = __ldg(rp), b = __ldg(rp + 1), c = __ldg(rp + 2);      // same address in every lane: one broadcast transaction each
@@ -869,6 +870,7 @@ __global__ void __launch_bounds__(128) mid_kernel(const __grid_constant__ FrameP
         e.init(a.x, a.y, a.z, a.w, b.x, b.y);
         const int x0 = max(0, first_pixel(min3i(a.x, a.z, b.x), ms)), x1 = min(P.width - 1, last_pixel(max3i(a.x, a.z, b.x), ms));
         const int y0 = max(0, first_pixel(min3i(a.y, a.w, b.y), ms)), y1 = min(P.height - 1, last_pixel(max3i(a.y, a.w, b.y), ms));
+        if (x1 >= x0 && y1 >= y0) boxArea += (unsigned long long)((x1 - x0 + 1) * (y1 - y0 + 1));
         // biased edge values at this lane's pixel of the first block; a block step is 8 pixels in x, 4 in y
         const int cx = ((x0 + lx) << 4) + 8, cy = ((y0 + ly) << 4) + 8;
         uint32_t r0 = (uint32_t)e.e0(cx, cy), r1 = (uint32_t)e.e1(cx, cy), r2 = (uint32_t)e.e2(cx, cy);
@@ -909,6 +911,7 @@ __global__ void __launch_bounds__(128) mid_kernel(const __grid_constant__ FrameP
             r0 += sC0; r1 += sC1; r2 += sC2;
         }
     }
+    if (lane == 0 && boxArea) atomicAdd(&P.counters->midArea, boxArea);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1778,6 +1781,7 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     // reads the pinned copy only after the stream has completed this kernel
     volatile Counters* d = P.counters;
     const uint32_t nBig = d->nBig, nClip1 = d->nClipQueue, nClipN = d->nClipMulti, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid, nMidDiverted = d->nMidDiverted, serial = d->frameSerial + 1u, nBinPairs = d->nBinPairs, binned = d->binned;
+    const unsigned long long midArea = d->midArea;
     // the clip queue is split in two halves (clip_kernel): publish a demand that exceeds the capacity exactly when a half overflowed
     const uint32_t halfQ = P.clipQueueCap / 2u;
     const uint32_t nClipQueue = (nClip1 > halfQ || nClipN > P.clipQueueCap - halfQ) ? 2u * max(nClip1, nClipN) + 2u : nClip1 + nClipN;
@@ -1788,10 +1792,10 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
 #endif
     if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap || nMid > P.midCap) overFrames++;
     d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0; d->nMidDiverted = 0; d->bigSorted = 0; d->frameSerial = serial;
-    d->binned = 0; d->binKeyMin = 0; d->binKeyMax = 0; d->nBinPairs = 0; d->binPairs64 = 0;
+    d->binned = 0; d->binKeyMin = 0; d->binKeyMax = 0; d->nBinPairs = 0; d->binPairs64 = 0; d->midArea = 0;
     d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs; d->maxMid = maxMid;
     volatile Counters* h = P.hostCounters;
-    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid; h->nMidDiverted = nMidDiverted; h->frameSerial = serial; h->nBinPairs = nBinPairs; h->binned = binned;
+    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid; h->nMidDiverted = nMidDiverted; h->frameSerial = serial; h->nBinPairs = nBinPairs; h->binned = binned; h->midArea = midArea;
     h->overFrames = overFrames; h->maxBig = maxBig; h->maxClipQueue = maxClipQueue; h->maxClipRecs = maxClipRecs;
 }
 

@@ -66,6 +66,7 @@ struct edx_context {
     uint32_t* bigBox = nullptr; uint32_t bigBoxCap = 0;
     uint32_t* bigOrder = nullptr; uint32_t* bigKey = nullptr; uint32_t* bigBoxSorted = nullptr; uint32_t* bigBound = nullptr; uint32_t bigSortCap = 0;   // nearest-first view (sort_big_kernel)
     int sortBig = 1;                         // edx_set_option("sort_big", 0 | 1)
+    bool midShrunk = false; int midAuto = 1;  // edx_set_option("mid_auto", 0 | 1): see enqueue_frame
     int binMin = 16384;                      // edx_set_option("bin_min", n): tile-path lists at least this long get per-bin lists (0 = never)
     uint32_t* binCursor = nullptr; uint32_t* binList = nullptr; uint32_t* binKey = nullptr; uint32_t binCursorCap = 0, binListCap = 0, binKeyCap = 0;
     ClipItem* clipQueue = nullptr; uint32_t clipQueueCap = 0;
@@ -316,6 +317,16 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
             launchSort = launchSort && h->nBig >= (uint32_t)SORT_MIN;
         }
     }
+    // The warp-per-triangle path has no occlusion culling: it tests every pixel of every box. That is the cheapest way
+    // through a frame whose mid-size triangles cover the screen a few times (C4: 7x), and the wrong one when they cover it
+    // hundreds of times (the M1 stress: 740x) - there the tile path, which culls hierarchically and reads per-bin lists,
+    // wins even at its higher cost per triangle. mid_kernel publishes the pixels its boxes spanned; above 128 screens the
+    // following frames of an equal-sized mesh keep only boxes below 32 px on the path (until another mesh arrives: the
+    // measure itself changes with the routing, so the decision is not revisited every frame).
+    if (c->hintTris != m->nTris || c->hintVerts != m->nVerts) c->midShrunk = false;
+    else if (c->midAuto && c->hostCounters->frameSerial != 0 &&
+             ((const volatile Counters*)c->hostCounters)->midArea > 128ull * c->width * c->height) c->midShrunk = true;
+    if (c->midShrunk && c->midMax > 32) { P.midMax = 32; T.midMax = 32; }
     c->hintTris = m->nTris; c->hintVerts = m->nVerts;
     P.midLaunched = launchMid ? 1 : 0; T.midLaunched = P.midLaunched;
     if (m->nTris) add("clip_kernel", clip_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
@@ -742,6 +753,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "skip_idle")) { c->skipIdle = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "sort_big")) { c->sortBig = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "bin_min")) { c->binMin = value; return EDX_OK; }
+    if (!strcmp(name, "mid_auto")) { c->midAuto = value ? 1 : 0; c->midShrunk = false; return EDX_OK; }
     if (!strcmp(name, "graphs")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "graphs: 0 never, 1 small meshes, 2 always"); c->useGraphs = value; return EDX_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "fuse_clip")) { c->fuseClip = value ? 1 : 0; return EDX_OK; }
