@@ -1628,7 +1628,7 @@ struct TileShared {
     uint32_t survCount, candCount;
     uint32_t binU;                             // order_f32 of the bin's depth upper bound
     uint32_t keyMax;                           // scratch: max ordered depth currently stored in the bin
-    uint32_t admitCount, admitNear;            // scratch: candidates the bin's bound admits, the nearest of them
+    uint32_t admitCount, admitNear, admitFar;  // scratch: candidates the bin's bound admits, the nearest and the farthest of them
     unsigned long long keysReady;              // mbarrier: the bulk copy of the bin's keys has landed
 };
 
@@ -1858,7 +1858,7 @@ __global__ void __launch_bounds__(256) lean_resolve_kernel(const __grid_constant
 }
 
 #ifdef EDX_DEBUG_STATS
-__device__ unsigned long long g_binDbg[8192][6];   // per bin: cycles cand / sweep / flush+final raster / resolve, candidates, survivors
+__device__ unsigned long long g_binDbg[8192][10];   // per bin: cycles cand / sweep / flush+final raster / resolve, candidates, survivors
 __device__ uint32_t g_tileResident[512];       // [sm] live tile_kernel CTAs, [256 + sm] the most seen at once
 struct ResidentScope {
     uint32_t sm;
@@ -1931,10 +1931,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
             if (k2.x != KEY_EMPTY || k2.y != KEY_EMPTY) gk2[b4 * 32 + lane] = empty2;
         }
     }
-    if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; S.admitCount = 0; S.admitNear = 0xFFFFFFFFu; }
+    if (tid == 0) { S.survCount = 0; S.candCount = 0; S.binU = order_f32(1.0f); S.keyMax = 0; S.admitCount = 0; S.admitNear = 0xFFFFFFFFu; S.admitFar = 0; }
     __syncthreads();
 #ifdef EDX_DEBUG_STATS
-    long long tMark = clock64(), tCand = 0, tSweep = 0, tFlush = 0, nFlush = 0, nSurvTot = 0;
+    long long tMark = clock64(), tCand = 0, tSweep = 0, tFlush = 0, nFlush = 0, nSurvTot = 0, nIter = 0, nCandTot = 0, tClass = 0, tCount = 0, tSlab = 0, tTop = 0, tFlushSlab = 0;
 #endif
 
     const bool hizOn = P.hiz && P.hierarchical;
@@ -1991,7 +1991,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
                 // not behind the bound yet: the bin may still get bounded by what the admitted triangles draw
                 const uint32_t haveSurv = S.survCount;
                 __syncthreads();
+#ifdef EDX_DEBUG_STATS
+                const long long t0 = clock64();
+#endif
                 if (haveSurv) { flush_bin(haveSurv, true); behind = bound > S.binU; }
+#ifdef EDX_DEBUG_STATS
+                tTop += clock64() - t0;
+#endif
             }
             if (behind) break;
         }
@@ -2042,6 +2048,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         tCand += clock64() - tMark; tMark = clock64();
 #endif
         const uint32_t nCand = S.candCount;
+#ifdef EDX_DEBUG_STATS
+        nIter++; nCandTot += nCand;
+#endif
         const bool hiz = hizOn && nCand >= HIZ_MIN_CAND;
         // 3a. classify every candidate against the bin: exact reject, and (hierarchical Z) its conservative near depth;
         //     a candidate that covers the whole bin lowers the bin's depth upper bound S.binU to its far side. The bound
@@ -2070,23 +2079,35 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         //     NEAREST FIRST, in eight slabs of near depth with a raster flush after each: once the near triangles are
         //     drawn, the bin's (and in raster_survivors each tile's) stored depth culls the slabs behind them - again
         //     whatever order the list was appended in.
+#ifdef EDX_DEBUG_STATS
+        tClass += clock64() - tMark;
+#endif
         auto flush = [&](uint32_t haveSurv) { flush_bin(haveSurv, hiz); };
         uint32_t nSlabs = 1, zNear = 0, zFar = 0xFFFFFFFEu;
         if (hiz) {
             const uint32_t U0 = S.binU;
-            uint32_t cnt = 0, zmin = 0xFFFFFFFFu;
+            uint32_t cnt = 0, zmin = 0xFFFFFFFFu, zmax = 0u;
             for (uint32_t j = tid; j < nCand; j += TILE_THREADS) {
                 const uint32_t z = S.candZ[j];
-                if (z <= U0) { cnt++; zmin = min(zmin, z); }
+                if (z <= U0) { cnt++; zmin = min(zmin, z); zmax = max(zmax, z); }
             }
             cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
             zmin = __reduce_min_sync(0xFFFFFFFFu, zmin);
-            if (lane == 0 && cnt) { atomicAdd(&S.admitCount, cnt); atomicMin(&S.admitNear, zmin); }
+            zmax = __reduce_max_sync(0xFFFFFFFFu, zmax);
+            if (lane == 0 && cnt) { atomicAdd(&S.admitCount, cnt); atomicMin(&S.admitNear, zmin); atomicMax(&S.admitFar, zmax); }
             __syncthreads();
-            if (S.admitCount > (uint32_t)(SURV_CAP - TILE_THREADS)) { nSlabs = 8; zNear = S.admitNear; zFar = U0; }
+            // The slabs divide the depth range the admitted candidates actually occupy. (They used to run up to the bin's
+            // bound - 1.0 where nothing covers the bin - and the few hundred triangles of a diagonal bin, whose depths
+            // lie within a sliver of that range, all fell into the first slab: 280 admitted and rasterised per pixel
+            // where the nearest handful settles the bin - those bins took 8x the mean and set the kernel's tail.)
+            if (S.admitCount > (uint32_t)(SURV_CAP - TILE_THREADS)) { nSlabs = 8; zNear = S.admitNear; zFar = S.admitFar; }
             __syncthreads();
-            if (tid == 0) { S.admitCount = 0; S.admitNear = 0xFFFFFFFFu; }
+            if (tid == 0) { S.admitCount = 0; S.admitNear = 0xFFFFFFFFu; S.admitFar = 0; }
         }
+#ifdef EDX_DEBUG_STATS
+        tCount += clock64() - tMark;
+        const long long tFlushBefore = tFlush;
+#endif
         for (uint32_t slab = 0; slab < nSlabs; slab++) {
             const uint32_t span = zFar - zNear;
             const uint32_t lo = slab == 0 ? 0u : zNear + (uint32_t)(((unsigned long long)span * slab) / nSlabs) + 1u;
@@ -2119,6 +2140,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         if (tid == 0) S.candCount = 0;
         __syncthreads();
 #ifdef EDX_DEBUG_STATS
+        tSlab += clock64() - tMark; tFlushSlab += tFlush - tFlushBefore;
         tSweep += clock64() - tMark; tMark = clock64();
 #endif
     }
@@ -2135,7 +2157,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) tile_kernel(const __grid_cons
         atomicAdd(&P.counters->dbg[2], (unsigned long long)tFlush); atomicAdd(&P.counters->dbg[3], (unsigned long long)tFinal);
         atomicAdd(&P.counters->dbg[4], (unsigned long long)nFlush); atomicAdd(&P.counters->dbg[5], (unsigned long long)nSurvTot);
         atomicAdd(&P.counters->dbg[6], 1ull);
-        if (bin < 8192) { g_binDbg[bin][0] = tCand; g_binDbg[bin][1] = tSweep - tFlush; g_binDbg[bin][2] = tFlush + tFinal; g_binDbg[bin][5] = nSurvTot; }
+        if (bin < 8192) { g_binDbg[bin][0] = tCand; g_binDbg[bin][1] = tSweep - tFlush; g_binDbg[bin][2] = tFlush + tFinal; g_binDbg[bin][5] = nSurvTot; g_binDbg[bin][4] = (unsigned long long)(nIter * 1000000ll + nFlush * 10000ll) + (unsigned long long)min(nCandTot, 9999ll) + ((unsigned long long)tClass << 32); g_binDbg[bin][6] = tCount; g_binDbg[bin][7] = tSlab; g_binDbg[bin][8] = tTop; g_binDbg[bin][9] = tFlushSlab; }
     }
     tMark = clock64();
 #endif

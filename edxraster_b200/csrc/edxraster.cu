@@ -504,7 +504,7 @@ int finish_frame(edx_context* c)
             }
         }
         if (getenv("EDX_DEBUG_PRINT") && k.dbg[6]) {
-            static unsigned long long hb[8192][6];
+            static unsigned long long hb[8192][10];
             if (cudaMemcpyFromSymbol(hb, g_binDbg, sizeof(hb)) == cudaSuccess) {
                 const int nb = std::min<int>(8192, c->binsX * c->binsY);
                 std::vector<int> order(nb);
@@ -516,7 +516,7 @@ int finish_frame(edx_context* c)
                 fprintf(stderr, "[edx dbg] per-bin cycles: mean %llu; heaviest bins (bin: cand sweep raster resolve | survivors)\n", sum / std::max(nb, 1));
                 for (int i = 0; i < std::min(nb, 10); i++) {
                     const int b = order[i];
-                    fprintf(stderr, "[edx dbg]   bin %4d (%2d,%2d): %7llu %7llu %7llu %7llu | %llu\n", b, b % (int)c->binsX, b / (int)c->binsX, hb[b][0], hb[b][1], hb[b][2], hb[b][3], hb[b][5]);
+                    fprintf(stderr, "[edx dbg]   bin %4d (%2d,%2d): %7llu %7llu %7llu %7llu | %llu | iterations/flushes/candidates %llu cycles until: classified %llu counted %llu slabs done %llu (flushes in them %llu); flush at loop top %llu\n", b, b % (int)c->binsX, b / (int)c->binsX, hb[b][0], hb[b][1], hb[b][2], hb[b][3], hb[b][5], hb[b][4] & 0xFFFFFFFFull, hb[b][4] >> 32, hb[b][6], hb[b][7], hb[b][9], hb[b][8]);
                 }
                 memset(hb, 0, sizeof(hb));
                 cudaMemcpyToSymbol(g_binDbg, hb, sizeof(hb));
