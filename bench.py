@@ -521,14 +521,16 @@ class Farm:
             lr.close()
 
 
-def secondary_config(name, device, peak, R, with_cpu=True):
+def secondary_config(name, device, peak, R, with_cpu=True, options=None, sc=None):
     """Quick device-resident measurement of another BASELINE config (rank 0, N=1 only), with its CPU baseline."""
     t0 = time.time()
-    sc = make_scene(name, 1.0)
+    sc = sc if sc is not None else make_scene(name, 1.0)
     r = R.Renderer(device)
     r.Initialize(sc.width, sc.height)
     r.SetTransform(sc.mv, sc.proj, sc.raster)
     r.SetPixelShader(sc.shader)
+    for k, v in (options or {}).items():
+        r.SetOption(k, int(v))
     copies = mesh_copies(sc.num_verts, sc.num_tris)
     meshes = [r.CreateMesh(sc.vertices, sc.indices) for _ in range(copies)]
     frames = 30 if sc.num_tris < 5_000_000 else 10
@@ -537,6 +539,8 @@ def secondary_config(name, device, peak, R, with_cpu=True):
     ring = R.FrameRing(device, depth=3)
     ring.Initialize(sc.width, sc.height)
     ring.SetPixelShader(sc.shader)
+    for k, v in (options or {}).items():
+        ring.SetOption(k, int(v))
     nring = frames * 4
     xf = R.PackedTransform(sc.mv, sc.proj, sc.raster)      # marshalled once: a 20 us frame leaves no room for numpy conversions
     for rep in range(2):
@@ -564,8 +568,8 @@ def secondary_config(name, device, peak, R, with_cpu=True):
            "algorithmic_bytes": ab, "hbm_frac_whole_frame": ab / (ms * 1e-3) / 1e9 / peak,
            "hbm_frac_whole_frame_3_in_flight": ab / (ms_ring * 1e-3) / 1e9 / peak,
            "fb_only_frac": (8 if sc.shader != 0 else 4) * sc.width * sc.height / (ms * 1e-3) / 1e9 / peak,
-           "stage_ms": stage, "binned_tris": st["binned_tris"], "clipped_tris": st["clipped_tris"],
-           "l2": "rotating %d mesh copies" % copies}
+           "stage_ms": stage, "binned_tris": st["binned_tris"], "clipped_tris": st["clipped_tris"], "mid_tris": st["mid_tris"],
+           "bin_pairs": st["bin_pairs"], "l2": "rotating %d mesh copies" % copies}
     for m in meshes:
         m.Release()
     r.close()
@@ -736,6 +740,17 @@ def ours_arm(args):
                         sc4 = scx
                 except Exception as e:
                     also[name] = {"error": str(e)}
+            # M1: not a BASELINE config - the stress case for long tile-path lists (per-bin lists, stage a7) and for the
+            # routing of mid-size triangles; the second line is the same frame with round 1's design (every triangle
+            # above 32 px on one shared list that every bin reads, no per-bin lists)
+            try:
+                also["M1"], scm = secondary_config("M1", local, peak, R, with_cpu=False)
+                old, _ = secondary_config("M1", local, peak, R, with_cpu=False, sc=scm,
+                                          options={"bin_min": 0, "mid_auto": 0, "mid_max": 0, "small_max": 32})
+                also["M1"]["shared_list_round1_routing"] = {k: old[k] for k in ("ms_per_frame", "ms_per_frame_3_in_flight", "stage_ms", "binned_tris", "mid_tris", "bin_pairs")}
+                del scm
+            except Exception as e:
+                also["M1"] = {"error": str(e)}
         try:
             also["C5"] = config5(torch, dist, R, sc4, local, rank, world, args, peak)
         except Exception as e:       # pragma: no cover

@@ -91,7 +91,8 @@ struct Counters {
     // per-bin lists of the tile path (bin_*_kernel): valid this frame, range of the depth keys, (triangle, bin) pairs wanted
     uint32_t binned, binKeyMin, binKeyMax, nBinPairs;      // (binKeyMin is kept complemented: zero is its identity)
     unsigned long long binPairs64;
-    unsigned long long midArea;  // pixels spanned by the boxes of the triangles mid_kernel rasterised this frame
+    unsigned long long midArea;  // pixels spanned by the boxes of the triangles mid_kernel rasterised this frame (host copy: the sum)
+    unsigned long long midAreaSlot[64];   // ... accumulated in 64 slots: ten thousand warps adding to ONE address cost mid_kernel 14 us
     unsigned long long dbg[8];   // EDX_DEBUG_STATS builds: summed per-CTA cycle counts of the tile kernel's phases
 };
 

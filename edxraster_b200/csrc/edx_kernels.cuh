@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(128) mid_kernel(const __grid_constant__ FrameP
             r0 += sC0; r1 += sC1; r2 += sC2;
         }
     }
-    if (lane == 0 && boxArea) atomicAdd(&P.counters->midArea, boxArea);
+    if (lane == 0 && boxArea) atomicAdd(&P.counters->midAreaSlot[gw & 63u], boxArea);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1577,9 +1577,15 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(const __grid_constant__ F
     }
     if (!SCATTER) {
         // the pair total in 64 bits (the 32-bit counts of a frame of a million screen-sized triangles would wrap)
+        // (one atomic per CTA: thousands of warps adding to one address serialise in L2)
+        __shared__ unsigned long long sPairs;
+        if (threadIdx.x == 0) sPairs = 0;
+        __syncthreads();
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
-        if ((threadIdx.x & 31u) == 0 && pairs) atomicAdd(&P.counters->binPairs64, pairs);
+        if ((threadIdx.x & 31u) == 0 && pairs) atomicAdd(&sPairs, pairs);
+        __syncthreads();
+        if (threadIdx.x == 0 && sPairs) atomicAdd(&P.counters->binPairs64, sPairs);
     }
 }
 
@@ -1776,12 +1782,19 @@ __device__ __forceinline__ void resolve_pixel(const FrameParams& P, unsigned lon
 __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
 {
     cudaGridDependencySynchronize();
+    unsigned long long midArea = 0;
+    {
+        volatile unsigned long long* slot = P.counters->midAreaSlot;
+        midArea = slot[threadIdx.x] + slot[threadIdx.x + 32];
+        if (midArea) { slot[threadIdx.x] = 0; slot[threadIdx.x + 32] = 0; }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) midArea += __shfl_xor_sync(0xFFFFFFFFu, midArea, o);
+    }
     if (threadIdx.x != 0) return;
     // every load first (nine independent L2 reads in flight), then the stores from registers; no fence: the host
     // reads the pinned copy only after the stream has completed this kernel
     volatile Counters* d = P.counters;
     const uint32_t nBig = d->nBig, nClip1 = d->nClipQueue, nClipN = d->nClipMulti, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid, nMidDiverted = d->nMidDiverted, serial = d->frameSerial + 1u, nBinPairs = d->nBinPairs, binned = d->binned;
-    const unsigned long long midArea = d->midArea;
     // the clip queue is split in two halves (clip_kernel): publish a demand that exceeds the capacity exactly when a half overflowed
     const uint32_t halfQ = P.clipQueueCap / 2u;
     const uint32_t nClipQueue = (nClip1 > halfQ || nClipN > P.clipQueueCap - halfQ) ? 2u * max(nClip1, nClipN) + 2u : nClip1 + nClipN;
@@ -1792,7 +1805,7 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
 #endif
     if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap || nMid > P.midCap) overFrames++;
     d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0; d->nMidDiverted = 0; d->bigSorted = 0; d->frameSerial = serial;
-    d->binned = 0; d->binKeyMin = 0; d->binKeyMax = 0; d->nBinPairs = 0; d->binPairs64 = 0; d->midArea = 0;
+    d->binned = 0; d->binKeyMin = 0; d->binKeyMax = 0; d->nBinPairs = 0; d->binPairs64 = 0;
     d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs; d->maxMid = maxMid;
     volatile Counters* h = P.hostCounters;
     h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid; h->nMidDiverted = nMidDiverted; h->frameSerial = serial; h->nBinPairs = nBinPairs; h->binned = binned; h->midArea = midArea;
