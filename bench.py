@@ -300,7 +300,7 @@ def time_frames(r, meshes, frames, warm):
     """Device time of `frames` back-to-back frames (CUDA events on the context's stream)."""
     for i in range(warm):
         r.RenderMesh(meshes[i % len(meshes)])
-    r.Synchronize()
+        r.Synchronize()               # (a synchronised frame sizes the internal queues: grow + re-run if it overflowed)
     r.TimerBegin()
     for i in range(frames):
         r.RenderMesh(meshes[i % len(meshes)])
@@ -543,6 +543,11 @@ def secondary_config(name, device, peak, R, with_cpu=True, options=None, sc=None
         ring.SetOption(k, int(v))
     nring = frames * 4
     xf = R.PackedTransform(sc.mv, sc.proj, sc.raster)      # marshalled once: a 20 us frame leaves no room for numpy conversions
+    for lane in ring.lanes:           # size every lane's queues (and let its routing settle) before frames pile up unsynchronised
+        lane.SetTransform(xf)
+        for _ in range(3):
+            lane.RenderMesh(meshes[0])
+            lane.Synchronize()
     for rep in range(2):
         ring.Synchronize()
         tw = time.perf_counter()

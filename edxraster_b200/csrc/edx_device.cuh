@@ -84,6 +84,7 @@ struct Counters {
     uint32_t maxMid;
     uint32_t bigSorted;      // this frame's tile-path list has a nearest-first order (sort_big_kernel)
     uint32_t nMidDiverted;   // mid-size triangles sent down the tile path because mid_kernel was not launched this frame
+    uint32_t nBigDiverted;   // large triangles sent down the warp-per-triangle path because tile_kernel was not launched this frame
     uint32_t frameSerial;    // frames completed on this context (never reset)
     uint32_t nClipMulti;     // straddlers of several planes (back half of the clip queue; nClipQueue counts the single-plane front half)
     uint32_t nWork;          // list front end: triangle clusters that survived cull_kernel this frame
@@ -114,7 +115,8 @@ struct FrameParams {
     int width, height, binsX, binsY;
     int shader, smallMax, smallMaxClip, hiz, hierarchical, captureIds, dump;
     int midMax;              // pixel-centre boxes below this (and not small) are rasterised one warp per triangle; 0 = none
-    int midLaunched;         // mid_kernel is part of this frame (else mid-size triangles take the tile path, which is always there)
+    int midLaunched;         // mid_kernel is part of this frame (else mid-size triangles take the tile path)
+    int tileLaunched;        // tile_kernel is part of this frame (else large triangles take the warp-per-triangle path and lean_resolve_kernel ends the frame)
     int part, parts;         // sort-first split: this context owns the bins b with b % parts == part (parts = 1: all)
     int clusterCull;         // skip whole 256-triangle clusters whose bounding box is outside one clip plane
     int fuseClip;            // clip single-plane straddlers inside geom_kernel instead of queueing them

@@ -292,9 +292,12 @@ __device__ __forceinline__ void route_triangle(const FrameParams& P, const Setup
                 r0 += sC0; r1 += sC1; r2 += sC2;
             }
         }
-    } else if (P.midLaunched && x1 - x0 < P.midMax && y1 - y0 < P.midMax) {
+    } else if (P.midLaunched && ((x1 - x0 < P.midMax && y1 - y0 < P.midMax) || !P.tileLaunched)) {
         // Mid-size triangle: a lone thread would serialise hundreds of pixel tests (and stall its warp), a whole-bin
-        // sweep is too heavy a machine for it. mid_kernel gives it one warp.
+        // sweep is too heavy a machine for it. mid_kernel gives it one warp. (A frame without tile_kernel - the previous
+        // frame of this mesh had no large triangle - sends a large one here as well: correct at any size, slow for a
+        // huge one, and it tells the host to bring the tile kernel back.)
+        if (!P.tileLaunched && !(x1 - x0 < P.midMax && y1 - y0 < P.midMax)) atomicAdd(&P.counters->nBigDiverted, 1u);
         const uint32_t at = warp_append(&P.counters->nMid);
         if (at < P.midCap) {
             int4* dst = reinterpret_cast<int4*>(P.mid + at);
@@ -1794,7 +1797,7 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     // every load first (nine independent L2 reads in flight), then the stores from registers; no fence: the host
     // reads the pinned copy only after the stream has completed this kernel
     volatile Counters* d = P.counters;
-    const uint32_t nBig = d->nBig, nClip1 = d->nClipQueue, nClipN = d->nClipMulti, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid, nMidDiverted = d->nMidDiverted, serial = d->frameSerial + 1u, nBinPairs = d->nBinPairs, binned = d->binned;
+    const uint32_t nBig = d->nBig, nClip1 = d->nClipQueue, nClipN = d->nClipMulti, nClipRecs = d->nClipRecs, nDump = d->nDump, tilePairs = d->tilePairs, nMid = d->nMid, nMidDiverted = d->nMidDiverted, nBigDiverted = d->nBigDiverted, serial = d->frameSerial + 1u, nBinPairs = d->nBinPairs, binned = d->binned;
     // the clip queue is split in two halves (clip_kernel): publish a demand that exceeds the capacity exactly when a half overflowed
     const uint32_t halfQ = P.clipQueueCap / 2u;
     const uint32_t nClipQueue = (nClip1 > halfQ || nClipN > P.clipQueueCap - halfQ) ? 2u * max(nClip1, nClipN) + 2u : nClip1 + nClipN;
@@ -1804,11 +1807,11 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     for (int i = 0; i < 8; i++) { P.hostCounters->dbg[i] = P.counters->dbg[i]; P.counters->dbg[i] = 0; }
 #endif
     if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap || nMid > P.midCap) overFrames++;
-    d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0; d->nMidDiverted = 0; d->bigSorted = 0; d->frameSerial = serial;
+    d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0; d->nMidDiverted = 0; d->nBigDiverted = 0; d->bigSorted = 0; d->frameSerial = serial;
     d->binned = 0; d->binKeyMin = 0; d->binKeyMax = 0; d->nBinPairs = 0; d->binPairs64 = 0;
     d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs; d->maxMid = maxMid;
     volatile Counters* h = P.hostCounters;
-    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid; h->nMidDiverted = nMidDiverted; h->frameSerial = serial; h->nBinPairs = nBinPairs; h->binned = binned; h->midArea = midArea;
+    h->nBig = nBig; h->nClipQueue = nClipQueue; h->nClipRecs = nClipRecs; h->nDump = nDump; h->tilePairs = tilePairs; h->nMid = nMid; h->maxMid = maxMid; h->nMidDiverted = nMidDiverted; h->nBigDiverted = nBigDiverted; h->frameSerial = serial; h->nBinPairs = nBinPairs; h->binned = binned; h->midArea = midArea;
     h->overFrames = overFrames; h->maxBig = maxBig; h->maxClipQueue = maxClipQueue; h->maxClipRecs = maxClipRecs;
 }
 
@@ -1866,7 +1869,7 @@ __global__ void __launch_bounds__(256) lean_resolve_kernel(const __grid_constant
     ulonglong2 kk[4];
     #pragma unroll
     for (int b4 = 0; b4 < 4; b4++) kk[b4] = gk2[b4 * 32 + lane];
-    if (min(P.counters->nBig, P.bigCap) != 0) return;           // the tile path has work: tile_kernel does everything
+    if (P.tileLaunched && min(P.counters->nBig, P.bigCap) != 0) return;      // the tile path has work: tile_kernel does everything
     resolve_tile_direct<DEPTH_ONLY>(P, gk2, kk, tx0, ty0, lane);
 }
 

@@ -66,6 +66,7 @@ struct edx_context {
     uint32_t* bigBox = nullptr; uint32_t bigBoxCap = 0;
     uint32_t* bigOrder = nullptr; uint32_t* bigKey = nullptr; uint32_t* bigBoxSorted = nullptr; uint32_t* bigBound = nullptr; uint32_t bigSortCap = 0;   // nearest-first view (sort_big_kernel)
     int sortBig = 1;                         // edx_set_option("sort_big", 0 | 1)
+    int skipTile = 1;                        // edx_set_option("skip_tile", 0 | 1): frames without large triangles end in lean_resolve_kernel instead of tile_kernel
     bool midShrunk = false; int midAuto = 1;  // edx_set_option("mid_auto", 0 | 1): see enqueue_frame
     int binMin = 16384;                      // edx_set_option("bin_min", n): tile-path lists at least this long get per-bin lists (0 = never)
     uint32_t* binCursor = nullptr; uint32_t* binList = nullptr; uint32_t* binKey = nullptr; uint32_t binCursorCap = 0, binListCap = 0, binKeyCap = 0;
@@ -287,7 +288,7 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
         seq.push_back(LaunchDesc{ (const void*)kernel, grid, block, (uint32_t)smem, which, stage, name });
     };
     const bool textured = c->shader == EDX_SHADER_LAMBERT_ALBEDO && m->nTex != 0;
-    const bool lean = c->msaaLog2 == 0 && (c->leanResolve == 2 || (c->leanResolve == 1 && c->stats.binned_tris == 0));
+    bool lean = c->msaaLog2 == 0 && (c->leanResolve == 2 || (c->leanResolve == 1 && c->stats.binned_tris == 0));
     P.leanResolve = lean ? 1 : 0;
     // tile_kernel resolves depth (+ owner ids); a shaded single-sample frame's colour is a pass of its own over those
     // ids (shade_kernel), so the tile kernel sees the frame as depth-only with id capture (parameter block T)
@@ -327,6 +328,19 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     else if (c->midAuto && c->hostCounters->frameSerial != 0 &&
              ((const volatile Counters*)c->hostCounters)->midArea > 128ull * c->width * c->height) c->midShrunk = true;
     if (c->midShrunk && c->midMax > 32) { P.midMax = 32; T.midMax = 32; }
+    // The tile kernel as well: a frame without large triangles needs it only for the final pass over the keys, and its
+    // CTAs own half an SM each (512 threads x 64 registers, 100 KB of shared memory) while they wait on one 32 KB copy -
+    // no geometry CTA of another frame in flight fits beside them. If the previous frame of this mesh put nothing on the
+    // tile path, lean_resolve_kernel (256-thread CTAs, no shared memory) ends the frame instead. A large triangle that
+    // turns up in such a frame is rasterised by mid_kernel - correct at any size - and reported (nBigDiverted), so the
+    // next frame has the tile kernel again.
+    bool launchTile = true;
+    if (c->skipIdle && c->skipTile && c->hintTris == m->nTris && c->hintVerts == m->nVerts && !dumpBuf && c->msaaLog2 == 0 && c->midMax > 0 && c->leanResolve == 0) {
+        const volatile Counters* h = c->hostCounters;
+        if (h->frameSerial != 0 && h->nBig == 0 && h->nBigDiverted == 0) { launchTile = false; launchMid = true; lean = true; }
+    }
+    P.leanResolve = lean ? 1 : 0; T.leanResolve = P.leanResolve;
+    P.tileLaunched = launchTile ? 1 : 0; T.tileLaunched = P.tileLaunched;
     c->hintTris = m->nTris; c->hintVerts = m->nVerts;
     P.midLaunched = launchMid ? 1 : 0; T.midLaunched = P.midLaunched;
     if (m->nTris) add("clip_kernel", clip_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
@@ -344,7 +358,7 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     if (c->msaaLog2 == 0) {
         if (lean && !shaded && !c->captureIds) add("lean_resolve_kernel", lean_resolve_kernel<true>, leanGrid, dim3(256), 0, 1, 2);
         else if (lean) add("lean_resolve_kernel", lean_resolve_kernel<false>, leanGrid, dim3(256), 0, 1, 2);
-        add("tile_kernel", tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared), 1, 2);
+        if (launchTile) add("tile_kernel", tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared), 1, 2);
         if (shaded) {
             const uint32_t tiles = ((c->width + TILE_PX - 1) / TILE_PX) * ((c->height + TILE_PX - 1) / TILE_PX);   // one CTA each
             if (textured) add("shade_kernel", shade_kernel<true>, dim3(tiles), dim3(256), 0, 0, 2);
@@ -753,6 +767,7 @@ int edx_set_option(edx_context* c, const char* name, int value)
     if (!strcmp(name, "skip_idle")) { c->skipIdle = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "sort_big")) { c->sortBig = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "bin_min")) { c->binMin = value; return EDX_OK; }
+    if (!strcmp(name, "skip_tile")) { c->skipTile = value ? 1 : 0; return EDX_OK; }
     if (!strcmp(name, "mid_auto")) { c->midAuto = value ? 1 : 0; c->midShrunk = false; return EDX_OK; }
     if (!strcmp(name, "graphs")) { if (value < 0 || value > 2) return fail(c, EDX_ERR_INVALID, "graphs: 0 never, 1 small meshes, 2 always"); c->useGraphs = value; return EDX_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return EDX_OK; }

@@ -689,10 +689,12 @@ def test_m1_mid_size_stress_every_routing():
     assert got["stats"]["mid_tris"] + got["stats"]["binned_tris"] > 50000
 
 
-def test_idle_kernels_are_left_out_safely():
-    # mid_kernel / sort_big_kernel are left out of a frame when the previous frame of the same mesh had no work for them
-    # (skip_idle). Same mesh, three views: far away (every triangle tiny), close up (mid-size and large triangles appear in
-    # a frame that has no mid_kernel: they must take the tile path), close up again (mid_kernel is back). All three exact.
+@pytest.mark.parametrize("skip_tile", [1, 0])
+def test_idle_kernels_are_left_out_safely(skip_tile):
+    # mid_kernel / sort_big_kernel / tile_kernel are left out of a frame when the previous frame of the same mesh had no
+    # work for them (skip_idle, skip_tile). Same mesh, five views: far away twice (every triangle tiny), then close up
+    # three times: mid-size and large triangles appear in a frame that lacks the kernel meant for them and must take the
+    # other path (without mid_kernel: the tile path; without tile_kernel: mid_kernel, at any size). All five exact.
     import copy
     from edxraster_b200 import camera as cam, renderer as R
     base = scenes.config1(width=640, height=360, slices=80, stacks=80)
@@ -700,8 +702,9 @@ def test_idle_kernels_are_left_out_safely():
     r.Initialize(base.width, base.height)
     r.SetCaptureIds(True)
     r.SetPixelShader(1)
+    r.SetOption("skip_tile", skip_tile)
     m = r.CreateMesh(base.vertices, base.indices)
-    launches = []
+    launches, stats = [], []
     for eye_z in (-60.0, -60.0, -1.6, -1.6, -1.6):
         c = cam.Camera((0.0, 0.0, eye_z), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), base.width, base.height, 65.0, 0.01, 100.0)
         sc = copy.copy(base)
@@ -710,8 +713,17 @@ def test_idle_kernels_are_left_out_safely():
         r.RenderMesh(m)
         got = {"color": r.GetBackBuffer().copy(), "depth": r.GetDepthBuffer(), "winner": r.GetWinnerIds(), "derived": r.DerivedState()}
         launches.append(r.LastLaunchList())
+        stats.append(r.GetStats())
         rep = parity.compare(parity.render_oracle(sc), got)
         assert parity.is_parity(rep), (eye_z, rep)
-    assert "mid_kernel" in launches[0] and "mid_kernel" not in launches[1]       # frame 0 had no mid-size triangle
-    assert "mid_kernel" not in launches[2] and "mid_kernel" in launches[3]       # frame 2 diverted some: back in frame 3
+    if skip_tile:
+        assert "tile_kernel" in launches[0] and "mid_kernel" in launches[0]
+        # frame 0 put nothing on the tile path: frames 1 and 2 end in lean_resolve_kernel, with mid_kernel as the catch-all
+        for i in (1, 2):
+            assert "tile_kernel" not in launches[i] and "lean_resolve_kernel" in launches[i] and "mid_kernel" in launches[i], launches[i]
+        # frame 2 (close up) had large triangles: the tile kernel is back, and they are on its path
+        assert "tile_kernel" in launches[3] and "tile_kernel" in launches[4] and stats[3]["binned_tris"] > 0
+    else:
+        assert "mid_kernel" in launches[0] and "mid_kernel" not in launches[1]       # frame 0 had no mid-size triangle
+        assert "mid_kernel" not in launches[2] and "mid_kernel" in launches[3]       # frame 2 diverted some: back in frame 3
     r.close()
