@@ -353,8 +353,10 @@ __device__ __forceinline__ void queue_straddler(const FrameParams& P, uint32_t t
 // Stages a1, a2, a5, a6 for one submitted triangle with its vertex work done per corner (front end 0 / 1), then routing.
 __device__ __forceinline__ void geom_triangle(const FrameParams& P, uint32_t t)
 {
-    uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
-    float4 p0 = __ldg(P.pos4 + i0), p1 = __ldg(P.pos4 + i1), p2 = __ldg(P.pos4 + i2);
+    // streaming loads (evict-first): the geometry is read once per frame and must not push the visibility keys, which
+    // every path hits with atomics and the final pass reads back, out of the L2
+    uint32_t i0 = __ldcs(P.i0 + t), i1 = __ldcs(P.i1 + t), i2 = __ldcs(P.i2 + t);
+    float4 p0 = __ldcs(P.pos4 + i0), p1 = __ldcs(P.pos4 + i1), p2 = __ldcs(P.pos4 + i2);
     V4 c0 = to_clip(P.mvp, p0.x, p0.y, p0.z);
     V4 c1 = to_clip(P.mvp, p1.x, p1.y, p1.z);
     V4 c2 = to_clip(P.mvp, p2.x, p2.y, p2.z);
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(256) vertex_kernel(const __grid_constant__ Fra
         if (P.vcFlag[vc]) continue;                     // every vertex of it is outside one plane: the flag stands in for the records
         const uint32_t v = vc * 256u + threadIdx.x;
         if (v >= P.nVerts) continue;
-        const float4 p = __ldg(P.pos4 + v);
+        const float4 p = __ldcs(P.pos4 + v);          // (streaming: read once per frame)
         const V4 c = to_clip(P.mvp, p.x, p.y, p.z);                          // a1
         const uint32_t code = surely_inside(c) ? 0u : clip_code(c);         // a2
         int4 rec;
@@ -517,7 +519,7 @@ __device__ __forceinline__ int4 load_vrec(const FrameParams& P, uint32_t i)
 // project_snap / inv_w / z*invW compute depends on the vertex only - so the results are bit-identical.
 __device__ __forceinline__ void geom_triangle_vrec(const FrameParams& P, uint32_t t)
 {
-    const uint32_t i0 = __ldg(P.i0 + t), i1 = __ldg(P.i1 + t), i2 = __ldg(P.i2 + t);
+    const uint32_t i0 = __ldcs(P.i0 + t), i1 = __ldcs(P.i1 + t), i2 = __ldcs(P.i2 + t);      // (streaming: read once per frame)
     const int4 r0 = load_vrec(P, i0), r1 = load_vrec(P, i1), r2 = load_vrec(P, i2);
     const uint32_t k0 = vrec_code(r0.w), k1 = vrec_code(r1.w), k2 = vrec_code(r2.w);
     if (k0 | k1 | k2) {
