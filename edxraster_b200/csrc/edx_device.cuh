@@ -88,7 +88,6 @@ struct Counters {
     uint32_t frameSerial;    // frames completed on this context (never reset)
     uint32_t nClipMulti;     // straddlers of several planes (back half of the clip queue; nClipQueue counts the single-plane front half)
     uint32_t nWork;          // list front end: triangle clusters that survived cull_kernel this frame
-    uint32_t ticket;         // list front end: work items handed out beyond the first gridDim.x
     // per-bin lists of the tile path (bin_*_kernel): valid this frame, range of the depth keys, (triangle, bin) pairs wanted
     uint32_t binned, binKeyMin, binKeyMax, nBinPairs;      // (binKeyMin is kept complemented: zero is its identity)
     unsigned long long binPairs64;

@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(256, 5) geom_kernel(const __grid_constant__ Fr
 //                     stall samples on the 10M-triangle grid); here culled clusters cost one thread each.
 //   vertex_kernel     stages a1, a2, a5 (project, raster transform, snap), a6 once per vertex of every unflagged
 //                     vertex cluster (Renderer::VertexProcessing is per vertex too, Renderer.cpp:120-127) -> vrec.
-//   geom_list_kernel  persistent: CTAs take surviving clusters off the list (static first item, then tickets).
+//   geom_list_kernel  persistent: CTA b walks surviving clusters b, b + gridDim.x, ... (no barrier: each warp its own slice).
 // ---------------------------------------------------------------------------------------------
 // Clip planes that ALL eight corners of the box are outside of, by a margin that dominates the fp32 rounding of the
 // transform of any point in the box: every vertex inside the box then has that bit in its clip code. 0 for an
@@ -511,8 +511,11 @@ __global__ void __launch_bounds__(256) vertex_kernel(const __grid_constant__ Fra
 
 __device__ __forceinline__ int4 load_vrec(const FrameParams& P, uint32_t i)
 {
+    // both loads are issued together (a culled cluster's records are stale, not unmapped): index -> flag -> record as a
+    // dependent chain was a third of geom_list_kernel's stall samples on the 10M-triangle grid
     const uint32_t f = __ldg(P.vcFlag + (i >> 8));
-    return f ? make_int4(0, 0, 0, (int)(VREC_OUTSIDE | f)) : __ldg(P.vrec + i);
+    const int4 r = __ldg(P.vrec + i);
+    return f ? make_int4(0, 0, 0, (int)(VREC_OUTSIDE | f)) : r;
 }
 
 // One submitted triangle from the per-vertex records (front end 2). Same arithmetic as geom_triangle - what
@@ -549,20 +552,17 @@ __device__ __forceinline__ void geom_triangle_vrec(const FrameParams& P, uint32_
 template <bool VREC>
 __global__ void __launch_bounds__(256, 5) geom_list_kernel(const __grid_constant__ FrameParams P)
 {
-    __shared__ uint32_t sNext;
     cudaGridDependencySynchronize();
     const uint32_t n = P.counters->nWork;
-    uint32_t cur = blockIdx.x;
-    while (cur < n) {
-        if (threadIdx.x == 0) sNext = atomicAdd(&P.counters->ticket, 1u) + gridDim.x;   // fetched while this cluster is processed
+    // Static round robin, no barrier: the surviving clusters of a frame are many per CTA and alike, and a ticket per
+    // cluster meant two CTA barriers around it - the warps of a CTA waited for the slowest at every cluster (a fifth of
+    // the kernel's stall samples). Each warp now walks its 32-triangle slice of the CTA's clusters on its own.
+    for (uint32_t cur = blockIdx.x; cur < n; cur += gridDim.x) {
         const uint32_t t = __ldg(P.workList + cur) * 256u + threadIdx.x;
         if (t < P.nTris) {
             if (VREC) geom_triangle_vrec(P, t);
             else geom_triangle(P, t);
         }
-        __syncthreads();
-        cur = sNext;
-        __syncthreads();
     }
 }
 
@@ -1809,7 +1809,7 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     for (int i = 0; i < 8; i++) { P.hostCounters->dbg[i] = P.counters->dbg[i]; P.counters->dbg[i] = 0; }
 #endif
     if (nBig > P.bigCap || nClipQueue > P.clipQueueCap || nClipRecs > P.clipRecCap || nMid > P.midCap) overFrames++;
-    d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->ticket = 0; d->nMidDiverted = 0; d->nBigDiverted = 0; d->bigSorted = 0; d->frameSerial = serial;
+    d->nBig = 0; d->nClipQueue = 0; d->nClipMulti = 0; d->nClipRecs = 0; d->nDump = 0; d->nMid = 0; d->tilePairs = 0; d->nWork = 0; d->nMidDiverted = 0; d->nBigDiverted = 0; d->bigSorted = 0; d->frameSerial = serial;
     d->binned = 0; d->binKeyMin = 0; d->binKeyMax = 0; d->nBinPairs = 0; d->binPairs64 = 0;
     d->overFrames = overFrames; d->maxBig = maxBig; d->maxClipQueue = maxClipQueue; d->maxClipRecs = maxClipRecs; d->maxMid = maxMid;
     volatile Counters* h = P.hostCounters;
