@@ -315,8 +315,11 @@ class Farm:
     NVLink, and each lane's context has its slot of it as frame sink (edx_set_frame_sink): right behind a frame's
     last kernel, on the lane's own stream, the COPY ENGINE pushes the finished buffer to rank 0 (no SM time, no host
     work; nothing waits for a batch to fill, so the only transfer that cannot overlap rendering is the last
-    frame's). One 4-byte all-reduce per G frames tells rank 0 that they have landed and lets the lanes reuse the
-    buffers two batches later.
+    frame's). Behind the push the context stores the number of frames it has pushed into a count word in rank 0's
+    memory (edx_set_frame_sink_signal) - what a consumer there polls. No collective and no batches: each lane cycles
+    two slots of the store, and its own stream orders a slot's reuse behind the previous push. (Until round 2's last
+    change a 4-byte NCCL all-reduce per 4 frames did the notification; its host cost - launch, event, three
+    stream waits - made the farm host-bound at 50 us per frame.)
     --gather nccl: dist.gather per batch of G frames. --gather stores: the resolve kernel writes its pixels straight
     into rank 0's memory (measured slower: 32-byte row segments). --gather none: diagnosis only."""
 
@@ -353,14 +356,28 @@ class Farm:
         self.result = self.tgt_color if self.shaded else self.tgt_depth
         self.frame_bytes = W * H * 4
         self.peer, self.recv, self.mode = None, None, mode
+        self.S = 2                        # --gather ce: slots per lane in rank 0's frame store (a lane's pushes are stream-ordered)
+        self.pushed = [0] * K
         if world > 1 and mode in ("stores", "ce"):
             try:
                 import torch.distributed._symmetric_memory as symm
-                sbuf = symm.empty((world, 2, G) + tuple(self.result[0].shape[1:]), dtype=self.result[0].dtype, device=dev)
+                shape = (world, K, self.S) if mode == "ce" else (world, 2, G)
+                sbuf = symm.empty(shape + tuple(self.result[0].shape[1:]), dtype=self.result[0].dtype, device=dev)
                 hdl = symm.rendezvous(sbuf, dist.group.WORLD)
                 self.sbuf = sbuf
                 self.peer = hdl.get_buffer(0, sbuf.shape, sbuf.dtype)      # rank 0's buffer, addressable from this GPU
                 self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+                if mode == "ce":
+                    # rank 0's count words, one per (rank, lane): edx_set_frame_sink_signal stores the number of frames
+                    # pushed so far behind every frame's pushes - what a consumer on rank 0 polls; no collective
+                    self.counts = symm.empty((world, K), dtype=torch.int32, device=dev)
+                    self.counts.zero_()
+                    torch.cuda.synchronize()
+                    hdl2 = symm.rendezvous(self.counts, dist.group.WORLD)
+                    peer_counts = hdl2.get_buffer(0, self.counts.shape, self.counts.dtype)
+                    dist.barrier()
+                    for l, (_, lr) in enumerate(self.lanes):
+                        lr.SetFrameSinkSignal(peer_counts[rank, l].data_ptr())
             except Exception as e:       # pragma: no cover
                 log("symmetric memory unavailable (%s): using NCCL gather" % e)
                 self.peer = None
@@ -371,7 +388,7 @@ class Farm:
         # device addresses, looked up once: tensor indexing costs more host time than a frame takes
         self.cptr = [[self.tgt_color[b][k].data_ptr() for k in range(G)] for b in range(2)]
         self.dptr = [[self.tgt_depth[b][k].data_ptr() for k in range(G)] for b in range(2)]
-        self.pptr = None if self.peer is None else [[self.peer[rank, b, k].data_ptr() for k in range(G)] for b in range(2)]
+        self.pptr = None if self.peer is None else [[self.peer[rank, b, k].data_ptr() for k in range(self.peer.shape[2])] for b in range(self.peer.shape[1])]
 
     # -- exchange ---------------------------------------------------------------------------------
     def notify(self, b, n, works):
@@ -396,6 +413,23 @@ class Farm:
 
     def step(self, i, works, nl):
         G, world, rank = self.G, self.world, self.rank
+        if world > 1 and self.mode == "ce":
+            # the copy engine pushes the finished frame into this lane's next slot of rank 0's store and the count word
+            # follows it; the lane's stream orders a slot's reuse behind its previous push: no batches, no collective
+            l = i % nl
+            ls, lr = self.lanes[l]
+            dst = self.pptr[l][(i // nl) % self.S]
+            if rank == 0 and not os.environ.get("EDX_BENCH_RANK0_SINK"):      # the store is rank 0's own memory: its frames are rendered in place
+                lr.SetRenderTarget(dst if self.shaded else 0, 0 if self.shaded else dst)
+            else:
+                lr.SetFrameSink(dst if self.shaded else 0, 0 if self.shaded else dst)
+            if self.views is not None:
+                lr.SetTransform(self.views[(i * world + rank) % len(self.views)])    # C5: view v is rendered by rank v mod N
+            else:
+                lr.SetTransform(self.xf)
+            lr.RenderMesh(self.meshes[i % len(self.meshes)])
+            self.pushed[l] += 1
+            return
         b, k = (i // G) & 1, i % G
         ls, lr = self.lanes[i % nl]
         if k == 0 and works[b] is not None:
@@ -421,7 +455,7 @@ class Farm:
 
     def flush(self, n_steps, works, nl):
         """exchange the frames of a trailing partial batch, then wait for everything in flight"""
-        if n_steps % self.G and self.world > 1:
+        if n_steps % self.G and self.world > 1 and self.mode != "ce":
             for s2, _ in self.lanes[:nl]:
                 self.stream.wait_stream(s2)
             self.notify((n_steps // self.G) & 1, n_steps % self.G, works)
@@ -461,8 +495,10 @@ class Farm:
                 s2.wait_stream(stream)
             for i in range(steps):
                 self.step(i, works, nl)
+            self.host_submit_ms = (time.perf_counter() - t0) * 1e3      # host time to enqueue the timed steps (not a result: says whether the loop is host-bound)
             self.flush(steps, works, nl)
-            for s2, _ in self.lanes[:nl]:
+            for s2, lr in self.lanes[:nl]:
+                lr.FlushFrameSink()               # the lane's stream waits for its pushes: they are inside the timed region
                 stream.wait_stream(s2)
             ev1.record(stream)
             torch.cuda.synchronize()
@@ -471,7 +507,14 @@ class Farm:
                 dist.barrier()
             ms = ev0.elapsed_time(ev1)
             self.sync_lanes()
+            if world > 1 and self.mode == "ce" and self.peer is not None and self.rank == 0:
+                # every rank ran the same schedule: rank 0's count words must show each lane's pushes, of every rank
+                got = self.counts.cpu().tolist()
+                if any(row != self.pushed for row in got):
+                    raise RuntimeError("frame gather incomplete: counts on rank 0 %s, expected %s per rank" % (got, self.pushed))
             if world > 1:
+                if os.environ.get("EDX_BENCH_RANK_TIMES"):
+                    sys.stderr.write("[bench] rank %d: %.4f ms for %d steps, %d in flight\n" % (self.rank, ms, steps, nl))
                 t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t.item())
@@ -498,7 +541,7 @@ class Farm:
             return "none (1 GPU)"
         what = "colour" if self.shaded else "depth"
         return {"stores": "every finished %s buffer lands on rank 0 by NVLink peer stores from the resolve kernel itself (symmetric memory), one 4-byte all-reduce per %d frames",
-                "ce": "every finished %s buffer is pushed into rank 0's symmetric-memory buffer over NVLink by the copy engine right behind the frame's last kernel (edx_set_frame_sink: one D2D copy per frame on the lane's stream, no SM time, no host work); a 4-byte all-reduce per %d frames tells rank 0 they have landed",
+                "ce": "every finished %s buffer is pushed into rank 0's symmetric-memory frame store over NVLink by the copy engine right behind the frame's last kernel (edx_set_frame_sink: one D2D copy per frame on the lane's stream, no SM time, no host work), followed by a 4-byte count in rank 0's memory (edx_set_frame_sink_signal) that a consumer polls: no collective, no batches (%d unused); each lane cycles 2 slots, rank 0 checks the counts after the run",
                 "none": "NOT GATHERED (--gather none, diagnosis only) %s %d",
                 "nccl": "NCCL gather of every finished %s buffer to rank 0, per batch of %d frames, overlapped with the next batch"}[self.mode] % (what, self.G)
 
@@ -660,6 +703,7 @@ def ours_arm(args):
     # same number of exchanges)
     n_warm = ((max(args.warmup, 3) + 1000 + G - 1) // G) * G
     ms_total, t0, t1 = farm.timed_run(K, args.steps, n_warm)
+    host_submit_ms = farm.host_submit_ms / args.steps
     sampler.stop()
     launches_per_step = r.LastLaunchCount()
     launch_list = r.LastLaunchList()
@@ -789,7 +833,8 @@ def ours_arm(args):
         "execution": {"frames_in_flight_per_gpu": K,
                       "in_flight": "each GPU keeps %d independent frames in flight (contexts on their own streams sharing the meshes); "
                                    "every frame is rendered completely and, at N > 1, gathered inside the timed region" % K,
-                      "gather": gather_text},
+                      "gather": gather_text,
+                      "host_submit_ms_per_step": host_submit_ms},        # rank 0's host time to enqueue one step; close to ms_per_step = host-bound
         "frames_per_s": world * 1000.0 / ms_step, "gpix_per_s": world * W * H / ms_step / 1e6,
         "one_frame_in_flight": None if ms_one is None else {"ms_per_step": ms_one, "value": world * nt / ms_one / 1e3},
         "clocks": sampler.summary(t0, t1),

@@ -17,7 +17,7 @@ SYMBOLS = [
     "edx_write_frame_to_file", "edx_set_pixel_shader", "edx_set_albedo", "edx_mesh_create", "edx_mesh_update",
     "edx_mesh_destroy", "edx_render_mesh", "edx_get_back_buffer", "edx_synchronize", "edx_read_depth",
     "edx_set_capture_ids", "edx_read_winner_ids", "edx_read_sample", "edx_debug_clip_vertices", "edx_debug_raster_triangles",
-    "edx_get_derived_state", "edx_device_color", "edx_device_depth", "edx_set_render_target", "edx_set_frame_sink", "edx_device_count", "edx_enable_peer_access", "edx_device_alloc", "edx_device_free", "edx_read_device", "edx_set_screen_partition", "edx_set_stream", "edx_timer_begin",
+    "edx_get_derived_state", "edx_device_color", "edx_device_depth", "edx_set_render_target", "edx_set_frame_sink", "edx_set_frame_sink_signal", "edx_flush_frame_sink", "edx_device_count", "edx_enable_peer_access", "edx_device_alloc", "edx_device_free", "edx_read_device", "edx_set_screen_partition", "edx_set_stream", "edx_timer_begin",
     "edx_timer_end", "edx_set_profiling", "edx_get_stats", "edx_set_option", "edx_last_launch_count", "edx_last_launch_list",
     "edx_mesh_set_textures", "edx_mesh_read_texture_level", "edx_debug_tile_residency",
 ]
@@ -93,6 +93,8 @@ def load():
     lib.edx_device_depth.restype = vp
     lib.edx_set_render_target.argtypes = [vp, vp, vp]
     lib.edx_set_frame_sink.argtypes = [vp, vp, vp]
+    lib.edx_set_frame_sink_signal.argtypes = [vp, vp]
+    lib.edx_flush_frame_sink.argtypes = [vp]
     lib.edx_enable_peer_access.argtypes = [vp, C.c_int]
     lib.edx_device_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
     lib.edx_device_free.argtypes = [vp, vp]

@@ -1817,6 +1817,15 @@ __global__ void frame_end_kernel(const __grid_constant__ FrameParams P)
     h->overFrames = overFrames; h->maxBig = maxBig; h->maxClipQueue = maxClipQueue; h->maxClipRecs = maxClipRecs;
 }
 
+// edx_set_frame_sink_signal: runs behind the copy-engine pushes of a finished frame (same stream) and publishes the
+// number of frames pushed so far where the consumer - usually another GPU - can poll it.
+__global__ void sink_signal_kernel(uint32_t* word, uint32_t serial)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(word) = serial;
+    __threadfence_system();
+}
+
 // A 16x16 tile whose pixels were all decided by the direct (small-triangle) path: turn its keys, already in
 // registers, into depth / ids / colour and leave the key buffer clean for the next frame. One warp per tile.
 template <bool DEPTH_ONLY>             // true: the caller guarantees a depth-only frame without id capture (no shading code at all)

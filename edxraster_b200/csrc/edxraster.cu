@@ -62,6 +62,10 @@ struct edx_context {
     uchar4* color = nullptr; float* depth = nullptr; uint32_t* ids = nullptr;
     uchar4* extColor = nullptr; float* extDepth = nullptr;      // caller-owned render targets (optional)
     void* sinkColor = nullptr; void* sinkDepth = nullptr;       // edx_set_frame_sink: where the copy engine pushes each finished frame
+    uint32_t* sinkSignal = nullptr; uint32_t sinkSerial = 0;    // edx_set_frame_sink_signal: word that receives the count of frames pushed so far
+    // The pushes run on a stream of their own, behind the frame that produced the buffers; the NEXT frame's geometry and
+    // clipping proceed meanwhile and only its final pass, which overwrites the buffers, waits for the push (evPushDone).
+    cudaStream_t sinkStream = nullptr; cudaEvent_t evFrameDone = nullptr, evPushDone = nullptr; bool pushPending = false;
     BigRec* big = nullptr; uint32_t bigCap = 0;
     uint32_t* bigBox = nullptr; uint32_t bigBoxCap = 0;
     uint32_t* bigOrder = nullptr; uint32_t* bigKey = nullptr; uint32_t* bigBoxSorted = nullptr; uint32_t* bigBound = nullptr; uint32_t bigSortCap = 0;   // nearest-first view (sort_big_kernel)
@@ -85,7 +89,7 @@ struct edx_context {
     struct Submitted {
         edx_host::Mat4 mvp, raster; float eye[3], light[3], albedo[3];
         int shader, texFilter, hierarchical, captureIds, part, parts;
-        uchar4* extColor; float* extDepth; void* sinkColor; void* sinkDepth;
+        uchar4* extColor; float* extDepth; void* sinkColor; void* sinkDepth; uint32_t* sinkSignal; uint32_t sinkSerial;
     } submitted;
     const edx_mesh* lastMesh = nullptr;
     bool framePending = false;
@@ -273,7 +277,13 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     if (fe == 2) P.vrec = c->vrec;
     if (dumpBuf) { P.dump = 1; P.dumpBuf = dumpBuf; P.dumpCap = dumpCap; }
 
+    auto wait_for_push = [&]() -> cudaError_t {       // before anything of this frame writes colour or depth
+        if (!c->pushPending) return cudaSuccess;
+        c->pushPending = false;
+        return cudaStreamWaitEvent(c->stream, c->evPushDone, 0);
+    };
     if (c->shader == EDX_SHADER_DEPTH_ONLY && c->colorDirty) {
+        EDX_CUDA(c, wait_for_push());
         // depth-only frames never touch colour: restore the cleared state once (FrameBuffer.cpp:91-95)
         EDX_CUDA(c, cudaMemsetAsync(c->extColor ? c->extColor : c->color, 0, (size_t)c->width * c->height * 4, c->stream));
         c->colorDirty = false;
@@ -433,22 +443,41 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
                 EDX_CUDA(c, cudaGraphExecKernelNodeSetParams(c->graphExec, c->graphNodes[i], &np));
             }
         }
-        if (viaGraph) EDX_CUDA(c, cudaGraphLaunch(c->graphExec, c->stream));
+        if (viaGraph) { EDX_CUDA(c, wait_for_push()); EDX_CUDA(c, cudaGraphLaunch(c->graphExec, c->stream)); }
     }
     if (!viaGraph) {
         int stage = 0;
         if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[0], c->stream));
         for (const LaunchDesc& d : seq) {
             while (c->profiling && stage < d.stage) EDX_CUDA(c, cudaEventRecord(c->evStage[++stage], c->stream));
+            if (d.stage == 2) EDX_CUDA(c, wait_for_push());      // the final pass overwrites the buffers a previous frame's push may still read
             EDX_CUDA(c, launch_one(d));
         }
         while (c->profiling && stage < 2) EDX_CUDA(c, cudaEventRecord(c->evStage[++stage], c->stream));
     }
     // frame sink (edx_set_frame_sink): the copy engine pushes the finished buffers, e.g. into the root GPU's memory over NVLink
-    if (c->sinkColor && c->shader != EDX_SHADER_DEPTH_ONLY && c->msaaLog2 == 0)
-        EDX_CUDA(c, cudaMemcpyAsync(c->sinkColor, P.color, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToDevice, c->stream));
-    if (c->sinkDepth && c->msaaLog2 == 0)
-        EDX_CUDA(c, cudaMemcpyAsync(c->sinkDepth, P.depth, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToDevice, c->stream));
+    const bool pushColor = c->sinkColor && c->shader != EDX_SHADER_DEPTH_ONLY && c->msaaLog2 == 0, pushDepth = c->sinkDepth && c->msaaLog2 == 0;
+    cudaStream_t tail = c->stream;                    // where the signal goes: behind the pushes, or behind the frame
+    if (pushColor || pushDepth) {
+        if (!c->sinkStream) {
+            EDX_CUDA(c, cudaStreamCreateWithFlags(&c->sinkStream, cudaStreamNonBlocking));
+            EDX_CUDA(c, cudaEventCreateWithFlags(&c->evFrameDone, cudaEventDisableTiming));
+            EDX_CUDA(c, cudaEventCreateWithFlags(&c->evPushDone, cudaEventDisableTiming));
+        }
+        EDX_CUDA(c, cudaEventRecord(c->evFrameDone, c->stream));
+        EDX_CUDA(c, cudaStreamWaitEvent(c->sinkStream, c->evFrameDone, 0));
+        if (pushColor) EDX_CUDA(c, cudaMemcpyAsync(c->sinkColor, P.color, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToDevice, c->sinkStream));
+        if (pushDepth) EDX_CUDA(c, cudaMemcpyAsync(c->sinkDepth, P.depth, (size_t)c->width * c->height * 4, cudaMemcpyDeviceToDevice, c->sinkStream));
+        tail = c->sinkStream;
+    }
+    // ... and a one-thread kernel behind the pushes publishes how many frames this context has finished and pushed
+    // (system-scope store into the same GPU's or a peer's memory): what a consumer on the root GPU polls instead of a
+    // collective. (No sink needed: the root's own contexts render straight into the store, edx_set_render_target.)
+    if (c->sinkSignal && c->msaaLog2 == 0) {
+        sink_signal_kernel<<<1, 1, 0, tail>>>(c->sinkSignal, c->sinkSerial);
+        c->launches++; c->launchList += ",sink_signal_kernel";
+    }
+    if (pushColor || pushDepth) { EDX_CUDA(c, cudaEventRecord(c->evPushDone, c->sinkStream)); c->pushPending = true; }
     if (c->profiling) EDX_CUDA(c, cudaEventRecord(c->evStage[3], c->stream));
     EDX_CUDA(c, cudaGetLastError());
     return EDX_OK;
@@ -484,7 +513,7 @@ void save_submitted(edx_context* c, edx_context::Submitted& s)
     memcpy(s.eye, c->eye, 12); memcpy(s.light, c->light, 12); memcpy(s.albedo, c->albedo, 12);
     s.shader = c->shader; s.texFilter = c->texFilter; s.hierarchical = c->hierarchical; s.captureIds = c->captureIds;
     s.part = c->part; s.parts = c->parts;
-    s.extColor = c->extColor; s.extDepth = c->extDepth; s.sinkColor = c->sinkColor; s.sinkDepth = c->sinkDepth;
+    s.extColor = c->extColor; s.extDepth = c->extDepth; s.sinkColor = c->sinkColor; s.sinkDepth = c->sinkDepth; s.sinkSignal = c->sinkSignal; s.sinkSerial = c->sinkSerial;
 }
 
 void load_submitted(edx_context* c, const edx_context::Submitted& s)
@@ -493,12 +522,13 @@ void load_submitted(edx_context* c, const edx_context::Submitted& s)
     memcpy(c->eye, s.eye, 12); memcpy(c->light, s.light, 12); memcpy(c->albedo, s.albedo, 12);
     c->shader = s.shader; c->texFilter = s.texFilter; c->hierarchical = s.hierarchical; c->captureIds = s.captureIds;
     c->part = s.part; c->parts = s.parts;
-    c->extColor = s.extColor; c->extDepth = s.extDepth; c->sinkColor = s.sinkColor; c->sinkDepth = s.sinkDepth;
+    c->extColor = s.extColor; c->extDepth = s.extDepth; c->sinkColor = s.sinkColor; c->sinkDepth = s.sinkDepth; c->sinkSignal = s.sinkSignal; c->sinkSerial = s.sinkSerial;
 }
 
 int finish_frame(edx_context* c)
 {
     EDX_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->sinkStream) EDX_CUDA(c, cudaStreamSynchronize(c->sinkStream));      // a synchronised frame has also been pushed
     if (!c->framePending) return EDX_OK;
     uint32_t repaired = 0;
     for (int attempt = 0; attempt < 8; attempt++) {
@@ -665,6 +695,9 @@ void edx_destroy(edx_context* c)
     if (c->hostCounters) cudaFreeHost(c->hostCounters);
     for (auto& e : c->evTimer) if (e) cudaEventDestroy(e);
     for (auto& e : c->evStage) if (e) cudaEventDestroy(e);
+    if (c->evFrameDone) cudaEventDestroy(c->evFrameDone);
+    if (c->evPushDone) cudaEventDestroy(c->evPushDone);
+    if (c->sinkStream) cudaStreamDestroy(c->sinkStream);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -946,6 +979,7 @@ int edx_render_mesh(edx_context* c, const edx_mesh* m)
     if (int r = bind(c)) return r;
     c->lastMesh = m;
     c->stats.submitted_tris = m->nTris;
+    c->sinkSerial++;                 // (a frame that has to be re-run after a queue overflow keeps its number)
     save_submitted(c, c->submitted);
     if (int r = enqueue_frame(c, m, nullptr, 0)) return r;
     c->framePending = true;
@@ -1140,6 +1174,23 @@ int edx_set_frame_sink(edx_context* c, void* color, void* depth)
     if ((color || depth) && c->msaaLog2 != 0) return fail(c, EDX_ERR_UNSUPPORTED, "frame sinks are single-sample only");
     c->sinkColor = color;
     c->sinkDepth = depth;
+    return EDX_OK;
+}
+
+int edx_flush_frame_sink(edx_context* c)
+{
+    if (!c) return EDX_ERR_INVALID;
+    if (int r = bind(c)) return r;
+    if (c->pushPending) { c->pushPending = false; EDX_CUDA(c, cudaStreamWaitEvent(c->stream, c->evPushDone, 0)); }
+    return EDX_OK;
+}
+
+int edx_set_frame_sink_signal(edx_context* c, void* word)
+{
+    if (!c) return EDX_ERR_INVALID;
+    if (word && ((uintptr_t)word & 3u)) return fail(c, EDX_ERR_INVALID, "the signal word must be 4-byte aligned");
+    c->sinkSignal = (uint32_t*)word;
+    c->sinkSerial = 0;
     return EDX_OK;
 }
 

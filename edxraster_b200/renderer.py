@@ -216,6 +216,29 @@ class Renderer:
         memory) with the copy engine, stream-ordered behind the frame: the frame-parallel gather."""
         self._check(self._lib.edx_set_frame_sink(self._h, C.c_void_p(color_ptr or None), C.c_void_p(depth_ptr or None)))
 
+    def DeviceAlloc(self, nbytes):
+        """Device memory on this context's GPU (e.g. a frame store for SetFrameSink); returns the address."""
+        out = C.c_void_p()
+        self._check(self._lib.edx_device_alloc(self._h, C.c_size_t(nbytes), C.byref(out)))
+        return out.value
+
+    def DeviceFree(self, ptr):
+        self._check(self._lib.edx_device_free(self._h, C.c_void_p(ptr)))
+
+    def ReadDevice(self, ptr, nbytes):
+        """Stream-ordered copy of device memory to a new numpy byte array (synchronises)."""
+        host = np.empty(nbytes, dtype=np.uint8)
+        self._check(self._lib.edx_read_device(self._h, host.ctypes.data_as(C.c_void_p), C.c_void_p(ptr), C.c_size_t(nbytes)))
+        return host
+
+    def SetFrameSinkSignal(self, word_ptr):
+        """Behind every frame's pushes the context stores the number of frames pushed so far to this device address."""
+        self._check(self._lib.edx_set_frame_sink_signal(self._h, C.c_void_p(word_ptr or None)))
+
+    def FlushFrameSink(self):
+        """The context's stream waits (on the device) for every push issued so far."""
+        self._check(self._lib.edx_flush_frame_sink(self._h))
+
     def ReadDepthInto(self, host_ptr):
         """Copy the depth buffer to caller memory (pinned for full PCIe speed); synchronises."""
         self._check(self._lib.edx_read_depth(self._h, C.cast(C.c_void_p(host_ptr), C.POINTER(C.c_float))))

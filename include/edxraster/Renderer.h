@@ -516,6 +516,9 @@ public:
     void Synchronize() { Call(edx_synchronize(mCtx)); }
     // frame-parallel gather: every finished frame is pushed to these device addresses (own or peer-mapped) by the copy engine
     void SetFrameSink(void* remoteColor, void* remoteDepth) { Call(edx_set_frame_sink(mCtx, remoteColor, remoteDepth)); }
+    // ... and the count of frames pushed so far, stored behind every frame's pushes where the consumer can poll it
+    void SetFrameSinkSignal(void* remoteWord) { Call(edx_set_frame_sink_signal(mCtx, remoteWord)); }
+    void FlushFrameSink() { Call(edx_flush_frame_sink(mCtx)); }     // the context's stream waits for the pushes issued so far
     int LastStatus() const { return mStatus; }
     const char* LastError() const { return mCtx ? edx_last_error(mCtx) : "no CUDA device (edx_create failed)"; }
     edx_context* Handle() const { return mCtx; }

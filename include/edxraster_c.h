@@ -169,11 +169,22 @@ int edx_set_render_target(edx_context* ctx, void* device_color, void* device_dep
 /* Frame-parallel gather (the call site it replaces is the per-frame read-back loop of
  * RealtimeViewer/Main.cpp:71-75 run once per GPU): after every frame this context renders, the finished colour
  * and / or depth buffer (width*height RGBA8 / float32) is pushed to `remote_color` / `remote_depth` by the COPY
- * ENGINE, stream-ordered behind the frame on the context's stream (no SM time). The addresses are device pointers
+ * ENGINE, ordered behind the frame (no SM time; see edx_flush_frame_sink). The addresses are device pointers
  * this GPU can reach - its own memory, or a peer's mapped over NVLink (cudaDeviceEnablePeerAccess, or a
  * symmetric-memory mapping) - typically this rank's slot of the root GPU's frame store. NULL, NULL switches it off.
- * Single-sample only. The caller owns the protocol that tells the root a slot has landed. */
+ * Single-sample only. */
 int edx_set_frame_sink(edx_context* ctx, void* remote_color, void* remote_depth);
+/* ... and the protocol, if the caller wants one without a collective: `remote_word` (a 4-byte-aligned device address
+ * this GPU can reach, usually on the root GPU next to the frame store) receives, behind the pushes of every frame and
+ * in stream order, the number of frames this context has finished (and pushed, if a sink is set) since this call
+ * (1, 2, 3 ...; system-scope store) - the root GPU's own contexts render straight into the store (edx_set_render_target).
+ * The consumer polls the word; slot reuse is the caller's ring discipline. NULL switches it off. */
+int edx_set_frame_sink_signal(edx_context* ctx, void* remote_word);
+/* The pushes run beside the context's stream (the next frame's geometry does not wait for them; only its final pass,
+ * which overwrites the buffers, does). edx_synchronize waits for them; work that the CALLER queues on the context's
+ * stream (edx_set_stream) and that must see the pushes finished calls this first: the stream then waits for every
+ * push issued so far. No host synchronisation. */
+int edx_flush_frame_sink(edx_context* ctx);
 /* Helpers for a frame farm inside ONE process (one context per GPU; include/edxraster/Renderer.h FrameFarm). They
  * only wrap what a caller without the CUDA runtime needs around edx_set_frame_sink: */
 int edx_device_count(void);                                            /* B200 devices visible to the process */

@@ -77,7 +77,7 @@ def test_null_handles_are_rejected_not_dereferenced():
         "edx_set_capture_ids": (None, 1), "edx_read_winner_ids": (None, C.cast(buf, C.POINTER(C.c_uint32))),
         "edx_read_sample": (None, 0, buf, C.cast(buf, C.POINTER(C.c_uint32))), "edx_debug_clip_vertices": (None, None, buf),
         "edx_debug_raster_triangles": (None, None, 0, C.cast(buf, C.POINTER(C.c_int32)), buf, C.byref(n64)),
-        "edx_get_derived_state": (None, f16, buf, buf), "edx_set_render_target": (None, None, None), "edx_set_frame_sink": (None, None, None), "edx_enable_peer_access": (None, 0), "edx_device_alloc": (None, 16, C.byref(out)),
+        "edx_get_derived_state": (None, f16, buf, buf), "edx_set_render_target": (None, None, None), "edx_set_frame_sink": (None, None, None), "edx_set_frame_sink_signal": (None, None), "edx_flush_frame_sink": (None,), "edx_enable_peer_access": (None, 0), "edx_device_alloc": (None, 16, C.byref(out)),
         "edx_device_free": (None, None), "edx_read_device": (None, None, None, 0),
         "edx_set_screen_partition": (None, 0, 1), "edx_set_stream": (None, None), "edx_timer_begin": (None,),
         "edx_timer_end": (None, C.byref(ms)), "edx_set_profiling": (None, 1), "edx_get_stats": (None, C.byref(st)),

@@ -727,3 +727,40 @@ def test_idle_kernels_are_left_out_safely(skip_tile):
         assert "mid_kernel" in launches[0] and "mid_kernel" not in launches[1]       # frame 0 had no mid-size triangle
         assert "mid_kernel" not in launches[2] and "mid_kernel" in launches[3]       # frame 2 diverted some: back in frame 3
     r.close()
+
+
+def test_frame_sink_pushes_every_frame_and_counts_them():
+    # edx_set_frame_sink / edx_set_frame_sink_signal on one GPU (the store is the context's own memory; over NVLink it is a
+    # peer's): three views, each pushed into its own slot by the copy engine behind the frame; the signal word counts them
+    import copy
+    from edxraster_b200 import camera as cam, renderer as R
+    base = scenes.config1(width=320, height=200, slices=40, stacks=40)
+    r = R.Renderer(0)
+    r.Initialize(base.width, base.height)
+    r.SetPixelShader(1)
+    m = r.CreateMesh(base.vertices, base.indices)
+    fb = base.width * base.height * 4
+    store = r.DeviceAlloc(3 * 2 * fb + 16)
+    word = store + 3 * 2 * fb
+    r.SetFrameSinkSignal(word)
+    scs = []
+    for i, eye_z in enumerate((-3.0, -2.2, -1.7)):
+        c = cam.Camera((0.3 * i, 0.0, eye_z), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), base.width, base.height, 65.0, 0.01, 100.0)
+        sc = copy.copy(base)
+        sc.mv, sc.proj, sc.raster = c.view, c.proj, c.raster
+        scs.append(sc)
+        r.SetTransform(sc.mv, sc.proj, sc.raster)
+        r.SetFrameSink(store + (2 * i) * fb, store + (2 * i + 1) * fb)
+        r.RenderMesh(m)                   # not synchronised: the pushes are stream-ordered behind each frame
+    r.Synchronize()
+    assert int(r.ReadDevice(word, 4).view(np.uint32)[0]) == 3
+    for i, sc in enumerate(scs):
+        ref = parity.render_oracle(sc)
+        color = r.ReadDevice(store + (2 * i) * fb, fb).reshape(base.height, base.width, 4)
+        depth = r.ReadDevice(store + (2 * i + 1) * fb, fb).view(np.float32).reshape(base.height, base.width)
+        assert np.array_equal(depth.view(np.uint32), np.asarray(ref["depth"], dtype=np.float32).reshape(base.height, base.width).view(np.uint32)), i
+        assert np.abs(color.astype(int) - np.asarray(ref["color"]).reshape(base.height, base.width, 4).astype(int)).max() <= 1, i
+    r.SetFrameSink(0, 0)
+    r.SetFrameSinkSignal(0)
+    r.DeviceFree(store)
+    r.close()
