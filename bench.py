@@ -293,7 +293,7 @@ def reference_arm(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 OPTIONS = []
-NVLINK_INGRESS_GBS = 733.0      # one B200's NVLink receive rate as measured in round 1 (7 senders, copy engine); nominal 900
+NVLINK_INGRESS_GBS = 900.0      # NVLink 5 per direction, nominal; measured into one B200 from 7 senders (copy engine): 733 in round 1, 781 in round 2
 
 
 def time_frames(r, meshes, frames, warm):
@@ -552,7 +552,7 @@ class Farm:
         inbound = (self.world - 1) * self.frame_bytes
         floor_ms = inbound / (NVLINK_INGRESS_GBS * 1e9) * 1e3
         return {"bytes_into_rank0_per_step": inbound, "ingress_peak_gbs": NVLINK_INGRESS_GBS,
-                "peak_source": "round-1 measurement on this pool (7 senders, copy engine); NVLink 5 nominal is 900 GB/s per direction",
+                "peak_source": "NVLink 5 nominal per direction (the most measured into one B200 on this pool, 7 senders: 781 GB/s)",
                 "floor_ms_per_step": floor_ms, "achieved_gbs": inbound / (ms_step * 1e-3) / 1e9,
                 "frac": floor_ms / ms_step}
 
