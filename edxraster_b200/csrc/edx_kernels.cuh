@@ -392,7 +392,7 @@ __device__ __forceinline__ void geom_triangle(const FrameParams& P, uint32_t t)
     route_triangle(P, s, fmul(c0.z, iw0), fmul(c1.z, iw1), fmul(c2.z, iw2), iw0, iw1, iw2, t * 8u, P.smallMax);
 }
 
-__global__ void __launch_bounds__(256, 5) geom_kernel(const __grid_constant__ FrameParams P)
+__global__ void __launch_bounds__(256, 6) geom_kernel(const __grid_constant__ FrameParams P)
 {
     // Programmatic dependent launch: the grid may be scheduled while the previous kernel in the stream is
     // still draining; everything before this point touches no global memory.
