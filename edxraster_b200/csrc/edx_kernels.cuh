@@ -805,7 +805,9 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
     }
     // Work item q goes to lane q / W of warp q % W (W = warps in the grid)
     const uint32_t W = gridDim.x * (blockDim.x >> 5);
-    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // (counted from the END of the grid: the single-plane items above fill the warps from the front, and a warp that
+    // had both would run the two latency chains one after the other)
+    const uint32_t gw = W - 1u - (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
     for (uint32_t q = (threadIdx.x & 31u) * W + gw; q < nN; q += 32u * W) {
         const float4* item = reinterpret_cast<const float4*>(P.clipQueue + half + q);
         const float4 q0 = __ldg(item), q1 = __ldg(item + 1), q2 = __ldg(item + 2), q3 = __ldg(item + 3);
