@@ -658,6 +658,9 @@ __device__ __forceinline__ uint32_t vertex_source(const float* w)
     return 3;
 }
 
+#ifdef EDX_DEBUG_STATS
+__device__ unsigned long long g_clipDbg[4];      // longest per-warp cycles: single-plane loop, multi-plane loop, whole kernel body; [3] multi-plane loop until the polygons are clipped
+#endif
 // One fan triangle (0, k-1, k) of a clipped polygon: setup, shading record, routing (Clipper.h:156-170).
 // Deliberately not inlined: the clipper runs a few thousand threads, each serially; a small code
 // footprint (instruction-cache hits) matters more than call overhead there.
@@ -788,6 +791,9 @@ __device__ __noinline__ void clip_single_plane(const FrameParams& P, uint32_t t,
 __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ FrameParams P)
 {
     cudaGridDependencySynchronize();
+#ifdef EDX_DEBUG_STATS
+    const long long tc0 = clock64();
+#endif
     // The queue has two halves. Front: straddlers of exactly one plane - one instruction stream whatever the plane,
     // so they are packed 32 to a warp. Back: straddlers of several planes - long, data-dependent loops over
     // local-memory polygons - spread one per warp first so a short queue costs one item's latency, not 32.
@@ -803,55 +809,117 @@ __global__ void __launch_bounds__(128) clip_kernel(const __grid_constant__ Frame
         c2.x = q2.x; c2.y = q2.y; c2.z = q2.z; c2.w = q2.w;
         clip_single_plane(P, __float_as_uint(q3.x), c0, c1, c2, __float_as_uint(q3.y));
     }
+#ifdef EDX_DEBUG_STATS
+    const long long tc1 = clock64();
+#endif
     // Work item q goes to lane q / W of warp q % W (W = warps in the grid)
     const uint32_t W = gridDim.x * (blockDim.x >> 5);
     // (counted from the END of the grid: the single-plane items above fill the warps from the front, and a warp that
     // had both would run the two latency chains one after the other)
     const uint32_t gw = W - 1u - (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
-    for (uint32_t q = (threadIdx.x & 31u) * W + gw; q < nN; q += 32u * W) {
-        const float4* item = reinterpret_cast<const float4*>(P.clipQueue + half + q);
-        const float4 q0 = __ldg(item), q1 = __ldg(item + 1), q2 = __ldg(item + 2), q3 = __ldg(item + 3);
-        const uint32_t t = __float_as_uint(q3.x);
-        V4 c[3];
-        c[0].x = q0.x; c[0].y = q0.y; c[0].z = q0.z; c[0].w = q0.w;
-        c[1].x = q1.x; c[1].y = q1.y; c[1].z = q1.z; c[1].w = q1.w;
-        c[2].x = q2.x; c[2].y = q2.y; c[2].z = q2.z; c[2].w = q2.w;
-        const uint32_t k0 = clip_code(c[0]), k1 = clip_code(c[1]), k2 = clip_code(c[2]);
-        const uint32_t planes = (k0 ^ k1) | (k1 ^ k2) | (k2 ^ k0);           // Clipper.h:119
-
-        // General path: several planes, up to 9 vertices, polygon in local memory.
+    const uint32_t lane = threadIdx.x & 31u;
+    // Warp-uniform loop (lane 0 has the smallest q): after the per-lane clip the fan triangles of a straddler are
+    // emitted by DIFFERENT LANES when the warp holds only a few straddlers - the usual case, one per warp - because setup
+    // + routing of up to seven fan triangles one after the other was most of this path's latency, with 31 lanes idle.
+    for (uint32_t q0w = gw; q0w < nN; q0w += 32u * W) {
+        const uint32_t q = q0w + lane * W;
+        const bool has = q < nN;
         Poly a, b;
-        a.n = 3;
-        for (int k = 0; k < 3; k++) {
-            a.p[k] = c[k];
-            a.w[k][0] = k == 0 ? 1.0f : 0.0f; a.w[k][1] = k == 1 ? 1.0f : 0.0f; a.w[k][2] = k == 2 ? 1.0f : 0.0f;
-        }
         Poly* cur = &a; Poly* buf = &b;
-        const int order[6] = { LEFT_BIT, RIGHT_BIT, BOTTOM_BIT, TOP_BIT, FAR_BIT, NEAR_BIT };   // Clipper.h:237-278
-        for (int k = 0; k < 6; k++) {
-            if (planes & order[k]) { clip_by_plane(order[k], *cur, *buf); Poly* tmp = cur; cur = buf; buf = tmp; }
+        a.n = 0;
+        uint32_t t = 0, srcs = 0, slot = 0;
+        int nv = 0;
+        bool haveRecs = false;
+        V4 c[3];
+        if (has) {
+            const float4* item = reinterpret_cast<const float4*>(P.clipQueue + half + q);
+            const float4 q0 = __ldg(item), q1 = __ldg(item + 1), q2 = __ldg(item + 2), q3 = __ldg(item + 3);
+            t = __float_as_uint(q3.x);
+            c[0].x = q0.x; c[0].y = q0.y; c[0].z = q0.z; c[0].w = q0.w;
+            c[1].x = q1.x; c[1].y = q1.y; c[1].z = q1.z; c[1].w = q1.w;
+            c[2].x = q2.x; c[2].y = q2.y; c[2].z = q2.z; c[2].w = q2.w;
+            const uint32_t k0 = clip_code(c[0]), k1 = clip_code(c[1]), k2 = clip_code(c[2]);
+            const uint32_t planes = (k0 ^ k1) | (k1 ^ k2) | (k2 ^ k0);           // Clipper.h:119
+
+            // General path: several planes, up to 9 vertices, polygon in local memory.
+            a.n = 3;
+            for (int k = 0; k < 3; k++) {
+                a.p[k] = c[k];
+                a.w[k][0] = k == 0 ? 1.0f : 0.0f; a.w[k][1] = k == 1 ? 1.0f : 0.0f; a.w[k][2] = k == 2 ? 1.0f : 0.0f;
+            }
+            const int order[6] = { LEFT_BIT, RIGHT_BIT, BOTTOM_BIT, TOP_BIT, FAR_BIT, NEAR_BIT };   // Clipper.h:237-278
+            for (int k = 0; k < 6; k++) {
+                if (planes & order[k]) { clip_by_plane(order[k], *cur, *buf); Poly* tmp = cur; cur = buf; buf = tmp; }
+            }
+            nv = cur->n;
+            for (int k = 0; k < cur->n; k++)
+                if (cur->p[k].w <= 0.0f) nv = 0;                           // Clipper.h:280-287
+            if (nv < 3) nv = 0;
+            for (int k = 0; k < nv; k++) {
+                const uint32_t src = vertex_source(cur->w[k]);
+                if (src < 3) cur->p[k] = pick3(c, src);
+                srcs |= src << (2 * k);
+            }
+            if (nv) {
+                const uint32_t nFan = (uint32_t)(nv - 2);
+                slot = atomicAdd(&P.counters->nClipRecs, nFan);
+                haveRecs = slot + nFan <= P.clipRecCap;
+                if (haveRecs) P.clipSlot[t] = slot;
+            }
         }
-        int nv = cur->n;
-        for (int k = 0; k < cur->n; k++)
-            if (cur->p[k].w <= 0.0f) nv = 0;                           // Clipper.h:280-287
-        if (nv < 3) continue;
-        uint32_t srcs = 0;
-        for (int k = 0; k < nv; k++) {
-            const uint32_t src = vertex_source(cur->w[k]);
-            if (src < 3) cur->p[k] = pick3(c, src);
-            srcs |= src << (2 * k);
+#ifdef EDX_DEBUG_STATS
+        if (lane == 0) atomicMax(&g_clipDbg[3], (unsigned long long)(clock64() - tc1));      // multi-plane: until the polygons are clipped (first iteration)
+#endif
+        const uint32_t act = __ballot_sync(0xFFFFFFFFu, nv != 0);
+        if (__popc(act) > 4) {
+            // a long queue: every lane has its own straddler, the lanes already run in parallel
+            if (nv) {
+                const V4 f0 = cur->p[0];
+                const float iwA = inv_w(f0.w), zA = fmul(f0.z, iwA);
+                for (int k = 2; k < nv; k++) {                                  // Clipper.h:156-170 fan (0, k-1, k)
+                    const uint32_t sb = (srcs & 3u) | (((srcs >> (2 * (k - 1))) & 3u) << 2) | (((srcs >> (2 * k)) & 3u) << 4);
+                    emit_fan(P, t, k - 2, slot, haveRecs, f0, cur->p[k - 1], cur->p[k], iwA, zA, sb, cur->w[0], cur->w[k - 1], cur->w[k]);
+                }
+            }
+            continue;
         }
-        const uint32_t nFan = (uint32_t)(nv - 2);
-        const uint32_t slot = atomicAdd(&P.counters->nClipRecs, nFan);
-        const bool haveRecs = slot + nFan <= P.clipRecCap;
-        if (haveRecs) P.clipSlot[t] = slot;
-        const V4 f0 = cur->p[0];
-        const float iwA = inv_w(f0.w), zA = fmul(f0.z, iwA);
-        for (int k = 2; k < nv; k++) {                                  // Clipper.h:156-170 fan (0, k-1, k)
-            const uint32_t sb = (srcs & 3u) | (((srcs >> (2 * (k - 1))) & 3u) << 2) | (((srcs >> (2 * k)) & 3u) << 4);
-            emit_fan(P, t, k - 2, slot, haveRecs, f0, cur->p[k - 1], cur->p[k], iwA, zA, sb, cur->w[0], cur->w[k - 1], cur->w[k]);
+        for (uint32_t rest = act; rest; rest &= rest - 1u) {
+            const int src = __ffs(rest) - 1;
+            const int nvS = __shfl_sync(0xFFFFFFFFu, nv, src);
+            const uint32_t tS = __shfl_sync(0xFFFFFFFFu, t, src), slotS = __shfl_sync(0xFFFFFFFFu, slot, src), srcsS = __shfl_sync(0xFFFFFFFFu, srcs, src);
+            const bool recsS = __shfl_sync(0xFFFFFFFFu, haveRecs ? 1 : 0, src) != 0;
+            // lane k takes fan triangle (0, k + 1, k + 2): the owner broadcasts its vertices one by one
+            V4 f0, fa, fb; float w0[3], wa[3], wb[3];
+            f0.x = f0.y = f0.z = f0.w = 0.0f; fa = f0; fb = f0;
+            #pragma unroll
+            for (int m = 0; m < 3; m++) { w0[m] = 0.0f; wa[m] = 0.0f; wb[m] = 0.0f; }
+            for (int j = 0; j < nvS; j++) {
+                const int jj = min(j, 8);
+                V4 v; float w[3];
+                v.x = __shfl_sync(0xFFFFFFFFu, cur->p[jj].x, src); v.y = __shfl_sync(0xFFFFFFFFu, cur->p[jj].y, src);
+                v.z = __shfl_sync(0xFFFFFFFFu, cur->p[jj].z, src); v.w = __shfl_sync(0xFFFFFFFFu, cur->p[jj].w, src);
+                #pragma unroll
+                for (int m = 0; m < 3; m++) w[m] = __shfl_sync(0xFFFFFFFFu, cur->w[jj][m], src);
+                if (j == 0) { f0 = v; for (int m = 0; m < 3; m++) w0[m] = w[m]; }
+                if (j == (int)lane + 1) { fa = v; for (int m = 0; m < 3; m++) wa[m] = w[m]; }
+                if (j == (int)lane + 2) { fb = v; for (int m = 0; m < 3; m++) wb[m] = w[m]; }
+            }
+            if ((int)lane + 2 < nvS) {
+                const int k = (int)lane + 2;
+                const float iwA = inv_w(f0.w), zA = fmul(f0.z, iwA);
+                const uint32_t sb = (srcsS & 3u) | (((srcsS >> (2 * (k - 1))) & 3u) << 2) | (((srcsS >> (2 * k)) & 3u) << 4);
+                emit_fan(P, tS, k - 2, slotS, recsS, f0, fa, fb, iwA, zA, sb, w0, wa, wb);
+            }
+            __syncwarp();
         }
     }
+#ifdef EDX_DEBUG_STATS
+    if ((threadIdx.x & 31u) == 0) {
+        const long long tc2 = clock64();
+        atomicMax(&g_clipDbg[0], (unsigned long long)(tc1 - tc0)); atomicMax(&g_clipDbg[1], (unsigned long long)(tc2 - tc1));
+        atomicMax(&g_clipDbg[2], (unsigned long long)(tc2 - tc0));
+    }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -547,6 +547,14 @@ int finish_frame(edx_context* c)
                 cudaMemcpyToSymbol(g_tileResident, h, sizeof(h));
             }
         }
+        if (getenv("EDX_DEBUG_PRINT")) {
+            unsigned long long cd[4];
+            if (cudaMemcpyFromSymbol(cd, g_clipDbg, sizeof(cd)) == cudaSuccess) {
+                fprintf(stderr, "[edx dbg] clip_kernel, longest warp (cycles): single-plane loop %llu, multi-plane loop %llu (of it, until the polygons are clipped: %llu), body %llu\n", cd[0], cd[1], cd[3], cd[2]);
+                memset(cd, 0, sizeof(cd));
+                cudaMemcpyToSymbol(g_clipDbg, cd, sizeof(cd));
+            }
+        }
         if (getenv("EDX_DEBUG_PRINT") && k.dbg[6]) {
             static unsigned long long hb[8192][10];
             if (cudaMemcpyFromSymbol(hb, g_binDbg, sizeof(hb)) == cudaSuccess) {
