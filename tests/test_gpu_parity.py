@@ -96,6 +96,23 @@ def test_msaa_every_sample_bit_exact(name, level):
     assert_parity(sc, msaa=level, shader=shader, stages=False)
 
 
+@pytest.mark.parametrize("name,level", [("C3", 2), ("C4", 1), ("C1", 3)])
+def test_msaa_with_per_bin_lists_and_without_the_mid_path(name, level):
+    # the per-bin lists (stage a7) are shared by the sample CTAs of a bin; forced here on short lists, with every
+    # non-small triangle on the tile path, and in a second frame of the same mesh (hints from the first frame apply)
+    from edxraster_b200 import renderer as R
+    sc = MSAA_SCENES[name]()
+    shader = 1 if sc.shader == 0 else sc.shader
+    ref = parity.render_oracle(sc, msaa=level, shader=shader)
+    r = R.Renderer(0)
+    for _ in range(2):
+        got = parity.render_gpu(sc, msaa=level, shader=shader, stages=False, renderer=r, options={"bin_min": -1, "mid_max": 0})
+        rep = parity.compare(ref, got)
+        assert parity.is_parity(rep), rep
+    assert got["stats"]["bin_pairs"] > 0
+    r.close()
+
+
 def test_msaa_32x_and_mode_switches():
     from edxraster_b200 import renderer as R
     sc = scenes.config1(width=320, height=200, slices=40, stacks=40)
