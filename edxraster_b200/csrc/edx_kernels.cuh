@@ -1450,7 +1450,10 @@ __device__ __forceinline__ void owner_from_smem(OwnerSetup& o, const uint32_t* d
     }
 }
 
-template <bool TEX>
+// FROM_KEYS: the frame has no tile_kernel (nothing on the tile path; skip_tile): the pass reads the visibility keys
+// itself - depth out, key reset, owner from the key - instead of the ids a resolve kernel would have written for it:
+// one kernel and one 4-byte round trip per pixel less in frames of small triangles.
+template <bool TEX, bool FROM_KEYS>
 __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ FrameParams P)
 {
     constexpr int OWN_WORDS = TEX ? 37 : 31;                       // odd strides: distinct slots fall into distinct banks
@@ -1467,7 +1470,16 @@ __global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ Fram
     if (!owns_pixel(tx0, ty0, P.binsX, P.part, P.parts)) return;           // (the whole CTA: a tile lies inside one bin)
     const bool inside = px < P.width && py < P.height;
     const size_t at = inside ? (size_t)px + (size_t)P.width * (size_t)(P.height - 1 - py) : 0;
-    const uint32_t prim = inside ? __ldg(P.ids + at) : 0xFFFFFFFFu;
+    uint32_t prim = 0xFFFFFFFFu;
+    if (FROM_KEYS) {
+        if (inside) {
+            unsigned long long* kp = P.keys + key_index(px, py, P.binsX);
+            const unsigned long long key = *kp;
+            if (key != KEY_EMPTY) { *kp = KEY_EMPTY; prim = key_prim(key); }
+            P.depth[at] = key != KEY_EMPTY ? key_depth(key) : 1.0f;              // clear value, FrameBuffer.cpp:103
+            if (P.captureIds) P.ids[at] = prim;
+        }
+    } else if (inside) prim = __ldg(P.ids + at);
     const bool hit = prim != 0xFFFFFFFFu;
     const uint32_t group = __match_any_sync(0xFFFFFFFFu, prim);
     const int leader = __ffs(group) - 1;

@@ -366,13 +366,19 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     }
     const dim3 leanGrid((c->binsX * c->binsY * 16 + 7) / 8);
     if (c->msaaLog2 == 0) {
-        if (lean && !shaded && !c->captureIds) add("lean_resolve_kernel", lean_resolve_kernel<true>, leanGrid, dim3(256), 0, 1, 2);
+        // (a shaded frame without tile_kernel needs no resolve kernel either: shade_kernel<., true> reads the keys itself)
+        const bool fusedShade = shaded && !launchTile;
+        if (fusedShade) { }
+        else if (lean && !shaded && !c->captureIds) add("lean_resolve_kernel", lean_resolve_kernel<true>, leanGrid, dim3(256), 0, 1, 2);
         else if (lean) add("lean_resolve_kernel", lean_resolve_kernel<false>, leanGrid, dim3(256), 0, 1, 2);
         if (launchTile) add("tile_kernel", tile_kernel<false>, dim3(c->binsX * c->binsY), dim3(TILE_THREADS), sizeof(TileShared), 1, 2);
         if (shaded) {
             const uint32_t tiles = ((c->width + TILE_PX - 1) / TILE_PX) * ((c->height + TILE_PX - 1) / TILE_PX);   // one CTA each
-            if (textured) add("shade_kernel", shade_kernel<true>, dim3(tiles), dim3(256), 0, 0, 2);
-            else add("shade_kernel", shade_kernel<false>, dim3(tiles), dim3(256), 0, 0, 2);
+            if (fusedShade) {
+                if (textured) add("shade_kernel", shade_kernel<true, true>, dim3(tiles), dim3(256), 0, 0, 2);
+                else add("shade_kernel", shade_kernel<false, true>, dim3(tiles), dim3(256), 0, 0, 2);
+            } else if (textured) add("shade_kernel", shade_kernel<true, false>, dim3(tiles), dim3(256), 0, 0, 2);
+            else add("shade_kernel", shade_kernel<false, false>, dim3(tiles), dim3(256), 0, 0, 2);
         }
     } else {
         // one CTA per (bin, sample), then the per-pixel resolve that also ends the frame

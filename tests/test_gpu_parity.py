@@ -735,9 +735,11 @@ def test_idle_kernels_are_left_out_safely(skip_tile):
         assert parity.is_parity(rep), (eye_z, rep)
     if skip_tile:
         assert "tile_kernel" in launches[0] and "mid_kernel" in launches[0]
-        # frame 0 put nothing on the tile path: frames 1 and 2 end in lean_resolve_kernel, with mid_kernel as the catch-all
+        # frame 0 put nothing on the tile path: frames 1 and 2 have no tile_kernel (a shaded frame then needs no resolve kernel
+        # either: shade_kernel reads the keys itself), with mid_kernel as the catch-all
         for i in (1, 2):
-            assert "tile_kernel" not in launches[i] and "lean_resolve_kernel" in launches[i] and "mid_kernel" in launches[i], launches[i]
+            assert "tile_kernel" not in launches[i] and "lean_resolve_kernel" not in launches[i], launches[i]
+            assert "shade_kernel" in launches[i] and "mid_kernel" in launches[i], launches[i]
         # frame 2 (close up) had large triangles: the tile kernel is back, and they are on its path
         assert "tile_kernel" in launches[3] and "tile_kernel" in launches[4] and stats[3]["binned_tris"] > 0
     else:
