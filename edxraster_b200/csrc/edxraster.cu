@@ -356,7 +356,14 @@ int enqueue_frame(edx_context* c, const edx_mesh* m, DumpRec* dumpBuf, uint32_t 
     if (m->nTris) add("clip_kernel", clip_kernel, dim3(148 * 4), dim3(128), 0, 0, 1);
     // one warp per mid-size triangle: as many warps as the chip holds (148 SMs x 16 CTAs x 4 warps) so that a queue of
     // tens of thousands is a couple of triangles per warp, not a serial walk whose every step waits on a record load
-    if (m->nTris && launchMid) add("mid_kernel", mid_kernel, dim3(148 * (unsigned)c->midCtasPerSm), dim3(128), 0, 0, 1);
+    // (when it is only the catch-all of a frame without tile_kernel - the previous frame had nothing for it - one CTA per
+    // SM will do: the grid-stride loop is correct at any grid size, and 2,368 CTAs that read a counter and exit cost 1-2 us)
+    bool midIdle = false;
+    if (launchMid && !launchTile && c->skipIdle && c->hostCounters->frameSerial != 0) {
+        const volatile Counters* h = c->hostCounters;
+        midIdle = h->nMid == 0 && h->nMidDiverted == 0 && h->nBigDiverted == 0;
+    }
+    if (m->nTris && launchMid) add("mid_kernel", mid_kernel, dim3(148 * (midIdle ? 1u : (unsigned)c->midCtasPerSm)), dim3(128), 0, 0, 1);
     if (m->nTris && launchSort) add("sort_big_kernel", sort_big_kernel, dim3(1), dim3(1024), 0, 0, 1);
     if (launchBin) {
         add("bin_keys_kernel", bin_keys_kernel, dim3(148 * 4), dim3(256), 0, 0, 1);
